@@ -1,0 +1,158 @@
+/*
+ * sobfu_b200.h -- C ABI of the Blackwell-native SobolevFusion solver hot path (libsobfu_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * The header-compatible C++ shim in include/sobfu/ and include/kfusion/ (same class names and signatures as
+ * dgrzech/sobfu) forwards to these entry points; sobfu_b200/ (Python, ctypes) binds the same symbols for the
+ * parity tests and bench.py.  Each entry point cites the reference interface (file:line in dgrzech/sobfu)
+ * it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative SOBFU_B200_E* code otherwise; the message of the
+ *     last failure on the calling thread is available from sobfu_b200_last_error().  (The reference prints
+ *     and exit(0)s on any CUDA error, src/kfusion/device_memory.cpp:7-10; the C++ shim keeps that behaviour.)
+ *   - pointers are DEVICE pointers on the current CUDA device unless the name ends in _host
+ *   - layouts are the reference's: a volume of dims (X,Y,Z) is row-major with x fastest,
+ *     idx = x + X*(y + Y*z) (test/deformation_field_test.cpp:102-104);
+ *     TSDF voxels are float2 {tsdf, weight} (include/kfusion/internal.hpp:59-78);
+ *     vector fields are float4 {x,y,z,0} and psi stores ABSOLUTE voxel coordinates
+ *     (src/sobfu/cuda/vector_fields.cu:72-78); a Jacobian voxel is Mat4f = 4 x float4, rows 0..2 used
+ *     (include/kfusion/internal.hpp:12-14)
+ *   - work is issued on the stream set by sobfu_b200_set_stream (default: the legacy default stream, as in the
+ *     reference) and every call is complete when it returns, like the reference's
+ *   - one thread at a time per solver handle
+ */
+#ifndef SOBFU_B200_H
+#define SOBFU_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOBFU_B200_OK 0
+#define SOBFU_B200_EINVAL (-1)   /* bad argument (e.g. unsupported (s, lambda), see below) */
+#define SOBFU_B200_ECUDA (-2)    /* a CUDA runtime/driver call failed */
+#define SOBFU_B200_ENOMEM (-3)
+#define SOBFU_B200_ECOMM (-4)    /* NCCL / peer-access failure */
+
+typedef struct sobfu_b200_solver sobfu_b200_solver; /* opaque */
+
+/* mirrors Params / SolverParams (include/sobfu/params.hpp:7-38, include/sobfu/solver.hpp:16-19) */
+typedef struct {
+    int   dims[3];        /* volume_dims */
+    float voxel_size[3];  /* Params::voxel_sizes() */
+    float trunc_dist, eta, max_weight;
+    int   verbosity;      /* 0 silent, 1 log at iter 1, %50, last (solver.cu:132), 2 every iteration */
+    int   max_iter;
+    int   s;              /* Sobolev filter length; only 7 is valid (KERNEL_RADIUS 3, solver.cu:211) */
+    float max_update_norm;
+    float lambda;         /* one of .05 .1 .2 .4 (solver.cpp:160-262); anything else -> SOBFU_B200_EINVAL */
+    float alpha, w_reg;
+} sobfu_b200_params;
+
+typedef struct {
+    int   iters;          /* iterations executed */
+    int   converged;      /* 1 if max update norm <= max_update_norm stopped the loop (solver.cu:183) */
+    float max_norm;       /* max update norm of the last executed iteration (Reductor::max_update_norm) */
+    float max_idx_f;      /* its voxel index as the reference reports it: a float (reductor.cu:367) */
+    long long max_idx;    /* the same voxel index, exact */
+    float loop_ms;        /* device time of the gradient-descent loop (CUDA events on the solver stream) */
+    float total_ms;       /* device time of the whole call incl. psi^-1 and the final warps */
+    int   launches;       /* kernels launched by this call */
+} sobfu_b200_solve_info;
+
+/* per-iteration record; energies are only filled on logging iterations (else 0) */
+typedef struct {
+    float max_norm, max_idx_f, e_data, e_reg;
+} sobfu_b200_iter_log;
+
+const char *sobfu_b200_last_error(void);
+const char *sobfu_b200_version(void);
+/* stream used by the free functions and as the caller-visible stream of solver calls (cudaStream_t) */
+int sobfu_b200_set_stream(void *cuda_stream);
+
+/* ---- solver: sobfu::cuda::Solver (include/sobfu/solver.hpp:56-67, src/sobfu/solver.cpp:7-101) ---- */
+int sobfu_b200_solver_create(sobfu_b200_solver **out, const sobfu_b200_params *p);
+int sobfu_b200_solver_destroy(sobfu_b200_solver *s);
+/* Solver::estimate_psi -> device::estimate_psi (src/sobfu/cuda/solver.cu:85-205).
+ * reads phi_global, phi_n; overwrites phi_n_psi, phi_global_psi_inv, psi (warm start, in place) and psi_inv */
+int sobfu_b200_solver_estimate_psi(sobfu_b200_solver *s, const void *phi_global, void *phi_global_psi_inv,
+                                   const void *phi_n, void *phi_n_psi, void *psi, void *psi_inv,
+                                   sobfu_b200_solve_info *info);
+/* same call with HOST buffers: H2D of phi_global, phi_n, psi and D2H of phi_n_psi, phi_global_psi_inv, psi,
+ * psi_inv happen inside (pinned staging owned by the handle).  Any output pointer may be NULL to skip its D2H. */
+int sobfu_b200_solver_estimate_psi_host(sobfu_b200_solver *s, const void *phi_global_host,
+                                        void *phi_global_psi_inv_host, const void *phi_n_host, void *phi_n_psi_host,
+                                        void *psi_host, void *psi_inv_host, sobfu_b200_solve_info *info);
+/* copies min(n, iters) records of the last solve */
+int sobfu_b200_solver_get_log(sobfu_b200_solver *s, sobfu_b200_iter_log *out, int n);
+/* the 7 normalised taps (decompose_sobolev_filter, src/sobfu/solver.cpp:160-262) */
+int sobfu_b200_solver_get_taps(sobfu_b200_solver *s, float *taps7);
+/* bytes of device scratch owned by the handle */
+size_t sobfu_b200_solver_workspace_bytes(sobfu_b200_solver *s);
+/* kernel variant: 0 = auto (fastest applicable), 1 = generic per-voxel kernels, 2 = tiled/TMA kernels */
+int sobfu_b200_solver_set_variant(sobfu_b200_solver *s, int variant);
+/* benchmarking aid: run `iters` gradient-descent iterations on the state left by the last estimate_psi
+ * without convergence checks; returns device ms of pass A, pass B and the whole loop */
+int sobfu_b200_solver_time_loop(sobfu_b200_solver *s, int iters, float *ms_pass_a, float *ms_pass_b, float *ms_loop);
+
+int sobfu_b200_sobolev_taps(int s, float lambda, float *taps); /* solver.cpp:160-262 */
+
+/* ---- deformation field: sobfu::cuda::DeformationField (include/sobfu/vector_fields.hpp:52-66) ---- */
+int sobfu_b200_init_identity(void *psi, int X, int Y, int Z);                       /* vector_fields.cu:56-79 */
+int sobfu_b200_apply(const void *phi, void *phi_warped, const void *psi, int X, int Y, int Z); /* :81-109 */
+int sobfu_b200_estimate_inverse(const void *psi, void *psi_inv, int X, int Y, int Z, int iters); /* :111-138 (48) */
+int sobfu_b200_clear_field(void *field4, int X, int Y, int Z);                      /* vector_fields.cu:28-50 */
+
+/* ---- differentiators used directly by the reference's gtest harness ---- */
+int sobfu_b200_tsdf_gradient(const void *phi, void *grad4, int X, int Y, int Z);    /* vector_fields.cu:149-208 */
+int sobfu_b200_laplacian(const void *psi, void *L4, int X, int Y, int Z);           /* vector_fields.cu:278-337 */
+int sobfu_b200_jacobian(const void *psi, void *J_mat4f, int X, int Y, int Z, int mode); /* :389-472 */
+int sobfu_b200_potential_gradient(const void *phi_n_psi, const void *phi_global, const void *grad4, const void *L4,
+                                  void *nabla_U4, float w_reg, int X, int Y, int Z);   /* solver.cu:15-47 */
+int sobfu_b200_sobolev_filter(void *dst4, const void *src4, const float *taps7_host, int X, int Y, int Z); /* solver.cu:237-459 */
+int sobfu_b200_update_psi(void *psi, const void *nabla_U_S4, void *updates4, float alpha, int X, int Y, int Z); /* solver.cu:53-79 */
+
+/* ---- Reductor (include/sobfu/reductor.hpp:24-50, src/sobfu/reductor.cpp:38-57) ---- */
+int sobfu_b200_data_energy(const void *phi_global, const void *phi_n, int N, float *out);      /* reductor.cu:11-112 */
+int sobfu_b200_reg_energy(const void *J_mat4f, int N, float *out);                              /* reductor.cu:114-214 */
+int sobfu_b200_max_update_norm(const void *updates4, int N, float *value, float *index_f, long long *index); /* :342-456 */
+
+/* ---- TSDF volume: kfusion::cuda::TsdfVolume (include/kfusion/cuda/tsdf_volume.hpp:17-92) ---- */
+int sobfu_b200_tsdf_clear(void *vol, int X, int Y, int Z);                          /* tsdf_volume.cu:23-46 */
+int sobfu_b200_tsdf_init_sphere(void *vol, int X, int Y, int Z, const float *voxel_size3, float trunc_dist,
+                                float eta, const float *centre3, float radius);     /* tsdf_volume.cu:249-275 */
+int sobfu_b200_tsdf_fuse(void *phi_global, const void *phi_n_psi, int X, int Y, int Z, float max_weight); /* :103-130 */
+/* vol2cam: R (row-major 3x3) and t; dists: float image with row pitch in bytes (tsdf_volume.cu:62-101,141-162) */
+int sobfu_b200_tsdf_integrate(const void *dists, size_t pitch_bytes, int cols, int rows, void *vol, int X, int Y,
+                              int Z, const float *voxel_size3, float trunc_dist, float eta, const float *R9,
+                              const float *t3, float fx, float fy, float cx, float cy);
+
+/* ---- depth pre-processing (include/kfusion/cuda/imgproc.hpp:11-23) ---- */
+int sobfu_b200_depth_bilateral(const void *src_u16, size_t src_pitch, void *dst_u16, size_t dst_pitch, int cols,
+                               int rows, int ksz, float sigma_spatial, float sigma_depth);  /* imgproc.cu:8-53 */
+int sobfu_b200_depth_truncate(void *depth_u16, size_t pitch, int cols, int rows, float max_dist); /* imgproc.cu:60-77 */
+int sobfu_b200_compute_dists(const void *depth_u16, size_t depth_pitch, void *dists_f32, size_t dists_pitch, int cols,
+                             int rows, float fx, float fy, float cx, float cy);               /* imgproc.cu:233-254 */
+
+/* ---- marching cubes: kfusion::cuda::MarchingCubes::run (include/kfusion/cuda/marching_cubes.hpp:19-56) ----
+ * verts/normals: float4 per vertex (pose*v with y,z negated, w=1: marching_cubes.cu:273-276); output is ordered by
+ * voxel index (deterministic, unlike the reference's atomics order).  occupied_* (optional, may be NULL) receive the
+ * compacted voxel ids / cube indices / vertex counts.  *n_vertices and *n_voxels are HOST outputs. */
+int sobfu_b200_marching_cubes(const void *vol, int X, int Y, int Z, const float *volume_size3, const float *R9,
+                              const float *t3, void *verts4, void *normals4, int vertex_cap, int *n_vertices,
+                              int *occupied_voxel, int *occupied_cube, int *occupied_nverts, int voxel_cap,
+                              int *n_voxels);
+
+/* ---- multi-GPU (z-slab partition): one process per GPU ----
+ * rank 0 obtains an id, the launcher broadcasts it (torch.distributed), every rank attaches. */
+#define SOBFU_B200_COMM_ID_BYTES 128
+int sobfu_b200_comm_unique_id(void *id128_host);
+int sobfu_b200_solver_attach_comm(sobfu_b200_solver *s, const void *id128_host, int rank, int nranks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOBFU_B200_H */

@@ -21,6 +21,13 @@ void orc_set_ftz(void) {
     _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON);
     _MM_SET_DENORMALS_ZERO_MODE(_MM_DENORMALS_ZERO_ON);
 }
+/* every parallel region switches FTZ+DAZ on for its threads and restores the caller's MXCSR afterwards, so that
+ * loading the oracle into a Python process does not change NumPy's arithmetic */
+static inline unsigned orc_ftz_on(void) {
+    const unsigned old = _mm_getcsr();
+    _mm_setcsr(old | 0x8040u); /* FTZ (bit 15) | DAZ (bit 6) */
+    return old;
+}
 
 /* __fsqrt_rd (utils.hpp:279-281): largest float r with r*r <= x */
 float orc_sqrt_rd(float x) {
@@ -103,7 +110,7 @@ static inline orc_f2 interp_tsdf(const orc_f2 *vol, float px, float py, float pz
 void orc_apply(const orc_f2 *phi, orc_f2 *out, const orc_f4 *psi, int X, int Y, int Z) {
 #pragma omp parallel
     {
-        orc_set_ftz();
+        const unsigned csr__ = orc_ftz_on();
 #pragma omp for
         for (int z = 0; z < Z; ++z)
             for (int y = 0; y < Y; ++y)
@@ -111,6 +118,7 @@ void orc_apply(const orc_f2 *phi, orc_f2 *out, const orc_f4 *psi, int X, int Y, 
                     orc_f4 p = psi[IDX(x, y, z)];
                     out[IDX(x, y, z)] = interp_tsdf(phi, p.x, p.y, p.z, X, Y, Z);
                 }
+        _mm_setcsr(csr__);
     }
 }
 
@@ -118,7 +126,7 @@ void orc_apply(const orc_f2 *phi, orc_f2 *out, const orc_f4 *psi, int X, int Y, 
 void orc_tsdf_gradient(const orc_f2 *phi, orc_f4 *grad, int X, int Y, int Z) {
 #pragma omp parallel
     {
-        orc_set_ftz();
+        const unsigned csr__ = orc_ftz_on();
 #pragma omp for
         for (int z = 0; z < Z; ++z)
             for (int y = 0; y < Y; ++y)
@@ -134,6 +142,7 @@ void orc_tsdf_gradient(const orc_f2 *phi, orc_f4 *grad, int X, int Y, int Z) {
                     n.w = 0.f;
                     grad[IDX(x, y, z)] = n;
                 }
+        _mm_setcsr(csr__);
     }
 }
 
@@ -141,7 +150,7 @@ void orc_tsdf_gradient(const orc_f2 *phi, orc_f4 *grad, int X, int Y, int Z) {
 void orc_laplacian(const orc_f4 *psi, orc_f4 *L, int X, int Y, int Z) {
 #pragma omp parallel
     {
-        orc_set_ftz();
+        const unsigned csr__ = orc_ftz_on();
 #pragma omp for
         for (int z = 0; z < Z; ++z)
             for (int y = 0; y < Y; ++y)
@@ -162,6 +171,7 @@ void orc_laplacian(const orc_f4 *psi, orc_f4 *L, int X, int Y, int Z) {
                     r.w = 0.f;
                     L[IDX(x, y, z)] = r;
                 }
+        _mm_setcsr(csr__);
     }
 }
 
@@ -169,7 +179,7 @@ void orc_laplacian(const orc_f4 *psi, orc_f4 *L, int X, int Y, int Z) {
 void orc_jacobian(const orc_f4 *psi, float *J, int X, int Y, int Z, int mode) {
 #pragma omp parallel
     {
-        orc_set_ftz();
+        const unsigned csr__ = orc_ftz_on();
 #pragma omp for
         for (int z = 0; z < Z; ++z)
             for (int y = 0; y < Y; ++y)
@@ -201,6 +211,7 @@ void orc_jacobian(const orc_f4 *psi, float *J, int X, int Y, int Z, int mode) {
                         o[4 * r + 0] = Jx[r]; o[4 * r + 1] = Jy[r]; o[4 * r + 2] = Jz[r]; o[4 * r + 3] = 0.f;
                     }
                 }
+        _mm_setcsr(csr__);
     }
 }
 
@@ -209,7 +220,7 @@ void orc_potential_gradient(const orc_f2 *phi_n_psi, const orc_f2 *phi_global, c
                             const orc_f4 *L, orc_f4 *nabla_U, float w_reg, int N) {
 #pragma omp parallel
     {
-        orc_set_ftz();
+        const unsigned csr__ = orc_ftz_on();
 #pragma omp for
         for (int i = 0; i < N; ++i) {
             float d = phi_n_psi[i].x - phi_global[i].x;
@@ -220,6 +231,7 @@ void orc_potential_gradient(const orc_f2 *phi_n_psi, const orc_f2 *phi_global, c
             r.w = 0.f;
             nabla_U[i] = r;
         }
+        _mm_setcsr(csr__);
     }
 }
 
@@ -230,7 +242,7 @@ static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ?
 void orc_sobolev_filter(orc_f4 *dst, const orc_f4 *src, const float *S, int X, int Y, int Z) {
 #pragma omp parallel
     {
-        orc_set_ftz();
+        const unsigned csr__ = orc_ftz_on();
 #pragma omp for
         for (int z = 0; z < Z; ++z)
             for (int y = 0; y < Y; ++y)
@@ -252,6 +264,7 @@ void orc_sobolev_filter(orc_f4 *dst, const orc_f4 *src, const float *S, int X, i
                     r.w = 0.f;
                     dst[IDX(x, y, z)] = r;
                 }
+        _mm_setcsr(csr__);
     }
 }
 
@@ -259,13 +272,14 @@ void orc_sobolev_filter(orc_f4 *dst, const orc_f4 *src, const float *S, int X, i
 void orc_update_psi(orc_f4 *psi, const orc_f4 *g, orc_f4 *updates, float alpha, int N) {
 #pragma omp parallel
     {
-        orc_set_ftz();
+        const unsigned csr__ = orc_ftz_on();
 #pragma omp for
         for (int i = 0; i < N; ++i) {
             orc_f4 u = {g[i].x * alpha, g[i].y * alpha, g[i].z * alpha, 0.f};
             updates[i] = u;
             psi[i].x -= u.x; psi[i].y -= u.y; psi[i].z -= u.z;
         }
+        _mm_setcsr(csr__);
     }
 }
 
@@ -290,7 +304,7 @@ void orc_max_update_norm(const orc_f4 *updates, int N, float *value, float *inde
     unsigned n = (unsigned)N, bs = (unsigned)threads, gridSize = bs * 2 * (unsigned)blocks;
 #pragma omp parallel
     {
-        orc_set_ftz();
+        const unsigned csr__ = orc_ftz_on();
         float *sv = (float *)malloc(sizeof(float) * bs), *si = (float *)malloc(sizeof(float) * bs);
 #pragma omp for
         for (int b = 0; b < blocks; ++b) {
@@ -314,6 +328,7 @@ void orc_max_update_norm(const orc_f4 *updates, int N, float *value, float *inde
             bv[b] = sv[0]; bi[b] = si[0];
         }
         free(sv); free(si);
+        _mm_setcsr(csr__);
     }
     float rv = 0.f, ri = 0.f;
     for (int b = 0; b < blocks; ++b)
@@ -348,7 +363,7 @@ float orc_data_energy(const orc_f2 *pg, const orc_f2 *pn, int N) {
     float *out = (float *)malloc(sizeof(float) * blocks);
 #pragma omp parallel
     {
-        orc_set_ftz();
+        const unsigned csr__ = orc_ftz_on();
         float *sd = (float *)calloc(bs < 64 ? 64 : bs, sizeof(float));
 #pragma omp for
         for (int b = 0; b < blocks; ++b) {
@@ -369,6 +384,7 @@ float orc_data_energy(const orc_f2 *pg, const orc_f2 *pn, int N) {
             out[b] = block_tree(sd, bs);
         }
         free(sd);
+        _mm_setcsr(csr__);
     }
     float r = 0.f;
     for (int b = 0; b < blocks; ++b) r += out[b]; /* reductor.cpp:68-79 */
@@ -385,7 +401,7 @@ float orc_reg_energy(const float *J, int N) {
 #define NSQ(p) (((p)[0] * (p)[0] + (p)[1] * (p)[1]) + (p)[2] * (p)[2])
 #pragma omp parallel
     {
-        orc_set_ftz();
+        const unsigned csr__ = orc_ftz_on();
         float *sd = (float *)calloc(bs < 64 ? 64 : bs, sizeof(float));
 #pragma omp for
         for (int b = 0; b < blocks; ++b) {
@@ -406,6 +422,7 @@ float orc_reg_energy(const float *J, int N) {
             out[b] = block_tree(sd, bs);
         }
         free(sd);
+        _mm_setcsr(csr__);
     }
 #undef NSQ
     float r = 0.f;
@@ -445,7 +462,7 @@ static inline void interp_disp(const orc_f4 *psi, float px, float py, float pz, 
 void orc_estimate_inverse(const orc_f4 *psi, orc_f4 *psi_inv, int X, int Y, int Z, int iters) {
 #pragma omp parallel
     {
-        orc_set_ftz();
+        const unsigned csr__ = orc_ftz_on();
 #pragma omp for
         for (int z = 0; z < Z; ++z)
             for (int y = 0; y < Y; ++y)
@@ -461,6 +478,7 @@ void orc_estimate_inverse(const orc_f4 *psi, orc_f4 *psi_inv, int X, int Y, int 
                     }
                     psi_inv[IDX(x, y, z)] = v;
                 }
+        _mm_setcsr(csr__);
     }
 }
 
@@ -533,7 +551,7 @@ void orc_tsdf_init_sphere(orc_f2 *vol, int X, int Y, int Z, float vx, float vy, 
                           float cx, float cy, float cz, float radius) {
 #pragma omp parallel
     {
-        orc_set_ftz();
+        const unsigned csr__ = orc_ftz_on();
 #pragma omp for
         for (int y = 0; y < Y; ++y)
             for (int x = 0; x < X; ++x) {
@@ -545,6 +563,7 @@ void orc_tsdf_init_sphere(orc_f2 *vol, int X, int Y, int Z, float vx, float vy, 
                     vol[IDX(x, y, z)] = pack_tsdf(sdf, trunc, (sdf > -eta) ? 1.f : 0.f);
                 }
             }
+        _mm_setcsr(csr__);
     }
 }
 
@@ -552,7 +571,7 @@ void orc_tsdf_init_sphere(orc_f2 *vol, int X, int Y, int Z, float vx, float vy, 
 void orc_tsdf_fuse(orc_f2 *pg, const orc_f2 *pn, int N, float max_weight) {
 #pragma omp parallel
     {
-        orc_set_ftz();
+        const unsigned csr__ = orc_ftz_on();
 #pragma omp for
         for (int i = 0; i < N; ++i) {
             orc_f2 t = pn[i];
@@ -561,6 +580,7 @@ void orc_tsdf_fuse(orc_f2 *pg, const orc_f2 *pn, int N, float max_weight) {
             orc_f2 r = {fmaf(p.y, p.x, t.x) / (p.y + 1.f), fminf(p.y + 1.f, max_weight)};
             pg[i] = r;
         }
+        _mm_setcsr(csr__);
     }
 }
 
@@ -570,7 +590,7 @@ void orc_tsdf_integrate(const float *dists, int cols, int rows, orc_f2 *vol, int
                         float fy, float cx, float cy) {
 #pragma omp parallel
     {
-        orc_set_ftz();
+        const unsigned csr__ = orc_ftz_on();
 #pragma omp for
         for (int y = 0; y < Y; ++y)
             for (int x = 0; x < X; ++x) {
@@ -587,6 +607,7 @@ void orc_tsdf_integrate(const float *dists, int cols, int rows, orc_f2 *vol, int
                     vol[IDX(x, y, z)] = pack_tsdf(psdf, trunc, (psdf > -eta) ? 1.f : 0.f);
                 }
             }
+        _mm_setcsr(csr__);
     }
 }
 

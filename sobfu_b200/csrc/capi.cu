@@ -1,0 +1,620 @@
+// capi.cu -- the C ABI of libsobfu_b200.so (include/sobfu_b200.h) and the host side of the solver.
+//
+// Host shell of the solver = what sobfu::cuda::Solver (src/sobfu/solver.cpp:7-101) and the launch loop of
+// sobfu::device::estimate_psi (src/sobfu/cuda/solver.cu:85-205) do in the reference, re-designed:
+//   * scratch is 36 B/voxel of float planes instead of 240 B/voxel of float4/Mat4f volumes
+//   * 2 kernels per iteration instead of 10 (12 when logging), no per-iteration host synchronisation:
+//     the convergence test (solver.cu:183) is evaluated on the device by every kernel of the following
+//     iteration; the host only looks at a pinned flag once per chunk of iterations
+//   * the 48 launches of the fixed-point inverse (vector_fields.cu:134-137) are one kernel
+#include <sobfu_b200.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "solver_kernels.cuh"
+
+namespace sb {
+// field_ops.cu
+void launch_tsdf_gradient(const float2 *phi, float4 *grad, Dims d, cudaStream_t st);
+void launch_laplacian(const float4 *psi, float4 *L, Dims d, cudaStream_t st);
+void launch_jacobian(const float4 *psi, float4 *J, Dims d, int mode, cudaStream_t st);
+void launch_potential_gradient(const float2 *pnp, const float2 *pg, const float4 *grad, const float4 *L, float4 *out,
+                               float w_reg, size_t n, cudaStream_t st);
+void launch_sobolev_filter(float4 *dst, const float4 *src, const float *taps7, Dims d, cudaStream_t st);
+void launch_update_psi(float4 *psi, const float4 *g, float4 *upd, float alpha, size_t n, cudaStream_t st);
+void launch_data_energy(const float2 *a, const float2 *b, size_t n, double *out, cudaStream_t st);
+void launch_reg_energy(const float4 *J, size_t n, double *out, cudaStream_t st);
+void launch_max_norm(const float4 *u, size_t n, RankMap rm, unsigned long long *out, cudaStream_t st);
+// tsdf_ops.cu
+void launch_tsdf_clear(float2 *vol, size_t n, cudaStream_t st);
+void launch_tsdf_init_sphere(float2 *vol, Dims d, float3 vs, float trunc, float eta, float3 c, float r, cudaStream_t st);
+void launch_tsdf_fuse(float2 *pg, const float2 *pn, size_t n, float max_weight, cudaStream_t st);
+void launch_tsdf_integrate(const float *dists, size_t pitch, int cols, int rows, float2 *vol, Dims d, float3 vs, float trunc,
+                           float eta, const float *R, const float *t, float fx, float fy, float cx, float cy, cudaStream_t st);
+void launch_bilateral(const unsigned short *src, size_t sp, unsigned short *dst, size_t dp, int cols, int rows, int ksz,
+                      float ss_inv_half, float sd_inv_half, cudaStream_t st);
+void launch_truncate(unsigned short *depth, size_t pitch, int cols, int rows, unsigned short max_mm, cudaStream_t st);
+void launch_dists(const unsigned short *depth, size_t dp, float *dists, size_t fp, int cols, int rows, float fix, float fiy,
+                  float cx, float cy, cudaStream_t st);
+// marching_cubes.cu
+int marching_cubes_run(const float2 *vol, Dims d, float3 size, const float *R, const float *t, float4 *verts, float4 *normals,
+                       int vertex_cap, int *n_vertices, int *occ_voxel, int *occ_cube, int *occ_nverts, int voxel_cap,
+                       int *n_voxels, cudaStream_t st, std::string &err);
+}  // namespace sb
+
+using namespace sb;
+
+// ------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static thread_local cudaStream_t g_stream = 0;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(expr)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e__ = (expr);                                                                          \
+        if (e__ != cudaSuccess) return fail(SOBFU_B200_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+#define CK_LAST() CK(cudaGetLastError())
+
+static bool dims_ok(int X, int Y, int Z) { return X >= 2 && Y >= 2 && Z >= 2 && (long long)X * Y * Z < (1ll << 31); }
+
+extern "C" const char *sobfu_b200_last_error(void) { return g_err.c_str(); }
+extern "C" const char *sobfu_b200_version(void) { return "sobfu_b200 0.1 (sm_100a)"; }
+extern "C" int sobfu_b200_set_stream(void *s) { g_stream = (cudaStream_t)s; return 0; }
+
+// decompose_sobolev_filter, src/sobfu/solver.cpp:160-262: tabulated taps, then fp32 normalisation to unit sum
+extern "C" int sobfu_b200_sobolev_taps(int s, float lambda, float *h) {
+    struct Row { int s; float lambda; int n; float v[11]; };
+    static const Row rows[] = {
+        {3, 0.1f, 3, {0.06537f, 0.99572f, 0.06537f}},
+        {7, 0.05f, 7, {0.00006f, 0.00015f, 0.03917f, 0.99846f, 0.03917f, 0.00015f, 0.00006f}},
+        {7, 0.1f, 7, {0.00030f, 0.00441f, 0.06571f, 0.99565f, 0.06571f, 0.00441f, 0.00030f}},
+        {7, 0.2f, 7, {0.00120f, 0.01094f, 0.10204f, 0.98941f, 0.10204f, 0.01094f, 0.00120f}},
+        {7, 0.4f, 7, {0.00169f, 0.01312f, 0.10927f, 0.98781f, 0.10927f, 0.01312f, 0.00169f}},
+        {9, 0.05f, 9, {0.000003f, 0.00006f, 0.00155f, 0.03917f, 0.99846f, 0.03917f, 0.00155f, 0.00006f, 0.000003f}},
+        {9, 0.1f, 9, {0.00002f, 0.00030f, 0.00441f, 0.06571f, 0.99565f, 0.06571f, 0.00441f, 0.00030f, 0.00002f}},
+        {11, 0.1f, 11, {0.0000015f, 0.00002f, 0.00030f, 0.00441f, 0.06571f, 0.99565f, 0.06571f, 0.00441f, 0.00030f, 0.00002f, 0.0000015f}},
+    };
+    for (const Row &r : rows)
+        if (r.s == s && r.lambda == lambda) {   // exact float compare, as the reference does
+            float sum = 0.f;
+            for (int i = 0; i < r.n; ++i) sum += r.v[i];
+            for (int i = 0; i < r.n; ++i) h[i] = r.v[i] / sum;
+            return 0;
+        }
+    // the reference leaves h_S_i uninitialised here (solver.cpp:160-251); we refuse instead
+    return fail(SOBFU_B200_EINVAL, "no Sobolev filter tabulated for s=%d lambda=%g (solver.cpp:160-251)", s, (double)lambda);
+}
+
+// __fsqrt_rd on the host: largest float r with r*r <= x (the product of two floats is exact in double)
+static float host_sqrt_rd(float x) {
+    if (!(x > 0.f)) return 0.f;
+    float r = sqrtf(x);
+    if ((double)r * (double)r > (double)x) r = nextafterf(r, 0.f);
+    return r;
+}
+
+// reference reduction sizing, src/sobfu/precomp.cpp:20-43 with (65536, 512) (reductor.cpp:17)
+static RankMap rank_map_for(size_t n) {
+    unsigned threads;
+    if (n < 1024) {
+        unsigned x = (unsigned)((n + 1) / 2);
+        --x; x |= x >> 1; x |= x >> 2; x |= x >> 4; x |= x >> 8; x |= x >> 16;
+        threads = x + 1;
+        if (threads == 0) threads = 1;
+    } else threads = 512;
+    unsigned blocks = (unsigned)((n + (threads * 2 - 1)) / (threads * 2));
+    if (blocks > 65536) blocks = 65536;
+    RankMap m;
+    m.bs = threads;
+    m.grid = threads * 2 * blocks;
+    m.npass = (unsigned)((n + m.grid - 1) / m.grid);
+    return m;
+}
+static long long unrank(unsigned rank, const RankMap m) {
+    const unsigned half = rank & 1u;
+    unsigned r = rank >> 1;
+    const unsigned pass = r % m.npass;
+    r /= m.npass;
+    const unsigned t = r % m.bs, b = r / m.bs;
+    return (long long)pass * m.grid + (long long)b * 2 * m.bs + (long long)half * m.bs + t;
+}
+// how the reference reports the index: (float) i for the first element of a thread, (float) i + blockSize for the second
+static float idx_as_ref_float(long long idx, const RankMap m) {
+    const long long q = (idx % m.grid) % (2 * (long long)m.bs);
+    if (q >= m.bs) return (float)(unsigned)(idx - m.bs) + (float)m.bs;
+    return (float)(unsigned)idx;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+struct sobfu_b200_solver {
+    sobfu_b200_params p;
+    Dims d;
+    size_t N;
+    float taps[7];
+    GLayout gl;
+    // device scratch
+    float *planes = nullptr;       // px,py,pz,w,pg,pn (6N floats)
+    float *g = nullptr;            // 3 * gl.total floats
+    LoopState *state = nullptr;
+    unsigned long long *maxkey = nullptr;
+    double *energies = nullptr;    // e_data[max_iter], e_reg[max_iter]
+    // host side
+    LoopState *h_state = nullptr;  // pinned
+    std::vector<unsigned long long> h_maxkey;
+    std::vector<double> h_energies;
+    std::vector<sobfu_b200_iter_log> log;
+    int last_iters = 0;
+    size_t ws_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_user = nullptr;
+    int variant = 0;
+    TmaMaps *tma = nullptr;
+    // host staging for the *_host entry point
+    void *stage_dev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *stage_pinned[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool have_state = false;       // planes hold a valid state (for time_loop)
+    LoopArgs args;
+};
+
+static bool use_tiled(const sobfu_b200_solver *s) {
+    if (s->variant == 1) return false;
+    return tiled_supported(s->d) && s->tma != nullptr;
+}
+
+static void fill_args(sobfu_b200_solver *s) {
+    LoopArgs &a = s->args;
+    a.px = s->planes; a.py = s->planes + s->N; a.pz = s->planes + 2 * s->N; a.w = s->planes + 3 * s->N;
+    a.pg = s->planes + 4 * s->N; a.pn = s->planes + 5 * s->N;
+    a.gx = s->g; a.gy = s->g + s->gl.total; a.gz = s->g + 2 * s->gl.total;
+    a.d = s->d; a.gl = s->gl;
+    for (int i = 0; i < 7; ++i) a.S[i] = s->taps[i];
+    a.alpha = s->p.alpha; a.w_reg = s->p.w_reg; a.thr = s->p.max_update_norm;
+    a.state = s->state; a.maxkey = s->maxkey; a.e_data = s->energies; a.e_reg = s->energies + s->p.max_iter;
+    a.rm = rank_map_for(s->N);
+    a.check = 1;
+}
+
+extern "C" int sobfu_b200_solver_destroy(sobfu_b200_solver *s) {
+    if (!s) return 0;
+    if (s->tma) tma_maps_destroy(s->tma);
+    cudaFree(s->planes); cudaFree(s->g); cudaFree(s->state); cudaFree(s->maxkey); cudaFree(s->energies);
+    if (s->h_state) cudaFreeHost(s->h_state);
+    for (int i = 0; i < 6; ++i) { if (s->stage_dev[i]) cudaFree(s->stage_dev[i]); if (s->stage_pinned[i]) cudaFreeHost(s->stage_pinned[i]); }
+    for (auto &e : s->ev) if (e) cudaEventDestroy(e);
+    if (s->ev_user) cudaEventDestroy(s->ev_user);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return 0;
+}
+
+extern "C" int sobfu_b200_solver_create(sobfu_b200_solver **out, const sobfu_b200_params *p) {
+    if (!out || !p) return fail(SOBFU_B200_EINVAL, "null argument");
+    *out = nullptr;
+    if (!dims_ok(p->dims[0], p->dims[1], p->dims[2])) return fail(SOBFU_B200_EINVAL, "volume dims must be >= 2 per axis and < 2^31 voxels");
+    if (p->s != 7) return fail(SOBFU_B200_EINVAL, "s=%d: the reference's convolution kernels are compiled for 7 taps only (solver.cu:211)", p->s);
+    if (p->max_iter < 0) return fail(SOBFU_B200_EINVAL, "max_iter < 0");
+    sobfu_b200_solver *s = new sobfu_b200_solver();
+    s->p = *p;
+    int rc = sobfu_b200_sobolev_taps(p->s, p->lambda, s->taps);
+    if (rc) { delete s; return rc; }
+    s->d = Dims{p->dims[0], p->dims[1], p->dims[2]};
+    s->N = (size_t)s->d.X * s->d.Y * s->d.Z;
+    s->gl.PX = s->d.X + 8; s->gl.PY = s->d.Y + 6; s->gl.PZ = s->d.Z + 6;
+    s->gl.plane = (size_t)s->gl.PX * s->gl.PY;
+    s->gl.total = s->gl.plane * s->gl.PZ;
+    const int mi = p->max_iter > 0 ? p->max_iter : 1;
+#define CKD(expr)                                                                                          \
+    do {                                                                                                   \
+        cudaError_t e__ = (expr);                                                                          \
+        if (e__ != cudaSuccess) {                                                                          \
+            int c__ = fail(e__ == cudaErrorMemoryAllocation ? SOBFU_B200_ENOMEM : SOBFU_B200_ECUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+            sobfu_b200_solver_destroy(s);                                                                  \
+            return c__;                                                                                    \
+        }                                                                                                  \
+    } while (0)
+    CKD(cudaMalloc(&s->planes, 6 * s->N * sizeof(float)));
+    CKD(cudaMalloc(&s->g, 3 * s->gl.total * sizeof(float)));
+    CKD(cudaMemset(s->g, 0, 3 * s->gl.total * sizeof(float)));
+    CKD(cudaMalloc(&s->state, sizeof(LoopState)));
+    CKD(cudaMalloc(&s->maxkey, mi * sizeof(unsigned long long)));
+    CKD(cudaMalloc(&s->energies, 2 * mi * sizeof(double)));
+    CKD(cudaMallocHost(&s->h_state, sizeof(LoopState)));
+    CKD(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (auto &e : s->ev) CKD(cudaEventCreate(&e));
+    CKD(cudaEventCreateWithFlags(&s->ev_user, cudaEventDisableTiming));
+    s->ws_bytes = 6 * s->N * sizeof(float) + 3 * s->gl.total * sizeof(float) + mi * 24 + sizeof(LoopState);
+    s->h_maxkey.resize(mi);
+    s->h_energies.resize(2 * mi);
+    fill_args(s);
+    if (tiled_supported(s->d)) s->tma = tma_maps_create(s->args);   // nullptr if the driver entry point is unavailable
+    *out = s;
+    return 0;
+}
+
+extern "C" size_t sobfu_b200_solver_workspace_bytes(sobfu_b200_solver *s) { return s ? s->ws_bytes : 0; }
+extern "C" int sobfu_b200_solver_get_taps(sobfu_b200_solver *s, float *t) {
+    if (!s || !t) return fail(SOBFU_B200_EINVAL, "null argument");
+    memcpy(t, s->taps, sizeof s->taps);
+    return 0;
+}
+extern "C" int sobfu_b200_solver_set_variant(sobfu_b200_solver *s, int v) {
+    if (!s || v < 0 || v > 2) return fail(SOBFU_B200_EINVAL, "variant must be 0, 1 or 2");
+    if (v == 2 && !(tiled_supported(s->d) && s->tma)) return fail(SOBFU_B200_EINVAL, "tiled/TMA kernels do not support dims %dx%dx%d", s->d.X, s->d.Y, s->d.Z);
+    s->variant = v;
+    return 0;
+}
+
+static inline bool log_iter(const sobfu_b200_params &p, int iter1) {   // iter1 is 1-based, solver.cu:132-133
+    return p.verbosity == 2 || (p.verbosity == 1 && (iter1 == 1 || iter1 % 50 == 0 || iter1 == p.max_iter));
+}
+
+static void launch_iteration(sobfu_b200_solver *s, int it, int log, int *launches) {
+    if (use_tiled(s)) {
+        launch_pass_a_tiled(s->args, it, log, s->stream);
+        launch_pass_b_tma(s->args, s->tma, it, s->stream);
+    } else {
+        launch_pass_a_generic(s->args, it, log, s->stream);
+        launch_pass_b_generic(s->args, it, s->stream);
+    }
+    *launches += 2;
+}
+
+static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *phi_global_psi_inv, const float2 *phi_n,
+                        float2 *phi_n_psi, float4 *psi, float4 *psi_inv, sobfu_b200_solve_info *info, bool order_with_user) {
+    const sobfu_b200_params &p = s->p;
+    const int mi = p.max_iter;
+    cudaStream_t st = s->stream;
+    int launches = 0;
+    if (order_with_user) {   // everything the caller enqueued on its stream happens-before the solve
+        CK(cudaEventRecord(s->ev_user, g_stream));
+        CK(cudaStreamWaitEvent(st, s->ev_user, 0));
+    }
+    s->args.check = 1;
+    CK(cudaEventRecord(s->ev[0], st));
+    CK(cudaMemsetAsync(s->state, 0, sizeof(LoopState), st));
+    if (mi > 0) {
+        CK(cudaMemsetAsync(s->maxkey, 0, mi * sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(s->energies, 0, 2 * mi * sizeof(double), st));
+    }
+    launch_unpack(psi, phi_global, phi_n, s->args, st);
+    launch_initial_warp(s->args, st);
+    launches += 2;
+    CK_LAST();
+    CK(cudaEventRecord(s->ev[1], st));
+
+    // gradient descent (solver.cu:114-193).  Iterations are enqueued in chunks; the device decides convergence.
+    const int CHUNK = 64;
+    int converged = 0, iters = mi;
+    for (int it0 = 0; it0 < mi && !converged; it0 += CHUNK) {
+        const int it1 = it0 + CHUNK < mi ? it0 + CHUNK : mi;
+        for (int it = it0; it < it1; ++it) launch_iteration(s, it, log_iter(p, it + 1) ? 1 : 0, &launches);
+        CK_LAST();
+        if (it1 < mi) {   // peek at the sticky flag (it is raised by pass A of the iteration after the converged one)
+            CK(cudaMemcpyAsync(s->h_state, s->state, sizeof(LoopState), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (s->h_state->converged) { converged = 1; iters = s->h_state->iters; }
+        }
+    }
+    CK(cudaEventRecord(s->ev[2], st));
+
+    // tail (solver.cu:195-199): write back psi / phi_n o psi, psi^-1 from identity (48 fixed-point steps), phi_global o psi^-1
+    launch_pack(psi, phi_n_psi, phi_n, s->args, st);
+    launch_estimate_inverse(psi, psi_inv, s->d, 48, true, st);
+    launch_apply(phi_global, phi_global_psi_inv, psi_inv, s->d, st);
+    launches += 3;
+    CK_LAST();
+    CK(cudaEventRecord(s->ev[3], st));
+    CK(cudaMemcpyAsync(s->h_state, s->state, sizeof(LoopState), cudaMemcpyDeviceToHost, st));
+    if (mi > 0) {
+        CK(cudaMemcpyAsync(s->h_maxkey.data(), s->maxkey, mi * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(s->h_energies.data(), s->energies, 2 * mi * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    s->have_state = true;
+
+    if (s->h_state->converged) { converged = 1; iters = s->h_state->iters; }
+    auto norm_of = [&](int it) { return host_sqrt_rd(__builtin_bit_cast(float, (unsigned)(s->h_maxkey[it] >> 32))); };
+    // the last enqueued iteration has no successor to evaluate its convergence test: do it here (solver.cu:183)
+    if (!converged && mi > 0 && norm_of(mi - 1) <= p.max_update_norm) { converged = 1; iters = mi; }
+    s->last_iters = iters;
+    s->log.assign(iters, sobfu_b200_iter_log{0, 0, 0, 0});
+    for (int it = 0; it < iters; ++it) {
+        const long long idx = unrank(0xffffffffu - (unsigned)(s->h_maxkey[it] & 0xffffffffull), s->args.rm);
+        s->log[it].max_norm = norm_of(it);
+        s->log[it].max_idx_f = s->log[it].max_norm > 0.f ? idx_as_ref_float(idx, s->args.rm) : 0.f;
+        s->log[it].e_data = 0.5f * (float)s->h_energies[it];
+        s->log[it].e_reg = 0.5f * (float)s->h_energies[mi + it];
+    }
+    if (info) {
+        memset(info, 0, sizeof *info);
+        info->iters = iters;
+        info->converged = converged;
+        if (iters > 0) {
+            info->max_norm = s->log[iters - 1].max_norm;
+            info->max_idx_f = s->log[iters - 1].max_idx_f;
+            info->max_idx = info->max_norm > 0.f ? unrank(0xffffffffu - (unsigned)(s->h_maxkey[iters - 1] & 0xffffffffull), s->args.rm) : 0;
+        }
+        cudaEventElapsedTime(&info->loop_ms, s->ev[1], s->ev[2]);
+        cudaEventElapsedTime(&info->total_ms, s->ev[0], s->ev[3]);
+        info->launches = launches;
+    }
+    // the reference's console output (solver.cu:115-117,140-141,179-190), same text and cadence
+    static const bool quiet = getenv("SOBFU_B200_QUIET") != nullptr;   // the reference always prints; tests/bench may silence
+    if (!quiet) {
+        for (int it = 0; it < iters; ++it) {
+            const int iter1 = it + 1;
+            if (iter1 == 1 || iter1 % 50 == 0) printf("iter. no. %d\n", iter1);
+            if (log_iter(p, iter1)) {
+                const float e = s->log[it].e_data + p.w_reg * s->log[it].e_reg;
+                printf("data energy + w_reg * reg energy = %g + %g * %g = %g\n", s->log[it].e_data, p.w_reg, s->log[it].e_reg, e);
+                const float yf = s->log[it].max_idx_f;
+                const int ix = (int)(yf / (s->d.X * s->d.Y));
+                const int iy = (int)((yf - ix * s->d.X * s->d.Y) / s->d.X);
+                const int iz = (int)(yf - s->d.X * (iy + s->d.Y * ix));
+                printf("max. update norm %g at voxel (%d, %d, %d)\n", s->log[it].max_norm, iz, iy, ix);
+            }
+            if (iter1 == iters && converged) printf("SOLVER CONVERGED AFTER %d ITERATIONS\n", iter1);
+            else if (iter1 == p.max_iter) printf("SOLVER REACHED MAX. NO. OF ITERATIONS WITHOUT CONVERGING\n");
+        }
+        fflush(stdout);
+    }
+    return 0;
+}
+
+extern "C" int sobfu_b200_solver_estimate_psi(sobfu_b200_solver *s, const void *phi_global, void *phi_global_psi_inv,
+                                              const void *phi_n, void *phi_n_psi, void *psi, void *psi_inv,
+                                              sobfu_b200_solve_info *info) {
+    if (!s || !phi_global || !phi_global_psi_inv || !phi_n || !phi_n_psi || !psi || !psi_inv) return fail(SOBFU_B200_EINVAL, "null argument");
+    return solve_device(s, (const float2 *)phi_global, (float2 *)phi_global_psi_inv, (const float2 *)phi_n, (float2 *)phi_n_psi,
+                        (float4 *)psi, (float4 *)psi_inv, info, true);
+}
+
+extern "C" int sobfu_b200_solver_estimate_psi_host(sobfu_b200_solver *s, const void *phi_global_h, void *phi_global_psi_inv_h,
+                                                   const void *phi_n_h, void *phi_n_psi_h, void *psi_h, void *psi_inv_h,
+                                                   sobfu_b200_solve_info *info) {
+    if (!s || !phi_global_h || !phi_n_h || !psi_h) return fail(SOBFU_B200_EINVAL, "null argument");
+    const size_t b2 = s->N * sizeof(float2), b4 = s->N * sizeof(float4);
+    const size_t bytes[6] = {b2, b2, b2, b2, b4, b4};   // phi_global, phi_global_psi_inv, phi_n, phi_n_psi, psi, psi_inv
+    for (int i = 0; i < 6; ++i) {
+        if (!s->stage_dev[i]) CK(cudaMalloc(&s->stage_dev[i], bytes[i]));
+        if (!s->stage_pinned[i]) CK(cudaMallocHost(&s->stage_pinned[i], bytes[i]));
+    }
+    cudaStream_t st = s->stream;
+    // host -> pinned -> device for the three inputs (pageable user memory cannot be DMA'd asynchronously)
+    const void *in_h[3] = {phi_global_h, phi_n_h, psi_h};
+    const int in_i[3] = {0, 2, 4};
+    for (int k = 0; k < 3; ++k) {
+        memcpy(s->stage_pinned[in_i[k]], in_h[k], bytes[in_i[k]]);
+        CK(cudaMemcpyAsync(s->stage_dev[in_i[k]], s->stage_pinned[in_i[k]], bytes[in_i[k]], cudaMemcpyHostToDevice, st));
+    }
+    int rc = solve_device(s, (const float2 *)s->stage_dev[0], (float2 *)s->stage_dev[1], (const float2 *)s->stage_dev[2],
+                          (float2 *)s->stage_dev[3], (float4 *)s->stage_dev[4], (float4 *)s->stage_dev[5], info, false);
+    if (rc) return rc;
+    void *out_h[4] = {phi_global_psi_inv_h, phi_n_psi_h, psi_h, psi_inv_h};
+    const int out_i[4] = {1, 3, 4, 5};
+    for (int k = 0; k < 4; ++k)
+        if (out_h[k]) CK(cudaMemcpyAsync(s->stage_pinned[out_i[k]], s->stage_dev[out_i[k]], bytes[out_i[k]], cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int k = 0; k < 4; ++k)
+        if (out_h[k]) memcpy(out_h[k], s->stage_pinned[out_i[k]], bytes[out_i[k]]);
+    return 0;
+}
+
+extern "C" int sobfu_b200_solver_get_log(sobfu_b200_solver *s, sobfu_b200_iter_log *out, int n) {
+    if (!s || !out) return fail(SOBFU_B200_EINVAL, "null argument");
+    const int m = n < (int)s->log.size() ? n : (int)s->log.size();
+    if (m > 0) memcpy(out, s->log.data(), m * sizeof(sobfu_b200_iter_log));
+    return 0;
+}
+
+extern "C" int sobfu_b200_solver_time_loop(sobfu_b200_solver *s, int iters, float *ms_a, float *ms_b, float *ms_loop) {
+    if (!s || iters <= 0) return fail(SOBFU_B200_EINVAL, "bad argument");
+    if (!s->have_state) return fail(SOBFU_B200_EINVAL, "time_loop needs the state left by a previous estimate_psi");
+    cudaStream_t st = s->stream;
+    s->args.check = 0;
+    const int slot = 0;   // partial maxima land in maxkey[0]; irrelevant here
+    const bool tiled = use_tiled(s);
+    auto run_a = [&]() { if (tiled) launch_pass_a_tiled(s->args, slot, 0, st); else launch_pass_a_generic(s->args, slot, 0, st); };
+    auto run_b = [&]() { if (tiled) launch_pass_b_tma(s->args, s->tma, slot, st); else launch_pass_b_generic(s->args, slot, st); };
+    float ta = 0.f, tb = 0.f, tl = 0.f;
+    // whole loop
+    CK(cudaEventRecord(s->ev[0], st));
+    for (int i = 0; i < iters; ++i) { run_a(); run_b(); }
+    CK(cudaEventRecord(s->ev[1], st));
+    // pass A alone / pass B alone (B keeps descending, which is fine for timing)
+    for (int i = 0; i < iters; ++i) run_a();
+    CK(cudaEventRecord(s->ev[2], st));
+    for (int i = 0; i < iters; ++i) run_b();
+    CK(cudaEventRecord(s->ev[3], st));
+    CK_LAST();
+    CK(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&tl, s->ev[0], s->ev[1]);
+    cudaEventElapsedTime(&ta, s->ev[1], s->ev[2]);
+    cudaEventElapsedTime(&tb, s->ev[2], s->ev[3]);
+    s->args.check = 1;
+    if (ms_a) *ms_a = ta / iters;
+    if (ms_b) *ms_b = tb / iters;
+    if (ms_loop) *ms_loop = tl / iters;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// free functions: issue on g_stream, complete on return (the reference's calls are synchronous in effect)
+#define SYNC_RET()            \
+    do {                      \
+        CK_LAST();            \
+        CK(cudaStreamSynchronize(g_stream)); \
+        return 0;             \
+    } while (0)
+#define NEED(c, msg) do { if (!(c)) return fail(SOBFU_B200_EINVAL, msg); } while (0)
+
+extern "C" int sobfu_b200_init_identity(void *psi, int X, int Y, int Z) {
+    NEED(psi && dims_ok(X, Y, Z), "init_identity: bad argument");
+    launch_init_identity((float4 *)psi, Dims{X, Y, Z}, g_stream);
+    SYNC_RET();
+}
+extern "C" int sobfu_b200_clear_field(void *f, int X, int Y, int Z) {
+    NEED(f && dims_ok(X, Y, Z), "clear_field: bad argument");
+    CK(cudaMemsetAsync(f, 0, (size_t)X * Y * Z * sizeof(float4), g_stream));
+    SYNC_RET();
+}
+extern "C" int sobfu_b200_apply(const void *phi, void *out, const void *psi, int X, int Y, int Z) {
+    NEED(phi && out && psi && dims_ok(X, Y, Z), "apply: bad argument");
+    NEED(phi != out, "apply: phi and phi_warped must not alias");
+    launch_apply((const float2 *)phi, (float2 *)out, (const float4 *)psi, Dims{X, Y, Z}, g_stream);
+    SYNC_RET();
+}
+extern "C" int sobfu_b200_estimate_inverse(const void *psi, void *psi_inv, int X, int Y, int Z, int iters) {
+    NEED(psi && psi_inv && dims_ok(X, Y, Z) && iters >= 0, "estimate_inverse: bad argument");
+    launch_estimate_inverse((const float4 *)psi, (float4 *)psi_inv, Dims{X, Y, Z}, iters, false, g_stream);
+    SYNC_RET();
+}
+extern "C" int sobfu_b200_tsdf_gradient(const void *phi, void *grad, int X, int Y, int Z) {
+    NEED(phi && grad && dims_ok(X, Y, Z), "tsdf_gradient: bad argument");
+    launch_tsdf_gradient((const float2 *)phi, (float4 *)grad, Dims{X, Y, Z}, g_stream);
+    SYNC_RET();
+}
+extern "C" int sobfu_b200_laplacian(const void *psi, void *L, int X, int Y, int Z) {
+    NEED(psi && L && dims_ok(X, Y, Z), "laplacian: bad argument");
+    launch_laplacian((const float4 *)psi, (float4 *)L, Dims{X, Y, Z}, g_stream);
+    SYNC_RET();
+}
+extern "C" int sobfu_b200_jacobian(const void *psi, void *J, int X, int Y, int Z, int mode) {
+    NEED(psi && J && dims_ok(X, Y, Z) && (mode == 0 || mode == 1), "jacobian: bad argument");
+    launch_jacobian((const float4 *)psi, (float4 *)J, Dims{X, Y, Z}, mode, g_stream);
+    SYNC_RET();
+}
+extern "C" int sobfu_b200_potential_gradient(const void *pnp, const void *pg, const void *grad, const void *L, void *out,
+                                             float w_reg, int X, int Y, int Z) {
+    NEED(pnp && pg && grad && L && out && dims_ok(X, Y, Z), "potential_gradient: bad argument");
+    launch_potential_gradient((const float2 *)pnp, (const float2 *)pg, (const float4 *)grad, (const float4 *)L, (float4 *)out, w_reg,
+                              (size_t)X * Y * Z, g_stream);
+    SYNC_RET();
+}
+extern "C" int sobfu_b200_sobolev_filter(void *dst, const void *src, const float *taps7, int X, int Y, int Z) {
+    NEED(dst && src && taps7 && dst != src && dims_ok(X, Y, Z), "sobolev_filter: bad argument");
+    launch_sobolev_filter((float4 *)dst, (const float4 *)src, taps7, Dims{X, Y, Z}, g_stream);
+    SYNC_RET();
+}
+extern "C" int sobfu_b200_update_psi(void *psi, const void *g, void *upd, float alpha, int X, int Y, int Z) {
+    NEED(psi && g && upd && dims_ok(X, Y, Z), "update_psi: bad argument");
+    launch_update_psi((float4 *)psi, (const float4 *)g, (float4 *)upd, alpha, (size_t)X * Y * Z, g_stream);
+    SYNC_RET();
+}
+
+static int reduce_scalar(double **dbuf) {
+    static thread_local double *buf = nullptr;
+    if (!buf) { cudaError_t e = cudaMalloc(&buf, 16); if (e != cudaSuccess) return fail(SOBFU_B200_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    *dbuf = buf;
+    return 0;
+}
+extern "C" int sobfu_b200_data_energy(const void *a, const void *b, int N, float *out) {
+    NEED(a && b && out && N > 0, "data_energy: bad argument");
+    double *d; int rc = reduce_scalar(&d); if (rc) return rc;
+    CK(cudaMemsetAsync(d, 0, 8, g_stream));
+    launch_data_energy((const float2 *)a, (const float2 *)b, (size_t)N, d, g_stream);
+    double h; CK_LAST(); CK(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, g_stream)); CK(cudaStreamSynchronize(g_stream));
+    *out = 0.5f * (float)h;   // reductor.cpp:42
+    return 0;
+}
+extern "C" int sobfu_b200_reg_energy(const void *J, int N, float *out) {
+    NEED(J && out && N > 0, "reg_energy: bad argument");
+    double *d; int rc = reduce_scalar(&d); if (rc) return rc;
+    CK(cudaMemsetAsync(d, 0, 8, g_stream));
+    launch_reg_energy((const float4 *)J, (size_t)N, d, g_stream);
+    double h; CK_LAST(); CK(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, g_stream)); CK(cudaStreamSynchronize(g_stream));
+    *out = 0.5f * (float)h;   // reductor.cpp:49
+    return 0;
+}
+extern "C" int sobfu_b200_max_update_norm(const void *u, int N, float *value, float *index_f, long long *index) {
+    NEED(u && N > 0, "max_update_norm: bad argument");
+    double *d; int rc = reduce_scalar(&d); if (rc) return rc;
+    const RankMap rm = rank_map_for((size_t)N);
+    CK(cudaMemsetAsync(d, 0, 8, g_stream));
+    launch_max_norm((const float4 *)u, (size_t)N, rm, (unsigned long long *)d, g_stream);
+    unsigned long long h; CK_LAST(); CK(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, g_stream)); CK(cudaStreamSynchronize(g_stream));
+    const float v = __builtin_bit_cast(float, (unsigned)(h >> 32));
+    const long long idx = v > 0.f ? unrank(0xffffffffu - (unsigned)(h & 0xffffffffull), rm) : 0;
+    if (value) *value = v;
+    if (index) *index = idx;
+    if (index_f) *index_f = v > 0.f ? idx_as_ref_float(idx, rm) : 0.f;
+    return 0;
+}
+
+// ---- TSDF / depth / marching cubes --------------------------------------------------------------------------
+extern "C" int sobfu_b200_tsdf_clear(void *vol, int X, int Y, int Z) {
+    NEED(vol && dims_ok(X, Y, Z), "tsdf_clear: bad argument");
+    launch_tsdf_clear((float2 *)vol, (size_t)X * Y * Z, g_stream);
+    SYNC_RET();
+}
+extern "C" int sobfu_b200_tsdf_init_sphere(void *vol, int X, int Y, int Z, const float *vs, float trunc, float eta, const float *c,
+                                           float radius) {
+    NEED(vol && vs && c && dims_ok(X, Y, Z), "tsdf_init_sphere: bad argument");
+    launch_tsdf_init_sphere((float2 *)vol, Dims{X, Y, Z}, make_float3(vs[0], vs[1], vs[2]), trunc, eta, make_float3(c[0], c[1], c[2]),
+                            radius, g_stream);
+    SYNC_RET();
+}
+extern "C" int sobfu_b200_tsdf_fuse(void *pg, const void *pn, int X, int Y, int Z, float max_weight) {
+    NEED(pg && pn && dims_ok(X, Y, Z), "tsdf_fuse: bad argument");
+    launch_tsdf_fuse((float2 *)pg, (const float2 *)pn, (size_t)X * Y * Z, max_weight, g_stream);
+    SYNC_RET();
+}
+extern "C" int sobfu_b200_tsdf_integrate(const void *dists, size_t pitch, int cols, int rows, void *vol, int X, int Y, int Z,
+                                         const float *vs, float trunc, float eta, const float *R9, const float *t3, float fx,
+                                         float fy, float cx, float cy) {
+    NEED(dists && vol && vs && R9 && t3 && dims_ok(X, Y, Z) && cols > 0 && rows > 0 && pitch >= cols * sizeof(float), "tsdf_integrate: bad argument");
+    launch_tsdf_integrate((const float *)dists, pitch, cols, rows, (float2 *)vol, Dims{X, Y, Z}, make_float3(vs[0], vs[1], vs[2]), trunc,
+                          eta, R9, t3, fx, fy, cx, cy, g_stream);
+    SYNC_RET();
+}
+extern "C" int sobfu_b200_depth_bilateral(const void *src, size_t sp, void *dst, size_t dp, int cols, int rows, int ksz,
+                                          float sigma_spatial, float sigma_depth) {
+    NEED(src && dst && src != dst && cols > 0 && rows > 0, "depth_bilateral: bad argument");
+    sigma_depth *= 1000;   // metres -> mm, imgproc.cu:44
+    launch_bilateral((const unsigned short *)src, sp, (unsigned short *)dst, dp, cols, rows, ksz, 0.5f / (sigma_spatial * sigma_spatial),
+                     0.5f / (sigma_depth * sigma_depth), g_stream);
+    SYNC_RET();
+}
+extern "C" int sobfu_b200_depth_truncate(void *depth, size_t pitch, int cols, int rows, float max_dist) {
+    NEED(depth && cols > 0 && rows > 0, "depth_truncate: bad argument");
+    launch_truncate((unsigned short *)depth, pitch, cols, rows, static_cast<unsigned short>(max_dist * 1000.f), g_stream);
+    SYNC_RET();
+}
+extern "C" int sobfu_b200_compute_dists(const void *depth, size_t dp, void *dists, size_t fp, int cols, int rows, float fx, float fy,
+                                        float cx, float cy) {
+    NEED(depth && dists && cols > 0 && rows > 0, "compute_dists: bad argument");
+    launch_dists((const unsigned short *)depth, dp, (float *)dists, fp, cols, rows, 1.f / fx, 1.f / fy, cx, cy, g_stream);
+    SYNC_RET();
+}
+extern "C" int sobfu_b200_marching_cubes(const void *vol, int X, int Y, int Z, const float *size3, const float *R9, const float *t3,
+                                         void *verts, void *normals, int vertex_cap, int *n_vertices, int *occ_voxel, int *occ_cube,
+                                         int *occ_nverts, int voxel_cap, int *n_voxels) {
+    NEED(vol && size3 && R9 && t3 && dims_ok(X, Y, Z) && n_vertices, "marching_cubes: bad argument");
+    std::string err;
+    int rc = marching_cubes_run((const float2 *)vol, Dims{X, Y, Z}, make_float3(size3[0], size3[1], size3[2]), R9, t3, (float4 *)verts,
+                                (float4 *)normals, vertex_cap, n_vertices, occ_voxel, occ_cube, occ_nverts, voxel_cap, n_voxels, g_stream, err);
+    if (rc) return fail(rc, "%s", err.c_str());
+    return 0;
+}
+
+// ---- multi-GPU ------------------------------------------------------------------------------------------------
+extern "C" int sobfu_b200_comm_unique_id(void *) { return fail(SOBFU_B200_ECOMM, "multi-GPU slab mode is not built into this library yet"); }
+extern "C" int sobfu_b200_solver_attach_comm(sobfu_b200_solver *, const void *, int, int) {
+    return fail(SOBFU_B200_ECOMM, "multi-GPU slab mode is not built into this library yet");
+}

@@ -1,0 +1,249 @@
+// field_ops.cu -- free-standing kernels on the reference's AoS layouts (float4 fields, float2 TSDF, Mat4f Jacobian).
+// These back the DeformationField / differentiator / Reductor entry points that the reference's gtest harness calls
+// directly and the once-per-frame tail of estimate_psi (psi^-1 and the final warp).
+#include "solver_kernels.cuh"
+
+namespace sb {
+namespace {
+
+constexpr int BX = 32, BY = 4, BZ = 2;
+SB_DEV bool voxel_of_thread(const Dims d, int &x, int &y, int &z) {
+    x = blockIdx.x * BX + threadIdx.x;
+    y = blockIdx.y * BY + threadIdx.y;
+    z = blockIdx.z * BZ + threadIdx.z;
+    return x < d.X && y < d.Y && z < d.Z;
+}
+inline dim3 grid3(const Dims d) { return dim3((d.X + BX - 1) / BX, (d.Y + BY - 1) / BY, (d.Z + BZ - 1) / BZ); }
+inline dim3 block3() { return dim3(BX, BY, BZ); }
+
+// init_identity_kernel, vector_fields.cu:64-79
+__global__ void init_identity_kernel(float4 *__restrict__ psi, Dims d) {
+    int x, y, z;
+    if (!voxel_of_thread(d, x, y, z)) return;
+    psi[x + (size_t)d.X * (y + (size_t)d.Y * z)] = make_float4((float)x, (float)y, (float)z, 0.f);
+}
+
+// apply_kernel, vector_fields.cu:81-100 + interpolate_tsdf, utils.hpp:50-86
+__global__ void apply_kernel(const float2 *__restrict__ phi, float2 *__restrict__ out, const float4 *__restrict__ psi,
+                             Dims d) {
+    int x, y, z;
+    if (!voxel_of_thread(d, x, y, z)) return;
+    const size_t i = x + (size_t)d.X * (y + (size_t)d.Y * z);
+    const float4 p = psi[i];
+    const TriCoord t = tri_coord(p.x, p.y, p.z, d);
+    const float v = sample_scalar<2>(reinterpret_cast<const float *>(phi), t, d);
+    const float wgt = phi[(size_t)t.gx + (size_t)d.X * ((size_t)t.gy + (size_t)d.Y * t.gz)].y;
+    out[i] = make_float2(v, wgt);
+}
+
+// estimate_inverse_kernel x iters, vector_fields.cu:111-138 with interpolate_field_inv, utils.hpp:124-164.
+// Every launch of the reference reads only psi and the voxel's own psi_inv value, so the launches collapse into a
+// per-voxel loop in registers: psi_inv <- (x,y,z) - 1.f * trilerp(psi - id)(psi_inv).
+SB_DEV float3 disp(const float4 *__restrict__ psi, int x, int y, int z, const Dims d) {
+    const float4 p = __ldg(psi + (size_t)x + (size_t)d.X * ((size_t)y + (size_t)d.Y * z));
+    return make_float3(sub(p.x, (float)x), sub(p.y, (float)y), sub(p.z, (float)z));   // get_displacement
+}
+__global__ void __launch_bounds__(BX *BY *BZ) estimate_inverse_kernel(const float4 *__restrict__ psi,
+                                                                    float4 *__restrict__ psi_inv, Dims d, int iters,
+                                                                    int from_identity) {
+    int x, y, z;
+    if (!voxel_of_thread(d, x, y, z)) return;
+    const size_t i = x + (size_t)d.X * (y + (size_t)d.Y * z);
+    float vx, vy, vz, vw;
+    if (from_identity) { vx = (float)x; vy = (float)y; vz = (float)z; vw = 0.f; }
+    else { const float4 v = psi_inv[i]; vx = v.x; vy = v.y; vz = v.z; vw = v.w; }
+    for (int it = 0; it < iters; ++it) {
+        const TriCoord t = tri_coord(vx, vy, vz, d);
+        const float3 d111 = disp(psi, t.x1, t.y1, t.z1, d), d110 = disp(psi, t.x1, t.y1, t.gz, d);
+        const float3 d101 = disp(psi, t.x1, t.gy, t.z1, d), d100 = disp(psi, t.x1, t.gy, t.gz, d);
+        const float3 d011 = disp(psi, t.gx, t.y1, t.z1, d), d010 = disp(psi, t.gx, t.y1, t.gz, d);
+        const float3 d001 = disp(psi, t.gx, t.gy, t.z1, d), d000 = disp(psi, t.gx, t.gy, t.gz, d);
+        const float ix = tri_lerp(d111.x, d110.x, d101.x, d100.x, d011.x, d010.x, d001.x, d000.x, t);
+        const float iy = tri_lerp(d111.y, d110.y, d101.y, d100.y, d011.y, d010.y, d001.y, d000.y, t);
+        const float iz = tri_lerp(d111.z, d110.z, d101.z, d100.z, d011.z, d010.z, d001.z, d000.z, t);
+        vx = sub((float)x, mul(ix, 1.f));
+        vy = sub((float)y, mul(iy, 1.f));
+        vz = sub((float)z, mul(iz, 1.f));
+        vw = 0.f;
+    }
+    psi_inv[i] = make_float4(vx, vy, vz, vw);
+}
+
+// TsdfDifferentiator::operator(), vector_fields.cu:157-208
+__global__ void tsdf_gradient_kernel(const float2 *__restrict__ phi, float4 *__restrict__ grad, Dims d) {
+    int x, y, z;
+    if (!voxel_of_thread(d, x, y, z)) return;
+    const size_t sy = d.X, sz = (size_t)d.X * d.Y, i = x + sy * y + sz * z;
+    const size_t xa = (x == d.X - 1) ? i - 1 : i + 1, xb = (x == 0) ? i + 1 : i - 1;
+    const size_t ya = (y == d.Y - 1) ? i - sy : i + sy, yb = (y == 0) ? i + sy : i - sy;
+    const size_t za = (z == d.Z - 1) ? i - sz : i + sz, zb = (z == 0) ? i + sz : i - sz;
+    grad[i] = make_float4(mul(sub(phi[xa].x, phi[xb].x), 0.5f), mul(sub(phi[ya].x, phi[yb].x), 0.5f),
+                          mul(sub(phi[za].x, phi[zb].x), 0.5f), 0.f);
+}
+
+// SecondOrderDifferentiator::laplacian, vector_fields.cu:291-337
+SB_DEV float lap1(float c, float a1, float a2, float b1, float b2, float c1, float c2) {
+    float v = mul(c, -6.f);
+    v = add(v, a1); v = add(v, a2); v = add(v, b1); v = add(v, b2); v = add(v, c1); v = add(v, c2);
+    return mul(v, -1.f);
+}
+__global__ void laplacian_kernel(const float4 *__restrict__ psi, float4 *__restrict__ L, Dims d) {
+    int x, y, z;
+    if (!voxel_of_thread(d, x, y, z)) return;
+    const size_t sy = d.X, sz = (size_t)d.X * d.Y, i = x + sy * y + sz * z;
+    const bool bx = (x == 0 || x == d.X - 1), by = (y == 0 || y == d.Y - 1), bz = (z == 0 || z == d.Z - 1);
+    const float4 c = psi[i];
+    const float4 a1 = psi[bx ? i : i + 1], a2 = psi[bx ? i : i - 1];
+    const float4 b1 = psi[by ? i : i + sy], b2 = psi[by ? i : i - sy];
+    const float4 c1 = psi[bz ? i : i + sz], c2 = psi[bz ? i : i - sz];
+    L[i] = make_float4(lap1(c.x, a1.x, a2.x, b1.x, b2.x, c1.x, c2.x), lap1(c.y, a1.y, a2.y, b1.y, b2.y, c1.y, c2.y),
+                       lap1(c.z, a1.z, a2.z, b1.z, b2.z, c1.z, c2.z), 0.f);
+}
+
+// Differentiator::operator(), vector_fields.cu:415-472.  Rows 0..2 of the Mat4f are written, row 3 untouched.
+__global__ void jacobian_kernel(const float4 *__restrict__ psi, float4 *__restrict__ J, Dims d, int mode) {
+    int x, y, z;
+    if (!voxel_of_thread(d, x, y, z)) return;
+    const size_t sy = d.X, sz = (size_t)d.X * d.Y, i = x + sy * y + sz * z;
+    const int xa = (x == d.X - 1) ? x - 1 : x + 1, xb = (x == 0) ? x + 1 : x - 1;
+    const int ya = (y == d.Y - 1) ? y - 1 : y + 1, yb = (y == 0) ? y + 1 : y - 1;
+    const int za = (z == d.Z - 1) ? z - 1 : z + 1, zb = (z == 0) ? z + 1 : z - 1;
+    auto ld = [&](int px, int py, int pz) {
+        const float4 p = psi[px + sy * py + sz * pz];
+        if (mode == 1) return make_float3(sub(p.x, (float)px), sub(p.y, (float)py), sub(p.z, (float)pz));
+        return make_float3(p.x, p.y, p.z);
+    };
+    const float3 X1 = ld(xa, y, z), X2 = ld(xb, y, z), Y1 = ld(x, ya, z), Y2 = ld(x, yb, z), Z1 = ld(x, y, za),
+                 Z2 = ld(x, y, zb);
+    const float3 Jx = make_float3(mul(sub(X1.x, X2.x), 0.5f), mul(sub(X1.y, X2.y), 0.5f), mul(sub(X1.z, X2.z), 0.5f));
+    const float3 Jy = make_float3(mul(sub(Y1.x, Y2.x), 0.5f), mul(sub(Y1.y, Y2.y), 0.5f), mul(sub(Y1.z, Y2.z), 0.5f));
+    const float3 Jz = make_float3(mul(sub(Z1.x, Z2.x), 0.5f), mul(sub(Z1.y, Z2.y), 0.5f), mul(sub(Z1.z, Z2.z), 0.5f));
+    J[4 * i + 0] = make_float4(Jx.x, Jy.x, Jz.x, 0.f);
+    J[4 * i + 1] = make_float4(Jx.y, Jy.y, Jz.y, 0.f);
+    J[4 * i + 2] = make_float4(Jx.z, Jy.z, Jz.z, 0.f);
+}
+
+// calculate_potential_gradient_kernel, solver.cu:15-33
+__global__ void potential_gradient_kernel(const float2 *__restrict__ pnp, const float2 *__restrict__ pg,
+                                          const float4 *__restrict__ grad, const float4 *__restrict__ L,
+                                          float4 *__restrict__ out, float w_reg, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float dd = sub(pnp[i].x, pg[i].x);
+        const float4 g = grad[i], l = L[i];
+        out[i] = make_float4(add(mul(g.x, dd), mul(l.x, w_reg)), add(mul(g.y, dd), mul(l.y, w_reg)),
+                             add(mul(g.z, dd), mul(l.z, w_reg)), 0.f);
+    }
+}
+
+// convolution_{rows,columns,depth}_kernel, solver.cu:237-446 (AoS, clamp-to-edge) -- test API
+struct Taps { float S[7]; };
+__global__ void sobolev_filter_kernel(float4 *__restrict__ dst, const float4 *__restrict__ src, Taps tp, Dims d) {
+    int x, y, z;
+    if (!voxel_of_thread(d, x, y, z)) return;
+    const size_t sy = d.X, sz = (size_t)d.X * d.Y;
+    float ax[3] = {0.f, 0.f, 0.f}, ay[3] = {0.f, 0.f, 0.f}, az[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = -3; j <= 3; ++j) {
+        const float s = tp.S[3 - j];
+        const int xx = min(max(x + j, 0), d.X - 1), yy = min(max(y + j, 0), d.Y - 1), zz = min(max(z + j, 0), d.Z - 1);
+        const float4 a = src[xx + sy * y + sz * z], b = src[x + sy * yy + sz * z], c = src[x + sy * y + sz * zz];
+        ax[0] = add(ax[0], mul(s, a.x)); ax[1] = add(ax[1], mul(s, a.y)); ax[2] = add(ax[2], mul(s, a.z));
+        ay[0] = add(ay[0], mul(s, b.x)); ay[1] = add(ay[1], mul(s, b.y)); ay[2] = add(ay[2], mul(s, b.z));
+        az[0] = add(az[0], mul(s, c.x)); az[1] = add(az[1], mul(s, c.y)); az[2] = add(az[2], mul(s, c.z));
+    }
+    dst[x + sy * y + sz * z] = make_float4(add(add(ax[0], ay[0]), az[0]), add(add(ax[1], ay[1]), az[1]),
+                                           add(add(ax[2], ay[2]), az[2]), 0.f);
+}
+
+// update_psi_kernel, solver.cu:53-69
+__global__ void update_psi_kernel(float4 *__restrict__ psi, const float4 *__restrict__ g, float4 *__restrict__ upd,
+                                  float alpha, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = g[i];
+        const float4 u = make_float4(mul(v.x, alpha), mul(v.y, alpha), mul(v.z, alpha), 0.f);
+        upd[i] = u;
+        float4 p = psi[i];
+        p.x = sub(p.x, u.x); p.y = sub(p.y, u.y); p.z = sub(p.z, u.z);
+        psi[i] = p;
+    }
+}
+
+// reductions: value semantics of reductor.cu; summation in double (the reference's fp32 tree order is not reproduced,
+// see DESIGN.md "Energies")
+__global__ void data_energy_kernel(const float2 *__restrict__ a, const float2 *__restrict__ b, size_t n, double *out) {
+    double s = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float dd = sub(a[i].x, b[i].x);
+        s += (double)dd * (double)dd;
+    }
+    s = warp_sum_f64(s);
+    __shared__ double sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0; for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += sm[k]; atomicAdd(out, t); }
+}
+__global__ void reg_energy_kernel(const float4 *__restrict__ J, size_t n, double *out) {
+    double s = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float4 v = J[4 * i + r];
+            const float nsq = add(add(mul(v.x, v.x), mul(v.y, v.y)), mul(v.z, v.z));
+            acc = (r == 0) ? nsq : add(acc, nsq);
+        }
+        s += (double)acc;
+    }
+    s = warp_sum_f64(s);
+    __shared__ double sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0; for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += sm[k]; atomicAdd(out, t); }
+}
+__global__ void max_norm_kernel(const float4 *__restrict__ u, size_t n, RankMap rm, unsigned long long *out) {
+    unsigned long long key = 0ull;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = u[i];
+        // the reference compares norms, i.e. __fsqrt_rd of the sum of squares (utils.hpp:279-281)
+        const float nr = __fsqrt_rd(add(add(mul(v.x, v.x), mul(v.y, v.y)), mul(v.z, v.z)));
+        const unsigned long long k = ((unsigned long long)__float_as_uint(nr) << 32) |
+                                     (unsigned long long)(0xffffffffu - rank_of((unsigned)i, rm));
+        if (nr > 0.f && k > key) key = k;
+    }
+    key = warp_max_u64(key);
+    __shared__ unsigned long long sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned long long m = 0; for (int k = 0; k < (int)(blockDim.x >> 5); ++k) m = sm[k] > m ? sm[k] : m; atomicMax(out, m); }
+}
+}  // namespace
+
+static int sgrid(size_t n) { size_t b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b ? b : 1)); }
+
+void launch_init_identity(float4 *psi, Dims d, cudaStream_t st) { init_identity_kernel<<<grid3(d), block3(), 0, st>>>(psi, d); }
+void launch_apply(const float2 *phi, float2 *out, const float4 *psi, Dims d, cudaStream_t st) {
+    apply_kernel<<<grid3(d), block3(), 0, st>>>(phi, out, psi, d);
+}
+void launch_estimate_inverse(const float4 *psi, float4 *psi_inv, Dims d, int iters, bool from_identity, cudaStream_t st) {
+    estimate_inverse_kernel<<<grid3(d), block3(), 0, st>>>(psi, psi_inv, d, iters, from_identity ? 1 : 0);
+}
+void launch_tsdf_gradient(const float2 *phi, float4 *grad, Dims d, cudaStream_t st) { tsdf_gradient_kernel<<<grid3(d), block3(), 0, st>>>(phi, grad, d); }
+void launch_laplacian(const float4 *psi, float4 *L, Dims d, cudaStream_t st) { laplacian_kernel<<<grid3(d), block3(), 0, st>>>(psi, L, d); }
+void launch_jacobian(const float4 *psi, float4 *J, Dims d, int mode, cudaStream_t st) { jacobian_kernel<<<grid3(d), block3(), 0, st>>>(psi, J, d, mode); }
+void launch_potential_gradient(const float2 *pnp, const float2 *pg, const float4 *grad, const float4 *L, float4 *out,
+                               float w_reg, size_t n, cudaStream_t st) {
+    potential_gradient_kernel<<<sgrid(n), 256, 0, st>>>(pnp, pg, grad, L, out, w_reg, n);
+}
+void launch_sobolev_filter(float4 *dst, const float4 *src, const float *taps7, Dims d, cudaStream_t st) {
+    Taps t;
+    for (int i = 0; i < 7; ++i) t.S[i] = taps7[i];
+    sobolev_filter_kernel<<<grid3(d), block3(), 0, st>>>(dst, src, t, d);
+}
+void launch_update_psi(float4 *psi, const float4 *g, float4 *upd, float alpha, size_t n, cudaStream_t st) {
+    update_psi_kernel<<<sgrid(n), 256, 0, st>>>(psi, g, upd, alpha, n);
+}
+void launch_data_energy(const float2 *a, const float2 *b, size_t n, double *out, cudaStream_t st) { data_energy_kernel<<<sgrid(n), 256, 0, st>>>(a, b, n, out); }
+void launch_reg_energy(const float4 *J, size_t n, double *out, cudaStream_t st) { reg_energy_kernel<<<sgrid(n), 256, 0, st>>>(J, n, out); }
+void launch_max_norm(const float4 *u, size_t n, RankMap rm, unsigned long long *out, cudaStream_t st) { max_norm_kernel<<<sgrid(n), 256, 0, st>>>(u, n, rm, out); }
+
+}  // namespace sb

@@ -1,0 +1,242 @@
+// solver_generic.cu -- shape-agnostic (any X,Y,Z) kernels of the gradient-descent loop: one thread per voxel.
+// They define the loop's data flow and serve as the in-library baseline for the tiled/TMA kernels, which must
+// produce identical bits.  Reference semantics cited per kernel (file:line in dgrzech/sobfu).
+#include "solver_kernels.cuh"
+
+namespace sb {
+
+namespace {
+constexpr int BX = 32, BY = 4, BZ = 2;   // 256 threads, x fastest
+
+SB_DEV bool voxel_of_thread(const Dims d, int &x, int &y, int &z) {
+    x = blockIdx.x * BX + threadIdx.x;
+    y = blockIdx.y * BY + threadIdx.y;
+    z = blockIdx.z * BZ + threadIdx.z;
+    return x < d.X && y < d.Y && z < d.Z;
+}
+inline dim3 grid_for(const Dims d) { return dim3((d.X + BX - 1) / BX, (d.Y + BY - 1) / BY, (d.Z + BZ - 1) / BZ); }
+
+// ---- prologue: AoS -> planes -------------------------------------------------------------------------------
+__global__ void unpack_kernel(const float4 *__restrict__ psi, const float2 *__restrict__ phi_global,
+                              const float2 *__restrict__ phi_n, LoopArgs a) {
+    const size_t n = (size_t)a.d.X * a.d.Y * a.d.Z;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 p = psi[i];
+        a.px[i] = p.x; a.py[i] = p.y; a.pz[i] = p.z;
+        const_cast<float *>(a.pg)[i] = phi_global[i].x;
+        const_cast<float *>(a.pn)[i] = phi_n[i].x;
+    }
+}
+
+// phi_n o psi before the first iteration (solver.cu:106 -> apply_kernel, vector_fields.cu:81-100)
+__global__ void initial_warp_kernel(LoopArgs a) {
+    const size_t n = (size_t)a.d.X * a.d.Y * a.d.Z;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const TriCoord t = tri_coord(a.px[i], a.py[i], a.pz[i], a.d);
+        a.w[i] = sample_scalar<1>(a.pn, t, a.d);
+    }
+}
+
+// ---- pass A: nabla_U = (phi_n_psi - phi_global) * grad(phi_n_psi) + w_reg * L(psi) ---------------------------
+//   grad : TsdfDifferentiator::operator(), vector_fields.cu:157-208 (axis term 0 on that axis' boundary planes)
+//   L    : SecondOrderDifferentiator::laplacian, vector_fields.cu:291-337 (both neighbours = self on a boundary)
+//   comb : calculate_potential_gradient_kernel, solver.cu:15-33
+// When `log` is set it also accumulates the data energy (reductor.cu:11-112) and the regulariser energy of the
+// displacement Jacobian (vector_fields.cu:415-472 mode 1 + reductor.cu:114-214) in double precision.
+SB_DEV float lap_comp(const float *__restrict__ p, size_t i, size_t ixa, size_t ixb, size_t iya, size_t iyb,
+                      size_t iza, size_t izb) {
+    float v = mul(p[i], -6.f);
+    v = add(v, p[ixa]); v = add(v, p[ixb]);
+    v = add(v, p[iya]); v = add(v, p[iyb]);
+    v = add(v, p[iza]); v = add(v, p[izb]);
+    return mul(v, -1.f);
+}
+
+template <bool LOG>
+__global__ void __launch_bounds__(BX *BY *BZ) pass_a_generic_kernel(LoopArgs a, int it) {
+    if (loop_finished(a, it)) {
+        if (a.check && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0 && threadIdx.y == 0 &&
+            threadIdx.z == 0 && !a.state->converged) {
+            a.state->iters = it;
+            a.state->converged = 1;
+        }
+        return;
+    }
+    int x, y, z;
+    const bool in = voxel_of_thread(a.d, x, y, z);
+    double ed = 0.0, er = 0.0;
+    if (in) {
+        const Dims d = a.d;
+        const size_t sy = (size_t)d.X, sz = (size_t)d.X * d.Y;
+        const size_t i = x + sy * y + sz * z;
+        const bool bx = (x == 0 || x == d.X - 1), by = (y == 0 || y == d.Y - 1), bz = (z == 0 || z == d.Z - 1);
+        // neighbour indices for the central differences (mirror onto the in-range neighbour at a boundary)
+        const size_t gxa = (x == d.X - 1) ? i - 1 : i + 1, gxb = (x == 0) ? i + 1 : i - 1;
+        const size_t gya = (y == d.Y - 1) ? i - sy : i + sy, gyb = (y == 0) ? i + sy : i - sy;
+        const size_t gza = (z == d.Z - 1) ? i - sz : i + sz, gzb = (z == 0) ? i + sz : i - sz;
+        // neighbour indices for the Laplacian (self on a boundary plane)
+        const size_t lxa = bx ? i : i + 1, lxb = bx ? i : i - 1;
+        const size_t lya = by ? i : i + sy, lyb = by ? i : i - sy;
+        const size_t lza = bz ? i : i + sz, lzb = bz ? i : i - sz;
+
+        const float wv = a.w[i];
+        const float diff = sub(wv, a.pg[i]);
+        // d.X == 1 would make gxa/gxb point outside; volumes are at least 2 voxels wide on every axis
+        const float nx = mul(sub(a.w[gxa], a.w[gxb]), 0.5f);   // __fdividef(., 2.f)
+        const float ny = mul(sub(a.w[gya], a.w[gyb]), 0.5f);
+        const float nz = mul(sub(a.w[gza], a.w[gzb]), 0.5f);
+        const float Lx = lap_comp(a.px, i, lxa, lxb, lya, lyb, lza, lzb);
+        const float Ly = lap_comp(a.py, i, lxa, lxb, lya, lyb, lza, lzb);
+        const float Lz = lap_comp(a.pz, i, lxa, lxb, lya, lyb, lza, lzb);
+        const float ux = add(mul(nx, diff), mul(Lx, a.w_reg));
+        const float uy = add(mul(ny, diff), mul(Ly, a.w_reg));
+        const float uz = add(mul(nz, diff), mul(Lz, a.w_reg));
+
+        // store with a replicated halo (clamp-to-edge of the filter, solver.cu:256,263,270)
+        const GLayout gl = a.gl;
+        const size_t o = gl.at(x, y, z);
+        a.gx[o] = ux; a.gy[o] = uy; a.gz[o] = uz;
+        // every boundary voxel replicates itself three cells outwards along the axes it bounds
+#define SB_HALO(cond, stride)                                                                                   \
+    if (cond) {                                                                                                 \
+        _Pragma("unroll") for (int k = 1; k <= 3; ++k) {                                                        \
+            a.gx[o + (stride) * k] = ux; a.gy[o + (stride) * k] = uy; a.gz[o + (stride) * k] = uz;              \
+        }                                                                                                       \
+    }
+        SB_HALO(x == 0, -1L) SB_HALO(x == d.X - 1, 1L)
+        SB_HALO(y == 0, -(long)gl.PX) SB_HALO(y == d.Y - 1, (long)gl.PX)
+        SB_HALO(z == 0, -(long)gl.plane) SB_HALO(z == d.Z - 1, (long)gl.plane)
+#undef SB_HALO
+
+        if (LOG) {
+            ed = (double)diff * (double)diff;
+            // displacement Jacobian: get_displacement subtracts the neighbour's own coordinates (vector_fields.cu:24-26)
+            const float *P[3] = {a.px, a.py, a.pz};
+            const int cxa = (x == d.X - 1) ? x - 1 : x + 1, cxb = (x == 0) ? x + 1 : x - 1;
+            const int cya = (y == d.Y - 1) ? y - 1 : y + 1, cyb = (y == 0) ? y + 1 : y - 1;
+            const int cza = (z == d.Z - 1) ? z - 1 : z + 1, czb = (z == 0) ? z + 1 : z - 1;
+            float rows = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float ox_a = (c == 0) ? (float)cxa : (c == 1 ? (float)y : (float)z);
+                const float ox_b = (c == 0) ? (float)cxb : (c == 1 ? (float)y : (float)z);
+                const float oy_a = (c == 0) ? (float)x : (c == 1 ? (float)cya : (float)z);
+                const float oy_b = (c == 0) ? (float)x : (c == 1 ? (float)cyb : (float)z);
+                const float oz_a = (c == 0) ? (float)x : (c == 1 ? (float)y : (float)cza);
+                const float oz_b = (c == 0) ? (float)x : (c == 1 ? (float)y : (float)czb);
+                const float jx = mul(sub(sub(P[c][gxa], ox_a), sub(P[c][gxb], ox_b)), 0.5f);
+                const float jy = mul(sub(sub(P[c][gya], oy_a), sub(P[c][gyb], oy_b)), 0.5f);
+                const float jz = mul(sub(sub(P[c][gza], oz_a), sub(P[c][gzb], oz_b)), 0.5f);
+                const float nsq = add(add(mul(jx, jx), mul(jy, jy)), mul(jz, jz));   // norm_sq, utils.hpp:283-285
+                rows = (c == 0) ? nsq : add(rows, nsq);
+            }
+            er = (double)rows;
+        }
+    }
+    if (LOG) {
+        __shared__ double sd[BX * BY * BZ / 32], sr[BX * BY * BZ / 32];
+        const int tid = threadIdx.x + BX * (threadIdx.y + BY * threadIdx.z);
+        ed = warp_sum_f64(ed); er = warp_sum_f64(er);
+        if ((tid & 31) == 0) { sd[tid >> 5] = ed; sr[tid >> 5] = er; }
+        __syncthreads();
+        if (tid == 0) {
+            double td = 0.0, tr = 0.0;
+            for (int k = 0; k < BX * BY * BZ / 32; ++k) { td += sd[k]; tr += sr[k]; }
+            atomicAdd(&a.e_data[it], td);
+            atomicAdd(&a.e_reg[it], tr);
+        }
+    }
+}
+
+// ---- pass B: Sobolev filter + psi update + max-norm partials + re-warp ---------------------------------------
+//   filter : convolution_{rows,columns,depth}_kernel, solver.cu:237-446:  (S*x g + S*y g) + S*z g, taps
+//            S[KERNEL_RADIUS - j], j = -3..3, each sum started from 0 with un-fused mul/add
+//   update : update_psi_kernel, solver.cu:53-69
+//   max    : reduce_max_kernel + final_reduce_max, reductor.cu:342-456, reductor.cpp:81-94
+//   warp   : apply_kernel, vector_fields.cu:81-100 (solver.cu:168)
+SB_DEV float tap7(const float *__restrict__ g, size_t o, long stride, const float (&S)[7]) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = -3; j <= 3; ++j) s = add(s, mul(S[3 - j], g[o + (long)j * stride]));
+    return s;
+}
+
+__global__ void __launch_bounds__(BX *BY *BZ) pass_b_generic_kernel(LoopArgs a, int it) {
+    if (loop_finished(a, it)) return;
+    int x, y, z;
+    const bool in = voxel_of_thread(a.d, x, y, z);
+    unsigned long long key = 0ull;
+    if (in) {
+        const Dims d = a.d;
+        const size_t i = x + (size_t)d.X * y + (size_t)d.X * d.Y * z;
+        const GLayout gl = a.gl;
+        const size_t o = gl.at(x, y, z);
+        const long sy = gl.PX, sz = (long)gl.plane;
+        const float fx = add(add(tap7(a.gx, o, 1, a.S), tap7(a.gx, o, sy, a.S)), tap7(a.gx, o, sz, a.S));
+        const float fy = add(add(tap7(a.gy, o, 1, a.S), tap7(a.gy, o, sy, a.S)), tap7(a.gy, o, sz, a.S));
+        const float fz = add(add(tap7(a.gz, o, 1, a.S), tap7(a.gz, o, sy, a.S)), tap7(a.gz, o, sz, a.S));
+        const float ux = mul(fx, a.alpha), uy = mul(fy, a.alpha), uz = mul(fz, a.alpha);
+        const float npx = sub(a.px[i], ux), npy = sub(a.py[i], uy), npz = sub(a.pz[i], uz);
+        a.px[i] = npx; a.py[i] = npy; a.pz[i] = npz;
+        const float nsq = add(add(mul(ux, ux), mul(uy, uy)), mul(uz, uz));
+        key = ((unsigned long long)__float_as_uint(nsq) << 32) | (unsigned long long)(0xffffffffu - rank_of((unsigned)i, a.rm));
+        // NaN/negative never occur for a sum of squares; -0 cannot occur either
+        const TriCoord t = tri_coord(npx, npy, npz, d);
+        a.w[i] = sample_scalar<1>(a.pn, t, d);
+    }
+    __shared__ unsigned long long sk[BX * BY * BZ / 32];
+    const int tid = threadIdx.x + BX * (threadIdx.y + BY * threadIdx.z);
+    key = warp_max_u64(key);
+    if ((tid & 31) == 0) sk[tid >> 5] = key;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long m = 0ull;
+        for (int k = 0; k < BX * BY * BZ / 32; ++k) m = sk[k] > m ? sk[k] : m;
+        atomicMax(&a.maxkey[it], m);
+    }
+}
+
+// ---- epilogue: planes -> AoS ---------------------------------------------------------------------------------
+// psi.w is preserved (update_psi_kernel never writes it); phi_n_psi = {warped tsdf, weight of the floor voxel}
+// (utils.hpp:83).
+__global__ void pack_kernel(float4 *__restrict__ psi, float2 *__restrict__ phi_n_psi, const float2 *__restrict__ phi_n,
+                            LoopArgs a) {
+    const size_t n = (size_t)a.d.X * a.d.Y * a.d.Z;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float x = a.px[i], y = a.py[i], z = a.pz[i];
+        float4 p = psi[i];
+        p.x = x; p.y = y; p.z = z;
+        psi[i] = p;
+        const TriCoord t = tri_coord(x, y, z, a.d);
+        const float wgt = phi_n[(size_t)t.gx + (size_t)a.d.X * ((size_t)t.gy + (size_t)a.d.Y * t.gz)].y;
+        phi_n_psi[i] = make_float2(a.w[i], wgt);
+    }
+}
+}  // namespace
+
+static int stream_grid(size_t n) {
+    size_t b = (n + 255) / 256;
+    return (int)(b > 148 * 16 ? 148 * 16 : b);
+}
+
+void launch_unpack(const float4 *psi, const float2 *phi_global, const float2 *phi_n, const LoopArgs &a, cudaStream_t st) {
+    const size_t n = (size_t)a.d.X * a.d.Y * a.d.Z;
+    unpack_kernel<<<stream_grid(n), 256, 0, st>>>(psi, phi_global, phi_n, a);
+}
+void launch_initial_warp(const LoopArgs &a, cudaStream_t st) {
+    const size_t n = (size_t)a.d.X * a.d.Y * a.d.Z;
+    initial_warp_kernel<<<stream_grid(n), 256, 0, st>>>(a);
+}
+void launch_pass_a_generic(const LoopArgs &a, int it, int log, cudaStream_t st) {
+    if (log) pass_a_generic_kernel<true><<<grid_for(a.d), dim3(BX, BY, BZ), 0, st>>>(a, it);
+    else pass_a_generic_kernel<false><<<grid_for(a.d), dim3(BX, BY, BZ), 0, st>>>(a, it);
+}
+void launch_pass_b_generic(const LoopArgs &a, int it, cudaStream_t st) {
+    pass_b_generic_kernel<<<grid_for(a.d), dim3(BX, BY, BZ), 0, st>>>(a, it);
+}
+void launch_pack(float4 *psi, float2 *phi_n_psi, const float2 *phi_n, const LoopArgs &a, cudaStream_t st) {
+    const size_t n = (size_t)a.d.X * a.d.Y * a.d.Z;
+    pack_kernel<<<stream_grid(n), 256, 0, st>>>(psi, phi_n_psi, phi_n, a);
+}
+
+}  // namespace sb

@@ -1,0 +1,77 @@
+// solver_kernels.cuh -- device-side state and kernel launch prototypes of the solver loop.
+//
+// Workspace layout in HBM (DESIGN.md "Data layout"): the loop never touches the reference's float4 / float2
+// AoS volumes.  Per voxel it keeps
+//     psi      3 float planes  (px, py, pz)                     12 B   read by A, read+written by B
+//     w        1 float plane   (phi_n o psi).x                   4 B   read by A, written by B
+//     pg, pn   2 float planes  phi_global.x, phi_n.x            8 B   pg read by A, pn gathered by B
+//     g        3 float planes  nabla_U, padded by a replicated halo of 3 (4 along x for 16 B alignment)
+// = 36 B/voxel of scratch against the reference's 240 B.
+#pragma once
+#include "common.cuh"
+
+namespace sb {
+
+// padded layout of the nabla_U planes
+struct GLayout {
+    int PX, PY, PZ;        // padded extents: X+8, Y+6, Z+6
+    size_t plane;          // PX*PY
+    size_t total;          // PX*PY*PZ floats per component
+    __host__ __device__ size_t at(int x, int y, int z) const {
+        return (size_t)(x + 4) + (size_t)PX * ((size_t)(y + 3) + (size_t)PY * (size_t)(z + 3));
+    }
+};
+
+struct LoopState {            // lives in device memory, one per solver
+    int converged;            // sticky: set once an iteration's max update norm <= threshold
+    int iters;                // number of iterations executed when converged was set
+    int pad[2];
+};
+
+struct LoopArgs {
+    // planes
+    float *px, *py, *pz, *w;
+    const float *pg, *pn;
+    float *gx, *gy, *gz;
+    Dims d;
+    GLayout gl;
+    // parameters
+    float S[7];
+    float alpha, w_reg, thr;
+    // convergence / logging
+    LoopState *state;
+    unsigned long long *maxkey;   // [max_iter]
+    double *e_data, *e_reg;       // [max_iter] (sums, not yet halved)
+    RankMap rm;
+    int check;                    // 0: time_loop mode (no convergence logic)
+};
+
+// decision shared by every block of iteration `it` (0-based): has the loop already ended?
+SB_DEV bool loop_finished(const LoopArgs &a, int it) {
+    if (!a.check) return false;
+    if (a.state->converged) return true;
+    if (it == 0) return false;
+    const float s = __uint_as_float((unsigned)(a.maxkey[it - 1] >> 32));
+    return __fsqrt_rd(s) <= a.thr;      // norm = __fsqrt_rd(sum of squares), utils.hpp:279-281
+}
+
+void launch_unpack(const float4 *psi, const float2 *phi_global, const float2 *phi_n, const LoopArgs &a, cudaStream_t st);
+void launch_initial_warp(const LoopArgs &a, cudaStream_t st);
+void launch_pass_a_generic(const LoopArgs &a, int it, int log, cudaStream_t st);
+void launch_pass_b_generic(const LoopArgs &a, int it, cudaStream_t st);
+void launch_pack(float4 *psi, float2 *phi_n_psi, const float2 *phi_n, const LoopArgs &a, cudaStream_t st);
+
+// tiled kernels (pass_a_tiled.cu / pass_b_tma.cu); return false when the shape is not supported
+bool tiled_supported(const Dims d);
+void launch_pass_a_tiled(const LoopArgs &a, int it, int log, cudaStream_t st);
+struct TmaMaps;   // opaque: three CUtensorMap (one per nabla_U component)
+TmaMaps *tma_maps_create(const LoopArgs &a);
+void tma_maps_destroy(TmaMaps *m);
+void launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, cudaStream_t st);
+
+// free-standing field kernels (field_ops.cu)
+void launch_init_identity(float4 *psi, Dims d, cudaStream_t st);
+void launch_apply(const float2 *phi, float2 *out, const float4 *psi, Dims d, cudaStream_t st);
+void launch_estimate_inverse(const float4 *psi, float4 *psi_inv, Dims d, int iters, bool from_identity, cudaStream_t st);
+
+}  // namespace sb

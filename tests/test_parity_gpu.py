@@ -1,0 +1,220 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (via the reference-shaped host classes), against the
+CPU oracle on identical seeded inputs.  Bit-exact on the solver core (tolerance stated where approximate units are used)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests.common import assert_bits, f32, random_field, sphere_pair, wavy_psi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env(built):
+    import torch
+    import sobfu_b200 as sf
+    from oracle import pyoracle as orc
+    assert torch.cuda.is_available()
+    return sf, orc, torch
+
+
+def dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+DIMS = [(32, 32, 32), (20, 17, 13), (64, 24, 40)]
+
+
+@pytest.mark.parametrize("dims", DIMS)
+def test_field_ops_bit_exact(env, dims):
+    sf, orc, torch = env
+    from sobfu_b200._capi import check, lib
+    L = lib()
+    X, Y, Z = dims
+    pg, pn, vs, trunc, eta = sphere_pair(dims)
+    psi = wavy_psi(dims)
+    d_psi, d_pn, d_pg = dev(torch, psi), dev(torch, pn), dev(torch, pg)
+
+    # identity (DeformationFieldTest.ClearTest, deformation_field_test.cpp:92-108)
+    t = torch.empty((Z, Y, X, 4), dtype=torch.float32, device="cuda")
+    check(L.sobfu_b200_init_identity(ptr(t), X, Y, Z))
+    assert_bits(t.cpu().numpy(), orc.init_identity(X, Y, Z), "init_identity")
+
+    # warp
+    out = torch.empty_like(d_pn)
+    check(L.sobfu_b200_apply(ptr(d_pn), ptr(out), ptr(d_psi), X, Y, Z))
+    warped = orc.apply(pn, psi)
+    assert_bits(out.cpu().numpy(), warped, "apply")
+
+    # gradient / laplacian / jacobian (both modes)
+    g = torch.empty((Z, Y, X, 4), dtype=torch.float32, device="cuda")
+    check(L.sobfu_b200_tsdf_gradient(ptr(out), ptr(g), X, Y, Z))
+    grad = orc.tsdf_gradient(warped)
+    assert_bits(g.cpu().numpy(), grad, "tsdf_gradient")
+    l = torch.empty_like(g)
+    check(L.sobfu_b200_laplacian(ptr(d_psi), ptr(l), X, Y, Z))
+    lap = orc.laplacian(psi)
+    assert_bits(l.cpu().numpy(), lap, "laplacian")
+    for mode in (0, 1):
+        J = torch.zeros((Z, Y, X, 4, 4), dtype=torch.float32, device="cuda")
+        check(L.sobfu_b200_jacobian(ptr(d_psi), ptr(J), X, Y, Z, mode))
+        assert_bits(J.cpu().numpy(), orc.jacobian(psi, mode), "jacobian mode %d" % mode)
+
+    # potential gradient, filter, update, max norm
+    nu = torch.empty_like(g)
+    check(L.sobfu_b200_potential_gradient(ptr(out), ptr(d_pg), ptr(g), ptr(l), ptr(nu), f32(0.4), X, Y, Z))
+    nabla_u = orc.potential_gradient(warped, pg, grad, lap, 0.4)
+    assert_bits(nu.cpu().numpy(), nabla_u, "potential_gradient")
+    taps = orc.sobolev_taps(7, 0.1)
+    nus = torch.empty_like(g)
+    check(L.sobfu_b200_sobolev_filter(ptr(nus), ptr(nu), taps.ctypes.data_as(C.POINTER(C.c_float)), X, Y, Z))
+    nabla_us = orc.sobolev_filter(nabla_u, taps)
+    assert_bits(nus.cpu().numpy(), nabla_us, "sobolev_filter")
+    upd = torch.empty_like(g)
+    psi2 = d_psi.clone()
+    check(L.sobfu_b200_update_psi(ptr(psi2), ptr(nus), ptr(upd), f32(0.01), X, Y, Z))
+    psi_o = psi.copy()
+    upd_o = orc.update_psi(psi_o, nabla_us, 0.01)
+    assert_bits(psi2.cpu().numpy(), psi_o, "update_psi psi")
+    assert_bits(upd.cpu().numpy(), upd_o, "update_psi updates")
+    v, i_f, i = C.c_float(), C.c_float(), C.c_longlong()
+    check(L.sobfu_b200_max_update_norm(ptr(upd), X * Y * Z, C.byref(v), C.byref(i_f), C.byref(i)))
+    ov, oi = orc.max_update_norm(upd_o)
+    assert v.value == ov and i_f.value == oi, (v.value, ov, i_f.value, oi)
+
+    # inverse (from identity, 48 steps) and energies
+    inv = torch.empty_like(d_psi)
+    check(L.sobfu_b200_init_identity(ptr(inv), X, Y, Z))
+    check(L.sobfu_b200_estimate_inverse(ptr(d_psi), ptr(inv), X, Y, Z, 48))
+    assert_bits(inv.cpu().numpy(), orc.estimate_inverse(psi, orc.init_identity(X, Y, Z), 48), "estimate_inverse")
+    e = C.c_float()
+    check(L.sobfu_b200_data_energy(ptr(d_pg), ptr(out), X * Y * Z, C.byref(e)))
+    assert e.value == pytest.approx(orc.data_energy(pg, warped), rel=2e-5)   # fp32 tree (reference) vs double sum
+    J1 = torch.zeros((Z, Y, X, 4, 4), dtype=torch.float32, device="cuda")
+    check(L.sobfu_b200_jacobian(ptr(d_psi), ptr(J1), X, Y, Z, 1))
+    check(L.sobfu_b200_reg_energy(ptr(J1), X * Y * Z, C.byref(e)))
+    assert e.value == pytest.approx(orc.reg_energy(orc.jacobian(psi, 1)), rel=2e-5)
+
+
+def test_max_norm_ties_follow_reference_order(env):
+    """equal norms: the reference keeps the first voxel in its (block, tid, pass, half) traversal order"""
+    sf, orc, torch = env
+    from sobfu_b200._capi import check, lib
+    n = 5000
+    u = np.zeros((n, 4), dtype=f32)
+    u[[700, 188, 1212, 1024 + 5, 4099]] = (0.5, 0.25, 0.125, 0)
+    d = dev(torch, u)
+    v, i_f, i = C.c_float(), C.c_float(), C.c_longlong()
+    check(lib().sobfu_b200_max_update_norm(ptr(d), n, C.byref(v), C.byref(i_f), C.byref(i)))
+    ov, oi = orc.max_update_norm(u)
+    assert (v.value, i_f.value) == (ov, oi)
+    assert i.value == int(oi)
+
+
+def run_solver(sf, torch, dims, pg, pn, psi0, vs, trunc, eta, max_iter, thr, alpha, w_reg, verbosity=0, variant=0, lam=0.1):
+    p = sf.Params(volume_dims=dims, volume_size=tuple(float(vs[i]) * dims[i] for i in range(3)), max_iter=max_iter,
+                  max_update_norm=thr, s=7, lambda_=lam, alpha=alpha, w_reg=w_reg, verbosity=verbosity, tsdf_max_weight=64.0,
+                  tsdf_trunc_dist=float(trunc), eta=float(eta))
+    vol = [sf.TsdfVolume(p) for _ in range(4)]
+    vol[0].data().copy_(torch.from_numpy(pg))
+    vol[2].data().copy_(torch.from_numpy(pn))
+    psi, psi_inv = sf.DeformationField(dims), sf.DeformationField(dims)
+    psi.get_data().copy_(torch.from_numpy(psi0))
+    solver = sf.Solver(p)
+    if variant:
+        solver.set_variant(variant)
+    info = solver.estimate_psi(vol[0], vol[1], vol[2], vol[3], psi, psi_inv)
+    return dict(info=info, log=solver.get_log(), psi=psi.get_data().cpu().numpy(), psi_inv=psi_inv.get_data().cpu().numpy(),
+                phi_n_psi=vol[3].data().cpu().numpy(), phi_global_psi_inv=vol[1].data().cpu().numpy(), solver=solver,
+                vols=vol, psi_t=psi, psi_inv_t=psi_inv)
+
+
+def compare_solver(got, want, what):
+    assert got["info"].iters == want["iters"], (what, got["info"].iters, want["iters"])
+    assert got["info"].converged == want["converged"]
+    for k in ("psi", "phi_n_psi", "psi_inv", "phi_global_psi_inv"):
+        assert_bits(got[k], want[k], "%s: %s" % (what, k))
+    assert got["info"].max_norm == want["max_norm"]
+    for it, (mx, idx, ed, er) in enumerate(got["log"]):
+        assert mx == want["log"][it][0], (what, it, mx, want["log"][it][0])
+        assert idx == want["log"][it][1], (what, it, idx, want["log"][it][1])
+
+
+@pytest.mark.parametrize("dims,iters", [((32, 32, 32), 5), ((20, 17, 13), 7), ((64, 64, 64), 12)])
+def test_solver_matches_oracle_bit_exact(env, dims, iters):
+    """BASELINE config 1 (32^3, 5 iterations) plus an odd-sized and the reference fixtures' 64^3 volume"""
+    sf, orc, torch = env
+    pg, pn, vs, trunc, eta = sphere_pair(dims)
+    psi0 = orc.init_identity(*dims)
+    want = orc.estimate_psi(pg, pn, psi0, iters, -1.0, 7, 0.1, 0.01, 0.4, log_energies=2)
+    got = run_solver(sf, torch, dims, pg, pn, psi0, vs, trunc, eta, iters, -1.0, 0.01, 0.4, verbosity=2)
+    compare_solver(got, want, "solver %s" % (dims,))
+    for it, (mx, idx, ed, er) in enumerate(got["log"]):   # energies: fp32 tree vs double accumulation
+        assert ed == pytest.approx(want["log"][it][2], rel=2e-5, abs=1e-6)
+        assert er == pytest.approx(want["log"][it][3], rel=2e-5, abs=1e-6)
+
+
+def test_solver_warm_start_and_all_lambdas(env):
+    """SolverTest.SerialAlignmentTest style (solver_test.cpp:162-208): psi is warm-started; every tabulated lambda"""
+    sf, orc, torch = env
+    dims = (24, 24, 24)
+    pg, pn, vs, trunc, eta = sphere_pair(dims)
+    psi0 = wavy_psi(dims, amp=0.3)
+    for lam in (0.05, 0.1, 0.2, 0.4):
+        want = orc.estimate_psi(pg, pn, psi0, 4, -1.0, 7, lam, 0.02, 0.2)
+        got = run_solver(sf, torch, dims, pg, pn, psi0, vs, trunc, eta, 4, -1.0, 0.02, 0.2, lam=lam)
+        compare_solver(got, want, "lambda %g" % lam)
+
+
+def test_solver_converges_at_the_same_iteration(env):
+    """max_update_norm reached mid-way: the loop must stop exactly where the reference's per-iteration test stops it
+    (solver.cu:183), including across the host's chunk boundary (64 iterations)"""
+    sf, orc, torch = env
+    dims = (16, 16, 16)
+    pg, pn, vs, trunc, eta = sphere_pair(dims, shift=0.004)
+    psi0 = orc.init_identity(*dims)
+    probe = orc.estimate_psi(pg, pn, psi0, 100, -1.0, 7, 0.1, 0.05, 0.4)
+    for stop_after in (3, 70):
+        thr = float(probe["log"][stop_after - 1][0])
+        want = orc.estimate_psi(pg, pn, psi0, 100, thr, 7, 0.1, 0.05, 0.4)
+        assert want["converged"] == 1 and want["iters"] <= stop_after
+        got = run_solver(sf, torch, dims, pg, pn, psi0, vs, trunc, eta, 100, thr, 0.05, 0.4)
+        compare_solver(got, want, "early stop %d" % stop_after)
+
+
+def test_solver_zero_iterations_and_rejects_bad_filter(env):
+    sf, orc, torch = env
+    dims = (16, 16, 16)
+    pg, pn, vs, trunc, eta = sphere_pair(dims)
+    psi0 = wavy_psi(dims, amp=0.2)
+    want = orc.estimate_psi(pg, pn, psi0, 0, -1.0, 7, 0.1, 0.05, 0.4)
+    got = run_solver(sf, torch, dims, pg, pn, psi0, vs, trunc, eta, 0, -1.0, 0.05, 0.4)
+    for k in ("psi", "phi_n_psi", "psi_inv", "phi_global_psi_inv"):
+        assert_bits(got[k], want[k], "zero iterations: " + k)
+    with pytest.raises(sf.Sobfu200Error):   # the reference would run with uninitialised taps (solver.cpp:160-251)
+        sf.Solver(sf.Params(volume_dims=dims, max_iter=1, s=7, lambda_=0.3))
+    with pytest.raises(sf.Sobfu200Error):
+        sf.Solver(sf.Params(volume_dims=dims, max_iter=1, s=9, lambda_=0.1))
+
+
+def test_host_buffer_entry_point(env):
+    sf, orc, torch = env
+    dims = (32, 32, 32)
+    pg, pn, vs, trunc, eta = sphere_pair(dims)
+    psi0 = orc.init_identity(*dims)
+    want = orc.estimate_psi(pg, pn, psi0, 5, -1.0, 7, 0.1, 0.01, 0.4)
+    p = sf.Params(volume_dims=dims, volume_size=(0.25, 0.25, 0.25), max_iter=5, max_update_norm=-1.0, alpha=0.01, w_reg=0.4,
+                  tsdf_trunc_dist=float(trunc), eta=float(eta), tsdf_max_weight=64.0)
+    solver = sf.Solver(p)
+    psi = psi0.copy()
+    o = [np.zeros_like(pg), np.zeros_like(pn), np.zeros_like(psi)]
+    solver.estimate_psi_host(pg, o[0], pn, o[1], psi, o[2])
+    assert_bits(psi, want["psi"], "host: psi")
+    assert_bits(o[0], want["phi_global_psi_inv"], "host: phi_global_psi_inv")
+    assert_bits(o[1], want["phi_n_psi"], "host: phi_n_psi")
+    assert_bits(o[2], want["psi_inv"], "host: psi_inv")
