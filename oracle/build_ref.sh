@@ -29,5 +29,5 @@ for f in src/sobfu/solver.cpp src/sobfu/reductor.cpp src/sobfu/vector_fields.cpp
 done
 g++ $CXXFLAGS -c "$HERE/ref_harness.cpp" -o "$TMP/ref_harness.o" & pids+=($!)
 for p in "${pids[@]}"; do wait $p; done
-nvcc -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT/libsobfu_ref.so" "$TMP"/*.o -lcudart
+nvcc -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT/libsobfu_ref.so" "$TMP"/*.o -lcudart -L/usr/local/cuda/lib64/stubs -lcuda
 echo "build_ref: wrote $OUT/libsobfu_ref.so"

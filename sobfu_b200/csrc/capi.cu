@@ -121,6 +121,8 @@ static RankMap rank_map_for(size_t n) {
     if (blocks > 65536) blocks = 65536;
     RankMap m;
     m.bs = threads;
+    m.bits = 0;
+    while ((1u << m.bits) < threads) ++m.bits;
     m.grid = threads * 2 * blocks;
     m.npass = (unsigned)((n + m.grid - 1) / m.grid);
     return m;
@@ -130,7 +132,9 @@ static long long unrank(unsigned rank, const RankMap m) {
     unsigned r = rank >> 1;
     const unsigned pass = r % m.npass;
     r /= m.npass;
-    const unsigned t = r % m.bs, b = r / m.bs;
+    const unsigned tr = r % m.bs, b = r / m.bs;
+    unsigned t = 0;
+    for (unsigned k = 0; k < m.bits; ++k) t |= ((tr >> k) & 1u) << (m.bits - 1 - k);   // undo the bit reversal
     return (long long)pass * m.grid + (long long)b * 2 * m.bs + (long long)half * m.bs + t;
 }
 // how the reference reports the index: (float) i for the first element of a thread, (float) i + blockSize for the second

@@ -83,9 +83,13 @@ SB_DEV double warp_sum_f64(double v) {
 }
 
 // Traversal order of the reference's arg-max reduction (reductor.cu:342-456 + reductor.cpp:81-94):
-// ties resolve to the smallest (block, tid, pass, half).  rank() maps a voxel index to that order.
+// ties keep the FIRST candidate met: per thread in (pass, half) order, then through the shared-memory tree, where
+// slot tid keeps its own value against slot tid+s for s = bs/2 .. 1 -- i.e. among equal values the thread whose
+// bit-reversed tid is smallest survives -- and finally the lowest block on the CPU.  rank_of() maps a voxel index to
+// that order: (block, bitrev(tid), pass, half).
 struct RankMap {
-    unsigned bs;        // threads per block of the reference reduction (512 for N >= 1024)
+    unsigned bs;        // threads per block of the reference reduction (512 for N >= 1024), a power of two
+    unsigned bits;      // log2(bs)
     unsigned grid;      // bs * 2 * blocks
     unsigned npass;     // ceil(N / grid)
 };
@@ -93,7 +97,8 @@ SB_DEV unsigned rank_of(unsigned idx, const RankMap m) {
     const unsigned pass = idx / m.grid, r = idx - pass * m.grid;
     const unsigned b = r / (2 * m.bs), q = r - b * 2 * m.bs;
     const unsigned half = q >= m.bs ? 1u : 0u, t = q - half * m.bs;
-    return ((b * m.bs + t) * m.npass + pass) * 2u + half;
+    const unsigned tr = m.bits ? (__brev(t) >> (32u - m.bits)) : 0u;
+    return ((b * m.bs + tr) * m.npass + pass) * 2u + half;
 }
 
 }  // namespace sb
