@@ -1,0 +1,309 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the SobolevFusion solver hot path on B200 (contract: see the task statement).
+
+Workload (BASELINE.json configs[2]): 256^3 volume, params/params_boxing.ini of the reference (dims -> 256, MAX_ITER -> 200,
+MAX_UPDATE_NORM 1e-10 so that exactly 200 iterations run), synthetic 640x480 depth frames of an analytically ray-cast
+sphere translating 2 mm per frame.  One "step" = one frame = one Solver::estimate_psi (200 gradient-descent iterations +
+psi^-1 + the two warps).
+
+  value  : Gvoxel-iterations/s of estimate_psi with all volumes resident in HBM (device time, CUDA events)
+  e2e    : the same metric through the frame call a user of the reference makes -- SobFusion::operator()(depth) with the
+           depth frame in pinned HOST memory: H2D of the frame, bilateral/truncate/dists, TSDF integration, the solver,
+           TSDF fusion, and a D2H read of the solve result, all inside the timed region
+  roofline: pass B (Sobolev filter + psi update + warp + max-norm partials), algorithmic 64 B/voxel
+  --impl reference : the UNMODIFIED reference CUDA (oracle/_ref, built from /root/reference) on the same workload; the
+           reference has no CPU solver path, so its own CUDA on one B200 is the baseline arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("SOBFU_B200_QUIET", "1")
+
+# params/params_boxing.ini (reference), with the overrides BASELINE.json names for config 3
+BOXING = dict(vol_size=0.75, trunc_vox=48.0, eta_vox=3.0, max_weight=128.0, fx=570.342, fy=570.342, cx=320.0, cy=240.0,
+              trunc_depth=1.0, pose_tz=0.1, sigma_depth=0.005, sigma_spatial=4.5, ksz=7, start_frame=1,
+              max_update_norm=1e-10, s=7, lam=0.1, alpha=0.001, w_reg=0.6)
+COLS, ROWS = 640, 480
+ALGO_BYTES_PASS_B = 64      # R nabla_U 16 + R psi 16 + W psi 16 + R phi_n 8 + W phi_n_psi 8   
+ALGO_BYTES_ITER = 112
+
+
+def synth_depth(frame, radius=0.15, z0=0.5):
+    """analytically ray-cast sphere: centre (0.002*frame, 0, z0) m, ushort millimetres, background 0"""
+    u, v = np.meshgrid(np.arange(COLS, dtype=np.float64), np.arange(ROWS, dtype=np.float64))
+    dx, dy = (u - BOXING["cx"]) / BOXING["fx"], (v - BOXING["cy"]) / BOXING["fy"]
+    c = np.array([0.002 * frame, 0.0, z0])
+    a = dx * dx + dy * dy + 1.0
+    b = -2.0 * (dx * c[0] + dy * c[1] + c[2])
+    cc = float(c @ c) - radius * radius
+    disc = b * b - 4 * a * cc
+    t = np.where(disc > 0, (-b - np.sqrt(np.maximum(disc, 0))) / (2 * a), 0.0)
+    return np.ascontiguousarray(np.where(disc > 0, np.round(t * 1000.0), 0).astype(np.uint16))
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [r for r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows),
+                "samples": len(rows), "reasons": reasons}
+
+
+def make_params(sf, dim, iters):
+    b = BOXING
+    p = sf.Params(cols=COLS, rows=ROWS, volume_dims=(dim, dim, dim), volume_size=(b["vol_size"],) * 3,
+                  intr=sf.Intr(b["fx"], b["fy"], b["cx"], b["cy"]), icp_truncate_depth_dist=b["trunc_depth"],
+                  bilateral_sigma_depth=b["sigma_depth"], bilateral_sigma_spatial=b["sigma_spatial"], bilateral_kernel_size=b["ksz"],
+                  tsdf_max_weight=b["max_weight"], gradient_delta_factor=0.5, start_frame=b["start_frame"], verbosity=0, s=b["s"],
+                  max_iter=iters, max_update_norm=b["max_update_norm"], lambda_=b["lam"], alpha=b["alpha"], w_reg=b["w_reg"])
+    vs = p.voxel_sizes()
+    p.tsdf_trunc_dist = float(np.float32(b["trunc_vox"]) * vs[0])      # demo.cpp:71-72: given in voxels
+    p.eta = float(np.float32(b["eta_vox"]) * vs[0])
+    p.volume_pose = sf.Affine3f().translate((-b["vol_size"] / 2, -b["vol_size"] / 2, b["pose_tz"]))   # demo.cpp:73-74
+    return p
+
+
+def cpu_baseline(dim=96, iters=2):
+    """the oracle port (CPU restatement of the same iteration) on the host cores, bounded sample"""
+    from oracle import pyoracle as orc
+    from tests.common import sphere_pair
+    dims = (dim, dim, dim)
+    pg, pn, vs, trunc, eta = sphere_pair(dims)
+    psi = orc.init_identity(*dims)
+    pnp = orc.apply(pn, psi)
+    scratch = np.zeros((5,) + psi.shape, dtype=np.float32)
+    taps = orc.sobolev_taps(7, 0.1)
+    orc.solver_iteration(pg, pn, pnp, psi, scratch, taps, 0.001, 0.6)      # warm-up (page faults, omp pool)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        orc.solver_iteration(pg, pn, pnp, psi, scratch, taps, 0.001, 0.6)
+    dt = time.perf_counter() - t0
+    return {"value": dim ** 3 * iters / dt / 1e9, "unit": "Gvoxel-iter/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "%d solver iterations at %d^3 (oracle/sobfu_oracle.c, OpenMP on all host cores), %.2f s" % (iters, dim, dt)}
+
+
+def run_ours(args, rank, world, torch, dist):
+    import sobfu_b200 as sf
+    dim, iters = args.dim, args.iters
+    if world > 1:
+        raise SystemExit("z-slab multi-GPU mode is not wired into bench.py yet")
+    p = make_params(sf, dim, iters)
+    fusion = sf.SobFusion(p)
+    frames = [torch.from_numpy(synth_depth(f).view(np.int16)).pin_memory() for f in range(1 + 2 * (args.warmup + args.steps))]
+    dev_depth = torch.empty((ROWS, COLS), dtype=torch.int16, device="cuda")
+
+    def frame_step(f):
+        dev_depth.copy_(frames[f], non_blocking=True)              # H2D of this step's input from pinned memory
+        fusion(dev_depth.view(torch.uint16))
+        return fusion.solver.info.max_norm if fusion.solver is not None and fusion.solver.info is not None else 0.0   # D2H'd by the call
+
+    frame_step(0)                                                  # frame 0 only initialises phi_global
+    f = 1
+    for _ in range(args.warmup):
+        frame_step(f); f += 1
+    solver = fusion.solver
+    N = dim ** 3
+
+    # ---- value: solver only, volumes resident ------------------------------------------------------------------
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sync_all()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches, loop_ms = 0, 0.0
+    e0.record()
+    for _ in range(args.steps):
+        info = solver.estimate_psi(fusion.phi_global, fusion.phi_global_psi_inv, fusion.phi_n, fusion.phi_n_psi, fusion.psi, fusion.psi_inv)
+        launches += info.launches
+        loop_ms += info.loop_ms
+        assert info.iters == iters, info.iters
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    # ---- e2e: frames from pinned host memory through SobFusion::operator() ---------------------------------------
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        frame_step(f); f += 1
+    e3.record()
+    sync_all()
+    ms_e2e = e2.elapsed_time(e3)
+    clk = clocks.stop()
+    # ---- roofline of the dominant kernel: per-kernel device time measured on the solver's own stream ----------------
+    ms_a, ms_b, ms_it = solver.time_loop(max(20, min(iters, 100)))
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e, ms_a, ms_b, ms_it], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e, ms_a, ms_b, ms_it = [float(x) for x in t.tolist()]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = ALGO_BYTES_PASS_B * N / (ms_b * 1e-3) / 1e9
+    out = {
+        "metric": "solver_gvoxel_iters_per_s", "value": N * iters * args.steps / (ms * 1e-3) / 1e9, "unit": "Gvoxel-iter/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%d^3 volume, params_boxing.ini (dims->%d, MAX_ITER->%d), 640x480 synthetic sphere depth, 1 step = 1 frame = "
+                               "estimate_psi with %d iterations" % (dim, dim, iters, iters), "l2": "inputs exceed L2 (%.0f MB of solver state)" % (36 * N / 1e6),
+                   "parallelism": "1 GPU" if world == 1 else "z-slab x%d" % world},
+        "solver_iters_per_s": iters * args.steps / (ms * 1e-3), "loop_ms_per_iter": loop_ms / (args.steps * iters),
+        "kernel_ms": {"pass_a": ms_a, "pass_b": ms_b, "iteration": ms_it},
+        "iteration_roofline_frac": ALGO_BYTES_ITER * N / (ms_it * 1e-3) / 1e9 / peak,
+        "clocks": clk,
+        "e2e": {"value": N * iters * args.steps / (ms_e2e * 1e-3) / 1e9, "unit": "Gvoxel-iter/s", "frames_per_s": args.steps / (ms_e2e * 1e-3),
+                "h2d_bytes_per_step": COLS * ROWS * 2, "d2h_bytes_per_step": 4 + iters * 24 + 16},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "pass_b (Sobolev filter + psi update + warp + max partials)", "achieved": achieved,
+                     "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                     "unit": "GB/s", "frac": achieved / peak, "algorithmic_bytes_per_voxel": ALGO_BYTES_PASS_B, "traffic": None},
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(out), flush=True)
+
+
+def run_reference(args, rank, world):
+    """the unmodified reference CUDA through its own host API, same frames / same parameters (rank 0 only)"""
+    if rank != 0:
+        return
+    from oracle import pyoracle as orc
+    if not os.path.exists(orc.REF):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsobfu_ref.so was not built (needs /root/reference at build time)"}))
+        return
+    import torch
+    b = BOXING
+    dim, iters = args.dim, args.iters
+    vs = np.float32(b["vol_size"]) / np.float32(dim)
+    ref = orc.Reference((dim,) * 3, (b["vol_size"],) * 3, float(np.float32(b["trunc_vox"]) * vs), float(np.float32(b["eta_vox"]) * vs),
+                        b["max_weight"], 0, iters, b["s"], b["max_update_norm"], b["lam"], b["alpha"], b["w_reg"],
+                        pose_t=(-b["vol_size"] / 2, -b["vol_size"] / 2, b["pose_tz"]), intr=(b["fx"], b["fy"], b["cx"], b["cy"]))
+    frames = [synth_depth(f) for f in range(1 + 2 * (args.warmup + args.steps))]
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+
+    def frame_step(f):     # SobFusion::operator(), sob_fusion.cpp:71-145, through the reference's own classes
+        ref.depth_to_dists(frames[f], b["ksz"], b["sigma_spatial"], b["sigma_depth"], b["trunc_depth"])
+        if f == 0:
+            ref.integrate_dists(ref.GLOBAL)
+            return
+        ref.tsdf_clear(ref.N)
+        ref.integrate_dists(ref.N)
+        ref.estimate_psi()
+        ref.fuse(ref.GLOBAL, ref.N_PSI)
+
+    sys.stdout.flush()
+    os.dup2(devnull, 1)    # the reference prints from inside the solver loop (solver.cu:115-117)
+    try:
+        frame_step(0)
+        f = 1
+        for _ in range(args.warmup):
+            frame_step(f); f += 1
+        clocks = ClockSampler(0)
+        torch.cuda.synchronize()
+        clocks.start()
+        ms = sum(ref.estimate_psi() for _ in range(args.steps))      # cudaEvent pair around Solver::estimate_psi
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            frame_step(f); f += 1
+        torch.cuda.synchronize()
+        ms_e2e = (time.perf_counter() - t0) * 1e3
+        clk = clocks.stop()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+    N = dim ** 3
+    v = N * iters * args.steps / (ms * 1e-3) / 1e9
+    print(json.dumps({
+        "impl": "reference", "metric": "solver_gvoxel_iters_per_s", "value": v, "unit": "Gvoxel-iter/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%d^3 volume, params_boxing.ini (dims->%d, MAX_ITER->%d), 640x480 synthetic sphere depth, 1 step = 1 frame = "
+                               "estimate_psi with %d iterations" % (dim, dim, iters, iters), "parallelism": "1 GPU (the reference is single-GPU)"},
+        "solver_iters_per_s": iters * args.steps / (ms * 1e-3), "clocks": clk,
+        "cpu_baseline": {"value": v, "unit": "Gvoxel-iter/s", "cores": os.cpu_count(), "kind": "reference",
+                         "sample": "the reference has no CPU solver path: this is its own CUDA (sm_100a build of the unmodified sources) on one B200"},
+        "e2e": {"value": N * iters * args.steps / (ms_e2e * 1e-3) / 1e9, "unit": "Gvoxel-iter/s", "frames_per_s": args.steps / (ms_e2e * 1e-3),
+                "h2d_bytes_per_step": COLS * ROWS * 2, "d2h_bytes_per_step": 0},
+    }), flush=True)
+    ref.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dim", type=int, default=256)
+    ap.add_argument("--iters", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if rank == 0:
+            import torch
+            torch.cuda.set_device(0)
+        return run_reference(args, rank, world)
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if world > 1:
+        dist.init_process_group("nccl")
+    run_ours(args, rank, world, torch, dist)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
