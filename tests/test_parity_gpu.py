@@ -218,3 +218,29 @@ def test_host_buffer_entry_point(env):
     assert_bits(o[0], want["phi_global_psi_inv"], "host: phi_global_psi_inv")
     assert_bits(o[1], want["phi_n_psi"], "host: phi_n_psi")
     assert_bits(o[2], want["psi_inv"], "host: psi_inv")
+
+
+@pytest.mark.parametrize("dims,iters", [((64, 64, 64), 9), ((96, 40, 36), 6), ((128, 24, 16), 5), ((32, 8, 8), 4)])
+def test_tiled_tma_kernels_match_oracle_and_generic(env, dims, iters):
+    """the vectorised pass A and the TMA-fed pass B (variant 2) against the oracle and against the generic kernels
+    (variant 1): full and partial tiles in x and y, several z chunks, warm-started psi"""
+    sf, orc, torch = env
+    pg, pn, vs, trunc, eta = sphere_pair(dims, r=0.07)
+    psi0 = wavy_psi(dims, amp=0.5)
+    want = orc.estimate_psi(pg, pn, psi0, iters, -1.0, 7, 0.2, 0.02, 0.3)
+    for variant in (2, 1):
+        got = run_solver(sf, torch, dims, pg, pn, psi0, vs, trunc, eta, iters, -1.0, 0.02, 0.3, variant=variant, lam=0.2)
+        compare_solver(got, want, "variant %d %s" % (variant, dims))
+
+
+def test_tiled_equals_generic_at_128(env):
+    """larger volume (many work items per CTA, L2-sized working set): tiled vs generic, bit for bit, logging on"""
+    sf, orc, torch = env
+    dims = (128, 128, 128)
+    pg, pn, vs, trunc, eta = sphere_pair(dims, r=0.08, shift=0.004)
+    psi0 = wavy_psi(dims, amp=0.6)
+    a = run_solver(sf, torch, dims, pg, pn, psi0, vs, trunc, eta, 10, -1.0, 0.05, 0.4, verbosity=2, variant=1)
+    b = run_solver(sf, torch, dims, pg, pn, psi0, vs, trunc, eta, 10, -1.0, 0.05, 0.4, verbosity=2, variant=2)
+    for k in ("psi", "phi_n_psi", "psi_inv", "phi_global_psi_inv"):
+        assert_bits(a[k], b[k], "128^3 tiled vs generic: " + k)
+    assert a["log"] == b["log"]
