@@ -258,8 +258,8 @@ extern "C" int sobfu_b200_solver_get_taps(sobfu_b200_solver *s, float *t) {
     return 0;
 }
 extern "C" int sobfu_b200_solver_set_variant(sobfu_b200_solver *s, int v) {
-    if (!s || v < 0 || v > 2) return fail(SOBFU_B200_EINVAL, "variant must be 0, 1 or 2");
-    if (v == 2 && !(tiled_supported(s->d) && s->tma)) return fail(SOBFU_B200_EINVAL, "tiled/TMA kernels do not support dims %dx%dx%d", s->d.X, s->d.Y, s->d.Z);
+    if (!s || v < 0 || v > 3) return fail(SOBFU_B200_EINVAL, "variant must be 0..3");
+    if (v >= 2 && !(tiled_supported(s->d) && s->tma)) return fail(SOBFU_B200_EINVAL, "tiled/TMA kernels do not support dims %dx%dx%d", s->d.X, s->d.Y, s->d.Z);
     s->variant = v;
     return 0;
 }
@@ -268,14 +268,18 @@ static inline bool log_iter(const sobfu_b200_params &p, int iter1) {   // iter1 
     return p.verbosity == 2 || (p.verbosity == 1 && (iter1 == 1 || iter1 % 50 == 0 || iter1 == p.max_iter));
 }
 
+static void run_pass_a(sobfu_b200_solver *s, int it, int log) {
+    if (!use_tiled(s)) launch_pass_a_generic(s->args, it, log, s->stream);
+    else if (s->variant == 3) launch_pass_a_tiled(s->args, it, log, s->stream);
+    else launch_pass_a_tma(s->args, s->tma, it, log, s->stream);
+}
+static void run_pass_b(sobfu_b200_solver *s, int it) {
+    if (!use_tiled(s)) launch_pass_b_generic(s->args, it, s->stream);
+    else launch_pass_b_tma(s->args, s->tma, it, s->stream);
+}
 static void launch_iteration(sobfu_b200_solver *s, int it, int log, int *launches) {
-    if (use_tiled(s)) {
-        launch_pass_a_tiled(s->args, it, log, s->stream);
-        launch_pass_b_tma(s->args, s->tma, it, s->stream);
-    } else {
-        launch_pass_a_generic(s->args, it, log, s->stream);
-        launch_pass_b_generic(s->args, it, s->stream);
-    }
+    run_pass_a(s, it, log);
+    run_pass_b(s, it);
     *launches += 2;
 }
 
@@ -433,9 +437,8 @@ extern "C" int sobfu_b200_solver_time_loop(sobfu_b200_solver *s, int iters, floa
     cudaStream_t st = s->stream;
     s->args.check = 0;
     const int slot = 0;   // partial maxima land in maxkey[0]; irrelevant here
-    const bool tiled = use_tiled(s);
-    auto run_a = [&]() { if (tiled) launch_pass_a_tiled(s->args, slot, 0, st); else launch_pass_a_generic(s->args, slot, 0, st); };
-    auto run_b = [&]() { if (tiled) launch_pass_b_tma(s->args, s->tma, slot, st); else launch_pass_b_generic(s->args, slot, st); };
+    auto run_a = [&]() { run_pass_a(s, slot, 0); };
+    auto run_b = [&]() { run_pass_b(s, slot); };
     float ta = 0.f, tb = 0.f, tl = 0.f;
     // whole loop
     CK(cudaEventRecord(s->ev[0], st));

@@ -1,213 +1,207 @@
-// solver_tiled.cu -- pass B of the solver iteration as a persistent, TMA-fed, z-marching kernel:
-//     nabla_U_S = S *x nabla_U + S *y nabla_U + S *z nabla_U           (solver.cu:237-446, 7 taps, clamp to edge)
-//     psi      -= alpha * nabla_U_S ; partial arg-max of |alpha * nabla_U_S|   (solver.cu:53-69, reductor.cu:342-456)
-//     (phi_n o psi).x re-warped with the new psi                              (vector_fields.cu:81-100, solver.cu:168)
-// -- five of the reference's launches (3 convolutions, update, apply) plus its reduction, in one pass over HBM.
+// solver_tiled.cu -- the two kernels of a solver iteration as persistent, TMA-fed, z-marching pipelines (sm_100a).
 //
-// Mapping to the hardware
-//   * one persistent CTA per SM walks (x-tile, y-tile, z-chunk) work items; inside an item it marches along z
-//   * nabla_U planes (3 components, tile + halo of 3 in x and y) are brought into a ring of shared-memory stages by
-//     TMA (cp.async.bulk.tensor.3d, one elected thread, mbarrier complete_tx); the halo needs no special cases
-//     because pass A stores nabla_U with a replicated border (clamp to edge == plain loads)
-//   * each thread owns 4 consecutive x: x taps = two extra LDS.128, y taps = six LDS.128, z taps = a 7-deep register
-//     window that is refilled with one LDS.128 per component and step
-//   * psi is read and written once (LDG/STG.128), the warp gathers phi_n.x from a 4 B/voxel plane
-//   * the max update norm is reduced warp-shuffle -> shared -> one 64-bit atomicMax per CTA
-// Algorithmic traffic: R nabla_U 12 + R psi 12 + W psi 12 + R phi_n 4 + W w 4 = 44 B/voxel (reference layouts: 64).
-// Arithmetic and summation order are the reference's (taps S[3-j], j=-3..3 from 0; (x + y) + z); results are
-// bit-identical to pass_b_generic_kernel.
-#include <cuda.h>
-
+//   pass A   nabla_U = (phi_n o psi - phi_global) * grad(phi_n o psi) + w_reg * L(psi)
+//            (TsdfDifferentiator vector_fields.cu:157-208, laplacian :291-337, potential gradient solver.cu:15-33)
+//   pass B   nabla_U_S = S *x nabla_U + S *y nabla_U + S *z nabla_U   (solver.cu:237-446, 7 taps, clamp to edge)
+//            psi -= alpha * nabla_U_S ; arg-max partials of |alpha * nabla_U_S|   (solver.cu:53-69, reductor.cu:342-456)
+//            (phi_n o psi).x re-warped with the new psi                          (vector_fields.cu:81-100, solver.cu:168)
+//
+// Mapping to the hardware (both kernels)
+//   * persistent CTAs walk (x-tile, y-tile, z-chunk) work items; the planes an item needs form one continuous stream
+//   * one elected thread feeds a ring of shared-memory stages with cp.async.bulk.tensor.3d (TMA); consumers wait on
+//     "full" mbarriers (complete_tx) and hand stages back through "empty" mbarriers (one arrival per warp), so warps
+//     drift independently up to the ring depth -- no __syncthreads in the steady state
+//   * every thread owns 4 consecutive x (128-bit shared and global accesses); x/y neighbours come from the staged
+//     tile + halo, z neighbours from the neighbouring stages (pass A) or a 7-deep register window (pass B)
+//   * pass B needs no border cases: pass A stores nabla_U with a replicated halo (clamp to edge == plain TMA box);
+//     pass A reads unpadded planes: out-of-range box elements are zero-filled by TMA and never used, because on a
+//     boundary plane the reference's stencils substitute in-range values (see below)
+// Algorithmic HBM traffic: A 32 B/voxel, B 44 B/voxel (reference layouts: 48 + 64).  Results are bit-identical to the
+// generic kernels and to the oracle (tests/test_parity_gpu.py).
 #include <cstdio>
 
 #include "solver_kernels.cuh"
+#include "tma_utils.cuh"
 
 namespace sb {
 
 struct TmaMaps {
-    CUtensorMap m[3];
+    CUtensorMap g[3];      // nabla_U components (padded), pass B input
+    CUtensorMap in[4];     // psi x/y/z and (phi_n o psi).x planes, pass A input
 };
 
 namespace {
 
-// ---- tile configuration -------------------------------------------------------------------------------------
-constexpr int LX = 16;                    // lanes along x per row -> 64 voxels
-constexpr int RW = 32 / LX;               // rows per warp
-constexpr int NW = 12;                    // warps per CTA
-constexpr int TX = 4 * LX, TY = NW * RW;  // 64 x 24 outputs per plane
-constexpr int SX = TX + 8, SY = TY + 6;   // staged box: 4|64|4 floats wide (16 B aligned own quads), 3|24|3 rows
-constexpr int NSTAGE = 6;                 // planes z .. z+3 live, two in flight
+struct Sched {
+    int tiles_x, tiles_y, nz, zchunk, nitems;
+};
+
+SB_DEVI float c4(const float4 &v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
+
+// position of a CTA in its plane stream: work item -> tile origin and plane range [p, p_last]
+template <int TX, int TY, int LO, int HI>
+struct Stream {
+    int item, p, p_last, x0t, y0t, zb, ze;
+    SB_DEVI void open(int it, const Sched &sc, int Z) {
+        item = it;
+        if (item >= sc.nitems) return;
+        const int xy = sc.tiles_x * sc.tiles_y;
+        const int tz = item / xy, rem = item - tz * xy;
+        const int tyi = rem / sc.tiles_x;
+        x0t = (rem - tyi * sc.tiles_x) * TX;
+        y0t = tyi * TY;
+        zb = tz * sc.zchunk;
+        ze = min(zb + sc.zchunk, Z);
+        p = zb - LO;
+        p_last = ze - 1 + HI;
+    }
+    SB_DEVI bool valid(const Sched &sc) const { return item < sc.nitems; }
+    SB_DEVI void next(const Sched &sc, int Z) {
+        if (++p > p_last) open(item + (int)gridDim.x, sc, Z);
+    }
+};
+
+// =============================================================================================================
+// pass B
+// =============================================================================================================
+namespace pb {
+constexpr int LX = 16, RW = 32 / LX, NW = 12;     // 16 lanes x 4 voxels per row, 2 rows per warp, 12 warps
+constexpr int TX = 4 * LX, TY = NW * RW;          // 64 x 24 outputs per plane
+constexpr int SX = TX + 8, SY = TY + 6;           // staged box 4|64|4 floats x 3|24|3 rows
+constexpr int NSTAGE = 6;                         // planes q-3..q live, two in flight
 constexpr int COMP_BYTES = ((SX * SY * 4 + 127) / 128) * 128;
 constexpr int STAGE_BYTES = 3 * COMP_BYTES;
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 128;
 constexpr unsigned TX_BYTES = 3u * SX * SY * 4u;
-
-SB_DEV unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-SB_DEV void mbar_init(unsigned long long *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-SB_DEV void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-SB_DEV void mbar_wait(unsigned long long *bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-SB_DEV void tma_load_3d(unsigned dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-            dst),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-
-// explicit shared-window loads (32-bit shared addresses; element offsets in floats)
-SB_DEV float4 lds4(unsigned saddr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
-    return v;
-}
-SB_DEV float c4(const float4 &v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
-
-struct Sched {
-    int tiles_x, tiles_y, nz, zchunk, nitems;
-};
 
 __global__ void __launch_bounds__(NW * 32, 1)
     pass_b_tma_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapy,
                       const __grid_constant__ CUtensorMap mapz, LoopArgs a, int it, Sched sc) {
     if (loop_finished(a, it)) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const unsigned smem = (smem_u32(smem_raw) + 127u) & ~127u;   // TMA destinations need 128 B alignment
-    __shared__ unsigned long long full[NSTAGE];
+    const unsigned smem = (smem_u32(smem_raw) + 127u) & ~127u;
+    __shared__ unsigned long long bars[2 * NSTAGE];
     __shared__ unsigned long long skey[NW];
+    const unsigned full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[NSTAGE]);
 
     const Dims d = a.d;
+    const int X = d.X, XY = d.X * d.Y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int lx = lane % LX, ly = lane / LX;
-    const int ty = warp * RW + ly;            // row inside the tile
-    const unsigned own_off = (unsigned)(((ty + 3) * SX + 4 * lx + 4) * 4);   // byte offset of the thread's own quad in a component
+    const int lx = lane % LX, ty = warp * RW + lane / LX;
+    const unsigned own_off = (unsigned)(((ty + 3) * SX + 4 * lx + 4) * 4);
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NW); }
+        mbar_fence_init();
     }
     __syncthreads();
 
-    const size_t sy = (size_t)d.X, sz = (size_t)d.X * d.Y;
+    typedef Stream<TX, TY, 3, 3> St;
+    // ---- producer (thread 0 only) ----
+    St pr;
+    unsigned q_issue = 0;
+    auto produce = [&]() {
+        if (!pr.valid(sc)) return;
+        const unsigned slot = q_issue % NSTAGE, n = q_issue / NSTAGE;
+        if (n > 0) mbar_wait(empty0 + 8 * slot, (n - 1) & 1u);     // every warp released the previous plane of this slot
+        const unsigned dst = smem + slot * STAGE_BYTES, bar = full0 + 8 * slot;
+        mbar_expect_tx(bar, TX_BYTES);
+        // padded coordinates: plane z sits at z + 3; the box origin (x0t, y0t) is interior (x0t - 4, y0t - 3)
+        tma_load_3d(dst, &mapx, bar, pr.x0t, pr.y0t, pr.p + 3);
+        tma_load_3d(dst + COMP_BYTES, &mapy, bar, pr.x0t, pr.y0t, pr.p + 3);
+        tma_load_3d(dst + 2 * COMP_BYTES, &mapz, bar, pr.x0t, pr.y0t, pr.p + 3);
+        ++q_issue;
+        pr.next(sc, d.Z);
+    };
+    if (tid == 0) {
+        pr.open(blockIdx.x, sc, d.Z);
+        produce();
+        produce();
+    }
+
+    // ---- consumers ----
     float *__restrict__ P[3] = {a.px, a.py, a.pz};
-    unsigned q_issue = 0, q_wait = 0;         // running plane counters (slot = q % NSTAGE, parity = (q / NSTAGE) & 1)
-    unsigned long long best = 0ull;
-
-    for (int item = blockIdx.x; item < sc.nitems; item += gridDim.x) {
-        const int tz = item / (sc.tiles_x * sc.tiles_y), rem = item - tz * sc.tiles_x * sc.tiles_y;
-        const int tyi = rem / sc.tiles_x, txi = rem - tyi * sc.tiles_x;
-        const int x0t = txi * TX, y0t = tyi * TY;
-        const int zb = tz * sc.zchunk, ze = min(zb + sc.zchunk, d.Z);
-        const int x0 = x0t + 4 * lx, y = y0t + ty;
-        const bool active = x0 < d.X && y < d.Y;
-        const size_t row = (size_t)min(x0, d.X - 4) + sy * min(y, d.Y - 1);
-        // planes zb-3 .. ze+2 stream through the ring; padded plane index = z + 3, box origin = (x0t, y0t) in padded
-        // coordinates, i.e. interior (x0t - 4, y0t - 3)
-        const int p_first = zb - 3, p_last = ze + 2;
-        auto issue = [&](int p) {
-            const unsigned slot = q_issue % NSTAGE;
-            const unsigned dst = smem + slot * STAGE_BYTES;
-            mbar_expect_tx(&full[slot], TX_BYTES);
-            tma_load_3d(dst, &mapx, &full[slot], x0t, y0t, p + 3);
-            tma_load_3d(dst + COMP_BYTES, &mapy, &full[slot], x0t, y0t, p + 3);
-            tma_load_3d(dst + 2 * COMP_BYTES, &mapz, &full[slot], x0t, y0t, p + 3);
-        };
-        __syncthreads();                      // every thread is done with the previous item's stages
-        if (tid == 0) {
-            issue(p_first); ++q_issue;
-            if (p_first + 1 <= p_last) { issue(p_first + 1); ++q_issue; }
-        } else {
-            q_issue += (p_first + 1 <= p_last) ? 2 : 1;
-        }
-
-        float4 win[7][3];                     // nabla_U of this thread's 4 voxels at planes c-3 .. c+3
-        for (int p = p_first; p <= p_last; ++p) {
-            __syncthreads();                  // all reads of the stage that plane p+2 will overwrite are finished
-            if (p + 2 <= p_last) {
-                if (tid == 0) issue(p + 2);
-                ++q_issue;
-            }
-            const unsigned slot = q_wait % NSTAGE, par = (q_wait / NSTAGE) & 1u;
-            ++q_wait;
-            mbar_wait(&full[slot], par);
-            const unsigned sp = smem + slot * STAGE_BYTES + own_off;
+    const float *__restrict__ pn = a.pn;
+    unsigned q = 0;                       // planes consumed so far
+    unsigned best_bits = 0u, best_idx = 0u;
+    float4 win[7][3];                     // nabla_U of this thread's 4 voxels at planes c-3 .. c+3
+    St cs;
+    for (cs.open(blockIdx.x, sc, d.Z); cs.valid(sc); cs.open(cs.item + (int)gridDim.x, sc, d.Z)) {
+        const int x0 = cs.x0t + 4 * lx, y = cs.y0t + ty;
+        const bool active = x0 < X && y < d.Y;
+        const int row = min(x0, X - 4) + X * min(y, d.Y - 1);
+        for (int p = cs.p; p <= cs.p_last; ++p) {
+            const unsigned slot = q % NSTAGE;
+            mbar_wait(full0 + 8 * slot, (q / NSTAGE) & 1u);
+            ++q;
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) win[k][c] = win[k + 1][c];
             }
+            const unsigned sp = smem + slot * STAGE_BYTES + own_off;
 #pragma unroll
             for (int c = 0; c < 3; ++c) win[6][c] = lds4(sp + c * COMP_BYTES);
-            const int zc = p - 3;             // centre plane whose window is now complete
-            if (zc < zb) continue;
-
-            // stage that holds the centre plane: it was the (q_wait-1-3)-th plane
-            const unsigned cslot = (q_wait - 4u) % NSTAGE;
-            const unsigned sc0 = smem + cslot * STAGE_BYTES + own_off;
-            const size_t o = row + sz * zc;
-            float4 psi4[3];
+            const int zc = p - 3;         // centre plane whose window is now complete
+            if (zc >= cs.zb) {
+                const unsigned sc0 = smem + ((q - 4u) % NSTAGE) * STAGE_BYTES + own_off;   // stage of the centre plane
+                const int o = row + XY * zc;
+                float4 psi4[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) psi4[c] = *reinterpret_cast<const float4 *>(P[c] + o);
-
-            float np[3][4], nsq[4];
+                for (int c = 0; c < 3; ++c) psi4[c] = *reinterpret_cast<const float4 *>(P[c] + o);
+                float np[3][4], nsq[4];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const unsigned s0 = sc0 + c * COMP_BYTES;
-                const float4 L = lds4(s0 - 16), R = lds4(s0 + 16), C = win[3][c];
-                const float v[12] = {L.x, L.y, L.z, L.w, C.x, C.y, C.z, C.w, R.x, R.y, R.z, R.w};
-                float fx[4] = {0.f, 0.f, 0.f, 0.f}, fy[4] = {0.f, 0.f, 0.f, 0.f}, fz[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int c = 0; c < 3; ++c) {
+                    const unsigned s0 = sc0 + c * COMP_BYTES;
+                    const float4 L = lds4(s0 - 16), R = lds4(s0 + 16), C = win[3][c];
+                    const float v[12] = {L.x, L.y, L.z, L.w, C.x, C.y, C.z, C.w, R.x, R.y, R.z, R.w};
+                    float fx[4] = {0.f, 0.f, 0.f, 0.f}, fy[4] = {0.f, 0.f, 0.f, 0.f}, fz[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int k = -3; k <= 3; ++k) {
-                    const float s = a.S[3 - k];
-                    const float4 yk = (k == 0) ? C : lds4(s0 + k * (SX * 4));
-                    const float4 zk = win[3 + k][c];
+                    for (int k = -3; k <= 3; ++k) {
+                        const float s = a.S[3 - k];
+                        const float4 yk = (k == 0) ? C : lds4(s0 + k * (SX * 4));
+                        const float4 zk = win[3 + k][c];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            fx[j] = add(fx[j], mul(s, v[4 + j + k]));
+                            fy[j] = add(fy[j], mul(s, c4(yk, j)));
+                            fz[j] = add(fz[j], mul(s, c4(zk, j)));
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        fx[j] = add(fx[j], mul(s, v[4 + j + k]));
-                        fy[j] = add(fy[j], mul(s, c4(yk, j)));
-                        fz[j] = add(fz[j], mul(s, c4(zk, j)));
+                        const float f = add(add(fx[j], fy[j]), fz[j]);
+                        const float u = mul(f, a.alpha);
+                        np[c][j] = sub(c4(psi4[c], j), u);
+                        nsq[j] = (c == 0) ? mul(u, u) : add(nsq[j], mul(u, u));
                     }
                 }
+                if (active) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float f = add(add(fx[j], fy[j]), fz[j]);
-                    const float u = mul(f, a.alpha);
-                    np[c][j] = sub(c4(psi4[c], j), u);
-                    nsq[j] = (c == 0) ? mul(u, u) : add(nsq[j], mul(u, u));
+                    for (int c = 0; c < 3; ++c)
+                        *reinterpret_cast<float4 *>(P[c] + o) = make_float4(np[c][0], np[c][1], np[c][2], np[c][3]);
+                    float wv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const TriCoord t = tri_coord(np[0][j], np[1][j], np[2][j], d);
+                        const int r00 = t.gy * X + t.gz * XY, r10 = t.y1 * X + t.gz * XY;
+                        const int r01 = t.gy * X + t.z1 * XY, r11 = t.y1 * X + t.z1 * XY;
+                        wv[j] = tri_lerp(__ldg(pn + r11 + t.x1), __ldg(pn + r10 + t.x1), __ldg(pn + r01 + t.x1), __ldg(pn + r00 + t.x1),
+                                         __ldg(pn + r11 + t.gx), __ldg(pn + r10 + t.gx), __ldg(pn + r01 + t.gx), __ldg(pn + r00 + t.gx), t);
+                        const unsigned bits = __float_as_uint(nsq[j]), idx = (unsigned)(o + j);
+                        if (bits > best_bits) { best_bits = bits; best_idx = idx; }
+                        else if (bits == best_bits && bits != 0u && rank_of(idx, a.rm) < rank_of(best_idx, a.rm)) best_idx = idx;
+                    }
+                    *reinterpret_cast<float4 *>(a.w + o) = make_float4(wv[0], wv[1], wv[2], wv[3]);
                 }
             }
-            if (active) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    *reinterpret_cast<float4 *>(P[c] + o) = make_float4(np[c][0], np[c][1], np[c][2], np[c][3]);
-                float wv[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const TriCoord t = tri_coord(np[0][j], np[1][j], np[2][j], d);
-                    wv[j] = sample_scalar<1>(a.pn, t, d);
-                    const unsigned long long key = ((unsigned long long)__float_as_uint(nsq[j]) << 32) |
-                                                   (unsigned long long)(0xffffffffu - rank_of((unsigned)(o + j), a.rm));
-                    best = key > best ? key : best;
-                }
-                *reinterpret_cast<float4 *>(a.w + o) = make_float4(wv[0], wv[1], wv[2], wv[3]);
-            }
+            // hand the stage of plane q-4 (0-based: the centre plane just used) back to the producer
+            __syncwarp();
+            if (lane == 0 && q >= 4u) mbar_arrive(empty0 + 8 * ((q - 4u) % NSTAGE));
+            if (tid == 0) produce();
         }
     }
+    unsigned long long best = best_bits ? (((unsigned long long)best_bits << 32) | (unsigned long long)(0xffffffffu - rank_of(best_idx, a.rm))) : 0ull;
     best = warp_max_u64(best);
     if (lane == 0) skey[warp] = best;
     __syncthreads();
@@ -218,42 +212,201 @@ __global__ void __launch_bounds__(NW * 32, 1)
         atomicMax(&a.maxkey[it], m);
     }
 }
+}  // namespace pb
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// =============================================================================================================
+// pass A
+// =============================================================================================================
+namespace pa {
+constexpr int LX = 16, RW = 32 / LX, NW = 8;      // 256 threads
+constexpr int TX = 4 * LX, TY = NW * RW;          // 64 x 16 outputs per plane
+constexpr int SX = TX + 8, SY = TY + 2;           // staged box 4|64|4 floats x 1|16|1 rows
+constexpr int NSTAGE = 5;                         // planes q-2..q live, two in flight
+constexpr int ARR_BYTES = ((SX * SY * 4 + 127) / 128) * 128;
+constexpr int STAGE_BYTES = 4 * ARR_BYTES;        // psi x, y, z, w
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 128;
+constexpr unsigned TX_BYTES = 4u * SX * SY * 4u;
 
-EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
+__global__ void __launch_bounds__(NW * 32, 2)
+    pass_a_tma_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__ CUtensorMap m1,
+                      const __grid_constant__ CUtensorMap m2, const __grid_constant__ CUtensorMap m3, LoopArgs a, int it, Sched sc) {
+    if (loop_finished(a, it)) {
+        if (a.check && blockIdx.x == 0 && threadIdx.x == 0 && !a.state->converged) {
+            a.state->iters = it;
+            a.state->converged = 1;
+        }
+        return;
     }
-    return fn;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned smem = (smem_u32(smem_raw) + 127u) & ~127u;
+    __shared__ unsigned long long bars[2 * NSTAGE];
+    const unsigned full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[NSTAGE]);
+
+    const Dims d = a.d;
+    const int X = d.X, XY = d.X * d.Y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lx = lane % LX, ty = warp * RW + lane / LX;
+    const unsigned own_off = (unsigned)(((ty + 1) * SX + 4 * lx + 4) * 4);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NW); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    typedef Stream<TX, TY, 1, 1> St;
+    St pr;
+    unsigned q_issue = 0;
+    auto produce = [&]() {
+        if (!pr.valid(sc)) return;
+        const unsigned slot = q_issue % NSTAGE, n = q_issue / NSTAGE;
+        if (n > 0) mbar_wait(empty0 + 8 * slot, (n - 1) & 1u);
+        const unsigned dst = smem + slot * STAGE_BYTES, bar = full0 + 8 * slot;
+        mbar_expect_tx(bar, TX_BYTES);
+        // unpadded planes: the box starts 4 floats / 1 row before the tile; out-of-range elements arrive as zeros
+        tma_load_3d(dst, &m0, bar, pr.x0t - 4, pr.y0t - 1, pr.p);
+        tma_load_3d(dst + ARR_BYTES, &m1, bar, pr.x0t - 4, pr.y0t - 1, pr.p);
+        tma_load_3d(dst + 2 * ARR_BYTES, &m2, bar, pr.x0t - 4, pr.y0t - 1, pr.p);
+        tma_load_3d(dst + 3 * ARR_BYTES, &m3, bar, pr.x0t - 4, pr.y0t - 1, pr.p);
+        ++q_issue;
+        pr.next(sc, d.Z);
+    };
+    if (tid == 0) {
+        pr.open(blockIdx.x, sc, d.Z);
+        produce();
+        produce();
+    }
+
+    float *__restrict__ G[3] = {a.gx, a.gy, a.gz};
+    const GLayout gl = a.gl;
+    unsigned q = 0;
+    St cs;
+    for (cs.open(blockIdx.x, sc, d.Z); cs.valid(sc); cs.open(cs.item + (int)gridDim.x, sc, d.Z)) {
+        const int x0 = cs.x0t + 4 * lx, y = cs.y0t + ty;
+        const bool active = x0 < X && y < d.Y;
+        const int row = min(x0, X - 4) + X * min(y, d.Y - 1);
+        const bool y_lo = (y == 0), y_hi = (y == d.Y - 1), by = y_lo || y_hi;
+        for (int p = cs.p; p <= cs.p_last; ++p) {
+            const unsigned slot = q % NSTAGE;
+            // phi_global of the plane that becomes the centre in this iteration: issue before the wait
+            const int zc = p - 1;
+            float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (zc >= cs.zb) g4 = *reinterpret_cast<const float4 *>(a.pg + row + XY * zc);
+            mbar_wait(full0 + 8 * slot, (q / NSTAGE) & 1u);
+            ++q;
+            if (zc >= cs.zb) {
+                // stages: z+1 = plane q-1 (just arrived), centre = q-2, z-1 = q-3
+                const unsigned sP = smem + ((q - 1u) % NSTAGE) * STAGE_BYTES + own_off;
+                const unsigned sC = smem + ((q - 2u) % NSTAGE) * STAGE_BYTES + own_off;
+                const unsigned sM = smem + ((q + NSTAGE - 3u) % NSTAGE) * STAGE_BYTES + own_off;
+                const bool z_lo = (zc == 0), z_hi = (zc == d.Z - 1), bz = z_lo || z_hi;
+                // warped TSDF: central differences, both taps on the in-range neighbour at a boundary (-> +0)
+                float nx[4], ny[4], nz[4], df[4];
+                {
+                    const unsigned w0 = sC + 3 * ARR_BYTES;
+                    const float4 C = lds4(w0), Ym = lds4(w0 - SX * 4), Yp = lds4(w0 + SX * 4);
+                    const float4 Zm = lds4(sM + 3 * ARR_BYTES), Zp = lds4(sP + 3 * ARR_BYTES);
+                    const float xl = lds1(w0 - 4), xr = lds1(w0 + 16);
+                    const float xm[4] = {xl, C.x, C.y, C.z}, xp[4] = {C.y, C.z, C.w, xr};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool x_lo = (x0 + j == 0), x_hi = (x0 + j == X - 1);
+                        const float a1 = x_hi ? xm[j] : xp[j], a2 = x_lo ? xp[j] : xm[j];
+                        const float b1 = y_hi ? c4(Ym, j) : c4(Yp, j), b2 = y_lo ? c4(Yp, j) : c4(Ym, j);
+                        const float c1 = z_hi ? c4(Zm, j) : c4(Zp, j), c2 = z_lo ? c4(Zp, j) : c4(Zm, j);
+                        nx[j] = mul(sub(a1, a2), 0.5f);      // __fdividef(., 2.f)
+                        ny[j] = mul(sub(b1, b2), 0.5f);
+                        nz[j] = mul(sub(c1, c2), 0.5f);
+                        df[j] = sub(c4(C, j), c4(g4, j));
+                    }
+                }
+                const size_t o = gl.at(min(x0, X - 4), min(y, d.Y - 1), zc);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const unsigned p0 = sC + c * ARR_BYTES;
+                    const float4 C = lds4(p0), Ym = lds4(p0 - SX * 4), Yp = lds4(p0 + SX * 4);
+                    const float4 Zm = lds4(sM + c * ARR_BYTES), Zp = lds4(sP + c * ARR_BYTES);
+                    const float xl = lds1(p0 - 4), xr = lds1(p0 + 16);
+                    const float xm[4] = {xl, C.x, C.y, C.z}, xp[4] = {C.y, C.z, C.w, xr};
+                    float u[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool bx = (x0 + j == 0) || (x0 + j == X - 1);
+                        const float ctr = c4(C, j);
+                        // laplacian: on a boundary plane both neighbours are the voxel itself (vector_fields.cu:299-331)
+                        float v = mul(ctr, -6.f);
+                        v = add(v, bx ? ctr : xp[j]);
+                        v = add(v, bx ? ctr : xm[j]);
+                        v = add(v, by ? ctr : c4(Yp, j));
+                        v = add(v, by ? ctr : c4(Ym, j));
+                        v = add(v, bz ? ctr : c4(Zp, j));
+                        v = add(v, bz ? ctr : c4(Zm, j));
+                        const float Lv = mul(v, -1.f);
+                        const float n = (c == 0) ? nx[j] : (c == 1 ? ny[j] : nz[j]);
+                        u[j] = add(mul(n, df[j]), mul(Lv, a.w_reg));
+                    }
+                    if (active) {
+                        float *__restrict__ g = G[c];
+                        const float4 uv = make_float4(u[0], u[1], u[2], u[3]);
+                        *reinterpret_cast<float4 *>(g + o) = uv;
+                        // replicated halo of 3 (clamp to edge of the filter, solver.cu:256,263,270)
+                        if (x0 == 0) *reinterpret_cast<float4 *>(g + o - 4) = make_float4(u[0], u[0], u[0], u[0]);
+                        if (x0 + 4 == X) *reinterpret_cast<float4 *>(g + o + 4) = make_float4(u[3], u[3], u[3], u[3]);
+                        if (y_lo) {
+#pragma unroll
+                            for (int k = 1; k <= 3; ++k) *reinterpret_cast<float4 *>(g + o - (size_t)k * gl.PX) = uv;
+                        }
+                        if (y_hi) {
+#pragma unroll
+                            for (int k = 1; k <= 3; ++k) *reinterpret_cast<float4 *>(g + o + (size_t)k * gl.PX) = uv;
+                        }
+                        if (z_lo) {
+#pragma unroll
+                            for (int k = 1; k <= 3; ++k) *reinterpret_cast<float4 *>(g + o - (size_t)k * gl.plane) = uv;
+                        }
+                        if (z_hi) {
+#pragma unroll
+                            for (int k = 1; k <= 3; ++k) *reinterpret_cast<float4 *>(g + o + (size_t)k * gl.plane) = uv;
+                        }
+                    }
+                }
+            }
+            // the z-1 plane of this iteration (plane q-3, 0-based) is not needed any more
+            __syncwarp();
+            if (lane == 0 && q >= 3u) mbar_arrive(empty0 + 8 * ((q - 3u) % NSTAGE));
+            if (tid == 0) produce();
+        }
+    }
+}
+}  // namespace pa
+
+int sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
 }
 
-Sched make_sched(const Dims d, int ctas) {
+// number of z chunks: fill whole rounds of `ctas` CTAs, chunks of >= 16 planes, few halo planes per chunk
+Sched make_sched(const Dims d, int TX, int TY, int halo_planes, double halo_cost, int ctas) {
     Sched s;
     s.tiles_x = (d.X + TX - 1) / TX;
     s.tiles_y = (d.Y + TY - 1) / TY;
     const int xy = s.tiles_x * s.tiles_y;
-    // pick the number of z chunks so that the item count fills whole rounds of `ctas` CTAs (chunks >= 16 planes)
     int best_nz = 1;
     double best_score = -1.0;
-    for (int nz = 1; nz <= d.Z / 8 && nz <= 64; ++nz) {
+    for (int nz = 1; nz <= 64; ++nz) {
         const int chunk = (d.Z + nz - 1) / nz;
         if (chunk < 16 && nz > 1) break;
         const int n = xy * ((d.Z + chunk - 1) / chunk);
         const int rounds = (n + ctas - 1) / ctas;
         const double balance = (double)n / ((double)rounds * ctas);
-        const double overlap = (double)chunk / (chunk + 6.0 * 0.35);   // the 6 window-fill steps are ~1/3 of a full step
-        const double score = balance * overlap;
-        if (score > best_score) { best_score = score; best_nz = nz; }
+        const double overlap = (double)chunk / (chunk + halo_planes * halo_cost);
+        if (balance * overlap > best_score) { best_score = balance * overlap; best_nz = nz; }
     }
     s.zchunk = (d.Z + best_nz - 1) / best_nz;
     s.nz = (d.Z + s.zchunk - 1) / s.zchunk;
@@ -264,30 +417,20 @@ Sched make_sched(const Dims d, int ctas) {
 }  // namespace
 
 TmaMaps *tma_maps_create(const LoopArgs &a) {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) return nullptr;
+    if (!get_tensor_map_encoder()) return nullptr;
     TmaMaps *m = new TmaMaps();
-    float *base[3] = {a.gx, a.gy, a.gz};
-    for (int c = 0; c < 3; ++c) {
-        const cuuint64_t dims[3] = {(cuuint64_t)a.gl.PX, (cuuint64_t)a.gl.PY, (cuuint64_t)a.gl.PZ};
-        const cuuint64_t strides[2] = {(cuuint64_t)a.gl.PX * 4, (cuuint64_t)a.gl.plane * 4};
-        const cuuint32_t box[3] = {SX, SY, 1};
-        const cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = enc(&m->m[c], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base[c], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            fprintf(stderr, "sobfu_b200: cuTensorMapEncodeTiled failed (%d); falling back to the generic kernels\n", (int)r);
-            delete m;
-            return nullptr;
-        }
-    }
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(pass_b_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
-            delete m;
-            return nullptr;
-        }
-        attr_set = true;
+    float *g[3] = {a.gx, a.gy, a.gz};
+    const float *in[4] = {a.px, a.py, a.pz, a.w};
+    bool ok = true;
+    for (int c = 0; c < 3; ++c) ok = ok && encode_map_3d(&m->g[c], g[c], a.gl.PX, a.gl.PY, a.gl.PZ, pb::SX, pb::SY);
+    for (int c = 0; c < 4; ++c) ok = ok && encode_map_3d(&m->in[c], in[c], a.d.X, a.d.Y, a.d.Z, pa::SX, pa::SY);
+    ok = ok && cudaFuncSetAttribute(pb::pass_b_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pb::SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
+    if (!ok) {
+        fprintf(stderr, "sobfu_b200: TMA tensor maps unavailable; using the generic kernels\n");
+        cudaGetLastError();
+        delete m;
+        return nullptr;
     }
     return m;
 }
@@ -295,16 +438,18 @@ TmaMaps *tma_maps_create(const LoopArgs &a) {
 void tma_maps_destroy(TmaMaps *m) { delete m; }
 
 void launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, cudaStream_t st) {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    const Sched sc = make_sched(a.d, sms);
-    const int grid = sc.nitems < sms ? sc.nitems : sms;
-    pass_b_tma_kernel<<<grid, NW * 32, SMEM_BYTES, st>>>(m->m[0], m->m[1], m->m[2], a, it, sc);
+    const int ctas = sm_count();
+    const Sched sc = make_sched(a.d, pb::TX, pb::TY, 6, 0.35, ctas);
+    const int grid = sc.nitems < ctas ? sc.nitems : ctas;
+    pb::pass_b_tma_kernel<<<grid, pb::NW * 32, pb::SMEM_BYTES, st>>>(m->g[0], m->g[1], m->g[2], a, it, sc);
+}
+
+void launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, cudaStream_t st) {
+    if (log) { launch_pass_a_generic(a, it, 1, st); return; }   // logging iterations (rare) also accumulate the energies
+    const int ctas = 2 * sm_count();
+    const Sched sc = make_sched(a.d, pa::TX, pa::TY, 2, 0.5, ctas);
+    const int grid = sc.nitems < ctas ? sc.nitems : ctas;
+    pa::pass_a_tma_kernel<<<grid, pa::NW * 32, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], m->in[3], a, it, sc);
 }
 
 }  // namespace sb
