@@ -92,8 +92,8 @@ int sobfu_b200_solver_get_log(sobfu_b200_solver *s, sobfu_b200_iter_log *out, in
 int sobfu_b200_solver_get_taps(sobfu_b200_solver *s, float *taps7);
 /* bytes of device scratch owned by the handle */
 size_t sobfu_b200_solver_workspace_bytes(sobfu_b200_solver *s);
-/* kernel variant: 0 = auto (fastest applicable), 1 = generic per-voxel kernels, 2 = TMA pipelines for both passes,
- * 3 = register-window pass A (no TMA) + TMA pass B */
+/* kernel variant: 0 = auto (fastest applicable), 1 = generic per-voxel kernels, 2 = TMA pipelines for both passes
+ */
 int sobfu_b200_solver_set_variant(sobfu_b200_solver *s, int variant);
 /* benchmarking aid: run `iters` gradient-descent iterations on the state left by the last estimate_psi
  * without convergence checks; returns device ms of pass A, pass B and the whole loop */

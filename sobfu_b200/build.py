@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libsobfu_b200.so")
-SOURCES = ["capi.cu", "solver_generic.cu", "pass_a_tiled.cu", "solver_tiled.cu", "field_ops.cu", "tsdf_ops.cu", "marching_cubes.cu"]
+SOURCES = ["capi.cu", "solver_generic.cu", "solver_tiled.cu", "field_ops.cu", "tsdf_ops.cu", "marching_cubes.cu"]
 # --ftz/--prec-* are the reference's numerics flags (CMakeLists.txt:42-44): parity depends on them
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -247,6 +247,29 @@ extern "C" int sobfu_b200_solver_create(sobfu_b200_solver **out, const sobfu_b20
     s->h_energies.resize(2 * mi);
     fill_args(s);
     if (tiled_supported(s->d)) s->tma = tma_maps_create(s->args);   // nullptr if the driver entry point is unavailable
+    // phi_n.x (4 B/voxel) is gathered by every iteration of pass B and never written during a solve: ask L2 to keep it
+    // resident (persisting access-policy window on the solver stream).  Best effort: failures are ignored.
+    if (getenv("SOBFU_B200_L2_PERSIST")) {   // measured slower on B200 (r1): off unless asked for
+        int dev = 0, max_persist = 0, max_window = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        const size_t want = s->N * sizeof(float);
+        if (max_persist > 0 && max_window > 0) {
+            const size_t win = want < (size_t)max_window ? want : (size_t)max_window;
+            const size_t carve = win < (size_t)max_persist ? win : (size_t)max_persist;
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof av);
+            av.accessPolicyWindow.base_ptr = const_cast<float *>(s->args.pn);
+            av.accessPolicyWindow.num_bytes = win;
+            av.accessPolicyWindow.hitRatio = carve >= win ? 1.0f : (float)carve / (float)win;
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        }
+        cudaGetLastError();
+    }
     *out = s;
     return 0;
 }
@@ -258,7 +281,7 @@ extern "C" int sobfu_b200_solver_get_taps(sobfu_b200_solver *s, float *t) {
     return 0;
 }
 extern "C" int sobfu_b200_solver_set_variant(sobfu_b200_solver *s, int v) {
-    if (!s || v < 0 || v > 3) return fail(SOBFU_B200_EINVAL, "variant must be 0..3");
+    if (!s || v < 0 || v > 2) return fail(SOBFU_B200_EINVAL, "variant must be 0, 1 or 2");
     if (v >= 2 && !(tiled_supported(s->d) && s->tma)) return fail(SOBFU_B200_EINVAL, "tiled/TMA kernels do not support dims %dx%dx%d", s->d.X, s->d.Y, s->d.Z);
     s->variant = v;
     return 0;
@@ -270,7 +293,6 @@ static inline bool log_iter(const sobfu_b200_params &p, int iter1) {   // iter1 
 
 static void run_pass_a(sobfu_b200_solver *s, int it, int log) {
     if (!use_tiled(s)) launch_pass_a_generic(s->args, it, log, s->stream);
-    else if (s->variant == 3) launch_pass_a_tiled(s->args, it, log, s->stream);
     else launch_pass_a_tma(s->args, s->tma, it, log, s->stream);
 }
 static void run_pass_b(sobfu_b200_solver *s, int it) {
@@ -322,6 +344,7 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
     CK(cudaEventRecord(s->ev[2], st));
 
     // tail (solver.cu:195-199): write back psi / phi_n o psi, psi^-1 from identity (48 fixed-point steps), phi_global o psi^-1
+    if (use_tiled(s) && mi > 0) { launch_initial_warp(s->args, st); ++launches; }   // the TMA loop keeps phi_n o psi on chip
     launch_pack(psi, phi_n_psi, phi_n, s->args, st);
     launch_estimate_inverse(psi, psi_inv, s->d, 48, true, st);
     launch_apply(phi_global, phi_global_psi_inv, psi_inv, s->d, st);

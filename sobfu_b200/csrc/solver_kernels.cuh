@@ -63,7 +63,6 @@ void launch_pack(float4 *psi, float2 *phi_n_psi, const float2 *phi_n, const Loop
 
 // tiled kernels (pass_a_tiled.cu / pass_b_tma.cu); return false when the shape is not supported
 bool tiled_supported(const Dims d);
-void launch_pass_a_tiled(const LoopArgs &a, int it, int log, cudaStream_t st);
 struct TmaMaps;   // opaque: CUtensorMaps of the nabla_U components (pass B) and of the psi / w planes (pass A)
 TmaMaps *tma_maps_create(const LoopArgs &a);
 void tma_maps_destroy(TmaMaps *m);

@@ -1,10 +1,12 @@
 // solver_tiled.cu -- the two kernels of a solver iteration as persistent, TMA-fed, z-marching pipelines (sm_100a).
 //
-//   pass A   nabla_U = (phi_n o psi - phi_global) * grad(phi_n o psi) + w_reg * L(psi)
+//   pass A   w = (phi_n o psi).x                                   (apply_kernel vector_fields.cu:81-100, solver.cu:106,168)
+//            nabla_U = (w - phi_global) * grad(w) + w_reg * L(psi)
 //            (TsdfDifferentiator vector_fields.cu:157-208, laplacian :291-337, potential gradient solver.cu:15-33)
 //   pass B   nabla_U_S = S *x nabla_U + S *y nabla_U + S *z nabla_U   (solver.cu:237-446, 7 taps, clamp to edge)
 //            psi -= alpha * nabla_U_S ; arg-max partials of |alpha * nabla_U_S|   (solver.cu:53-69, reductor.cu:342-456)
-//            (phi_n o psi).x re-warped with the new psi                          (vector_fields.cu:81-100, solver.cu:168)
+// The warp of the live TSDF is computed by its consumer (pass A, tile + a one-voxel cross halo) instead of being
+// written by pass B and read back: the warped volume never touches HBM inside the loop.
 //
 // Mapping to the hardware (both kernels)
 //   * persistent CTAs walk (x-tile, y-tile, z-chunk) work items; the planes an item needs form one continuous stream
@@ -16,7 +18,8 @@
 //   * pass B needs no border cases: pass A stores nabla_U with a replicated halo (clamp to edge == plain TMA box);
 //     pass A reads unpadded planes: out-of-range box elements are zero-filled by TMA and never used, because on a
 //     boundary plane the reference's stencils substitute in-range values (see below)
-// Algorithmic HBM traffic: A 32 B/voxel, B 44 B/voxel (reference layouts: 48 + 64).  Results are bit-identical to the
+// Algorithmic HBM traffic: A 32 B/voxel (psi 12, phi_global 4, phi_n gathers 4, nabla_U 12), B 36 B/voxel
+// (nabla_U 12, psi 12 + 12); the reference's layouts and kernel split would need 48 + 64.  Results are bit-identical to the
 // generic kernels and to the oracle (tests/test_parity_gpu.py).
 #include <cstdio>
 
@@ -27,7 +30,7 @@ namespace sb {
 
 struct TmaMaps {
     CUtensorMap g[3];      // nabla_U components (padded), pass B input
-    CUtensorMap in[4];     // psi x/y/z and (phi_n o psi).x planes, pass A input
+    CUtensorMap in[3];     // psi x/y/z planes, pass A input
 };
 
 namespace {
@@ -37,6 +40,15 @@ struct Sched {
 };
 
 SB_DEVI float c4(const float4 &v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
+
+// (phi_n o psi).x at one voxel: interpolate_tsdf of utils.hpp:50-86 on the phi_n.x plane
+SB_DEVI float warp_sample(const float *__restrict__ pn, float px, float py, float pz, const Dims d, int X, int XY) {
+    const TriCoord t = tri_coord(px, py, pz, d);
+    const int r00 = t.gy * X + t.gz * XY, r10 = t.y1 * X + t.gz * XY;
+    const int r01 = t.gy * X + t.z1 * XY, r11 = t.y1 * X + t.z1 * XY;
+    return tri_lerp(__ldg(pn + r11 + t.x1), __ldg(pn + r10 + t.x1), __ldg(pn + r01 + t.x1), __ldg(pn + r00 + t.x1),
+                    __ldg(pn + r11 + t.gx), __ldg(pn + r10 + t.gx), __ldg(pn + r01 + t.gx), __ldg(pn + r00 + t.gx), t);
+}
 
 // position of a CTA in its plane stream: work item -> tile origin and plane range [p, p_last]
 template <int TX, int TY, int LO, int HI>
@@ -69,14 +81,17 @@ constexpr int LX = 16, RW = 32 / LX, NW = 12;     // 16 lanes x 4 voxels per row
 constexpr int TX = 4 * LX, TY = NW * RW;          // 64 x 24 outputs per plane
 constexpr int SX = TX + 8, SY = TY + 6;           // staged box 4|64|4 floats x 3|24|3 rows
 constexpr int NSTAGE = 6;                         // planes q-3..q live, two in flight
+constexpr int PF_AHEAD = 4;                       // L2 prefetch distance (planes) ahead of the shared-memory fill
 constexpr int COMP_BYTES = ((SX * SY * 4 + 127) / 128) * 128;
 constexpr int STAGE_BYTES = 3 * COMP_BYTES;
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 128;
 constexpr unsigned TX_BYTES = 3u * SX * SY * 4u;
 
-__global__ void __launch_bounds__(NW * 32, 1)
+__global__ void __launch_bounds__((NW + 1) * 32, 1)
     pass_b_tma_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapy,
-                      const __grid_constant__ CUtensorMap mapz, LoopArgs a, int it, Sched sc) {
+                      const __grid_constant__ CUtensorMap mapz, const __grid_constant__ CUtensorMap mpx,
+                      const __grid_constant__ CUtensorMap mpy, const __grid_constant__ CUtensorMap mpz, LoopArgs a, int it,
+                      Sched sc) {
     if (loop_finished(a, it)) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned smem = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -97,31 +112,45 @@ __global__ void __launch_bounds__(NW * 32, 1)
     __syncthreads();
 
     typedef Stream<TX, TY, 3, 3> St;
-    // ---- producer (thread 0 only) ----
-    St pr;
-    unsigned q_issue = 0;
-    auto produce = [&]() {
-        if (!pr.valid(sc)) return;
-        const unsigned slot = q_issue % NSTAGE, n = q_issue / NSTAGE;
-        if (n > 0) mbar_wait(empty0 + 8 * slot, (n - 1) & 1u);     // every warp released the previous plane of this slot
-        const unsigned dst = smem + slot * STAGE_BYTES, bar = full0 + 8 * slot;
-        mbar_expect_tx(bar, TX_BYTES);
-        // padded coordinates: plane z sits at z + 3; the box origin (x0t, y0t) is interior (x0t - 4, y0t - 3)
-        tma_load_3d(dst, &mapx, bar, pr.x0t, pr.y0t, pr.p + 3);
-        tma_load_3d(dst + COMP_BYTES, &mapy, bar, pr.x0t, pr.y0t, pr.p + 3);
-        tma_load_3d(dst + 2 * COMP_BYTES, &mapz, bar, pr.x0t, pr.y0t, pr.p + 3);
-        ++q_issue;
-        pr.next(sc, d.Z);
-    };
-    if (tid == 0) {
+    if (warp == NW) {
+        // ---- producer warp: one lane streams nabla_U planes into the ring and prefetches further ahead into L2 ----
+        if (lane != 0) return;
+        St pr, pf;                         // pf runs PF_AHEAD planes ahead of pr and only prefetches into L2
         pr.open(blockIdx.x, sc, d.Z);
-        produce();
-        produce();
+        pf.open(blockIdx.x, sc, d.Z);
+        auto prefetch = [&]() {
+            if (!pf.valid(sc)) return;
+            tma_prefetch_3d(&mapx, pf.x0t, pf.y0t, pf.p + 3);
+            tma_prefetch_3d(&mapy, pf.x0t, pf.y0t, pf.p + 3);
+            tma_prefetch_3d(&mapz, pf.x0t, pf.y0t, pf.p + 3);
+            // psi of plane r is read with plain LDGs when r is the centre, i.e. 3 planes after nabla_U(r) arrives; pull
+            // it into L2 a few steps before that.  The psi maps carry pass A's box (72 x 18): two boxes cover 24 rows.
+            const int r = pf.p - 3;
+            if (r >= pf.zb) {
+                tma_prefetch_3d(&mpx, pf.x0t, pf.y0t, r); tma_prefetch_3d(&mpx, pf.x0t, pf.y0t + 12, r);
+                tma_prefetch_3d(&mpy, pf.x0t, pf.y0t, r); tma_prefetch_3d(&mpy, pf.x0t, pf.y0t + 12, r);
+                tma_prefetch_3d(&mpz, pf.x0t, pf.y0t, r); tma_prefetch_3d(&mpz, pf.x0t, pf.y0t + 12, r);
+            }
+            pf.next(sc, d.Z);
+        };
+        for (int k = 0; k < PF_AHEAD; ++k) prefetch();
+        for (unsigned qi = 0; pr.valid(sc); ++qi) {
+            prefetch();
+            const unsigned slot = qi % NSTAGE, n = qi / NSTAGE;
+            if (n > 0) mbar_wait(empty0 + 8 * slot, (n - 1) & 1u);   // every warp released the previous plane of this slot
+            const unsigned dst = smem + slot * STAGE_BYTES, bar = full0 + 8 * slot;
+            mbar_expect_tx(bar, TX_BYTES);
+            // padded coordinates: plane z sits at z + 3; the box origin (x0t, y0t) is interior (x0t - 4, y0t - 3)
+            tma_load_3d(dst, &mapx, bar, pr.x0t, pr.y0t, pr.p + 3);
+            tma_load_3d(dst + COMP_BYTES, &mapy, bar, pr.x0t, pr.y0t, pr.p + 3);
+            tma_load_3d(dst + 2 * COMP_BYTES, &mapz, bar, pr.x0t, pr.y0t, pr.p + 3);
+            pr.next(sc, d.Z);
+        }
+        return;
     }
 
     // ---- consumers ----
     float *__restrict__ P[3] = {a.px, a.py, a.pz};
-    const float *__restrict__ pn = a.pn;
     unsigned q = 0;                       // planes consumed so far
     unsigned best_bits = 0u, best_idx = 0u;
     float4 win[7][3];                     // nabla_U of this thread's 4 voxels at planes c-3 .. c+3
@@ -180,31 +209,23 @@ __global__ void __launch_bounds__(NW * 32, 1)
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
                         *reinterpret_cast<float4 *>(P[c] + o) = make_float4(np[c][0], np[c][1], np[c][2], np[c][3]);
-                    float wv[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const TriCoord t = tri_coord(np[0][j], np[1][j], np[2][j], d);
-                        const int r00 = t.gy * X + t.gz * XY, r10 = t.y1 * X + t.gz * XY;
-                        const int r01 = t.gy * X + t.z1 * XY, r11 = t.y1 * X + t.z1 * XY;
-                        wv[j] = tri_lerp(__ldg(pn + r11 + t.x1), __ldg(pn + r10 + t.x1), __ldg(pn + r01 + t.x1), __ldg(pn + r00 + t.x1),
-                                         __ldg(pn + r11 + t.gx), __ldg(pn + r10 + t.gx), __ldg(pn + r01 + t.gx), __ldg(pn + r00 + t.gx), t);
                         const unsigned bits = __float_as_uint(nsq[j]), idx = (unsigned)(o + j);
                         if (bits > best_bits) { best_bits = bits; best_idx = idx; }
                         else if (bits == best_bits && bits != 0u && rank_of(idx, a.rm) < rank_of(best_idx, a.rm)) best_idx = idx;
                     }
-                    *reinterpret_cast<float4 *>(a.w + o) = make_float4(wv[0], wv[1], wv[2], wv[3]);
                 }
             }
             // hand the stage of plane q-4 (0-based: the centre plane just used) back to the producer
             __syncwarp();
             if (lane == 0 && q >= 4u) mbar_arrive(empty0 + 8 * ((q - 4u) % NSTAGE));
-            if (tid == 0) produce();
         }
     }
     unsigned long long best = best_bits ? (((unsigned long long)best_bits << 32) | (unsigned long long)(0xffffffffu - rank_of(best_idx, a.rm))) : 0ull;
     best = warp_max_u64(best);
     if (lane == 0) skey[warp] = best;
-    __syncthreads();
+    asm volatile("bar.sync 1, %0;" ::"r"(NW * 32) : "memory");   // consumers only (the producer warp has left)
     if (tid == 0) {
         unsigned long long m = 0ull;
 #pragma unroll
@@ -218,18 +239,27 @@ __global__ void __launch_bounds__(NW * 32, 1)
 // pass A
 // =============================================================================================================
 namespace pa {
-constexpr int LX = 16, RW = 32 / LX, NW = 8;      // 256 threads
+constexpr int LX = 16, RW = 32 / LX, NW = 8;      // 8 consumer warps + 1 producer warp
+constexpr int NCONS = NW * 32;
 constexpr int TX = 4 * LX, TY = NW * RW;          // 64 x 16 outputs per plane
 constexpr int SX = TX + 8, SY = TY + 2;           // staged box 4|64|4 floats x 1|16|1 rows
-constexpr int NSTAGE = 5;                         // planes q-2..q live, two in flight
+constexpr int NSTAGE = 6;                         // planes q-1, q live (z-1 is kept in registers), four in flight
+constexpr int PF_AHEAD = 4;                       // L2 prefetch distance ahead of the shared-memory fill
 constexpr int ARR_BYTES = ((SX * SY * 4 + 127) / 128) * 128;
-constexpr int STAGE_BYTES = 4 * ARR_BYTES;        // psi x, y, z, w
-constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 128;
-constexpr unsigned TX_BYTES = 4u * SX * SY * 4u;
+constexpr int STAGE_BYTES = 3 * ARR_BYTES;        // psi x, y, z
+constexpr int WBUF_BYTES = ARR_BYTES;             // one plane of warped TSDF (tile + cross halo), same geometry
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 3 * WBUF_BYTES + 128;
+constexpr unsigned TX_BYTES = 3u * SX * SY * 4u;
+constexpr int NHALO = 2 * TX + 2 * TY;            // cross halo cells of a plane: rows y0-1, y0+TY and columns x0-1, x0+TX
 
-__global__ void __launch_bounds__(NW * 32, 2)
+SB_DEVI void sts4(unsigned saddr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+SB_DEVI void sts1(unsigned saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
+
+__global__ void __launch_bounds__((NW + 1) * 32, 2)
     pass_a_tma_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__ CUtensorMap m1,
-                      const __grid_constant__ CUtensorMap m2, const __grid_constant__ CUtensorMap m3, LoopArgs a, int it, Sched sc) {
+                      const __grid_constant__ CUtensorMap m2, LoopArgs a, int it, Sched sc) {
     if (loop_finished(a, it)) {
         if (a.check && blockIdx.x == 0 && threadIdx.x == 0 && !a.state->converged) {
             a.state->iters = it;
@@ -239,14 +269,13 @@ __global__ void __launch_bounds__(NW * 32, 2)
     }
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned smem = (smem_u32(smem_raw) + 127u) & ~127u;
+    const unsigned wbuf0 = smem + NSTAGE * STAGE_BYTES;
     __shared__ unsigned long long bars[2 * NSTAGE];
     const unsigned full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[NSTAGE]);
 
     const Dims d = a.d;
     const int X = d.X, XY = d.X * d.Y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int lx = lane % LX, ty = warp * RW + lane / LX;
-    const unsigned own_off = (unsigned)(((ty + 1) * SX + 4 * lx + 4) * 4);
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NW); }
@@ -255,29 +284,47 @@ __global__ void __launch_bounds__(NW * 32, 2)
     __syncthreads();
 
     typedef Stream<TX, TY, 1, 1> St;
-    St pr;
-    unsigned q_issue = 0;
-    auto produce = [&]() {
-        if (!pr.valid(sc)) return;
-        const unsigned slot = q_issue % NSTAGE, n = q_issue / NSTAGE;
-        if (n > 0) mbar_wait(empty0 + 8 * slot, (n - 1) & 1u);
-        const unsigned dst = smem + slot * STAGE_BYTES, bar = full0 + 8 * slot;
-        mbar_expect_tx(bar, TX_BYTES);
-        // unpadded planes: the box starts 4 floats / 1 row before the tile; out-of-range elements arrive as zeros
-        tma_load_3d(dst, &m0, bar, pr.x0t - 4, pr.y0t - 1, pr.p);
-        tma_load_3d(dst + ARR_BYTES, &m1, bar, pr.x0t - 4, pr.y0t - 1, pr.p);
-        tma_load_3d(dst + 2 * ARR_BYTES, &m2, bar, pr.x0t - 4, pr.y0t - 1, pr.p);
-        tma_load_3d(dst + 3 * ARR_BYTES, &m3, bar, pr.x0t - 4, pr.y0t - 1, pr.p);
-        ++q_issue;
-        pr.next(sc, d.Z);
-    };
-    if (tid == 0) {
+    if (warp == NW) {
+        // ---- producer warp: one lane streams psi planes into the ring and prefetches further ahead into L2 ----
+        if (lane != 0) return;
+        St pr, pf;
         pr.open(blockIdx.x, sc, d.Z);
-        produce();
-        produce();
+        pf.open(blockIdx.x, sc, d.Z);
+        auto prefetch = [&]() {
+            if (!pf.valid(sc)) return;
+            tma_prefetch_3d(&m0, pf.x0t - 4, pf.y0t - 1, pf.p);
+            tma_prefetch_3d(&m1, pf.x0t - 4, pf.y0t - 1, pf.p);
+            tma_prefetch_3d(&m2, pf.x0t - 4, pf.y0t - 1, pf.p);
+            pf.next(sc, d.Z);
+        };
+        for (int k = 0; k < PF_AHEAD; ++k) prefetch();
+        for (unsigned qi = 0; pr.valid(sc); ++qi) {
+            prefetch();
+            const unsigned slot = qi % NSTAGE, n = qi / NSTAGE;
+            if (n > 0) mbar_wait(empty0 + 8 * slot, (n - 1) & 1u);
+            const unsigned dst = smem + slot * STAGE_BYTES, bar = full0 + 8 * slot;
+            mbar_expect_tx(bar, TX_BYTES);
+            // unpadded planes: the box starts 4 floats / 1 row before the tile; out-of-range elements arrive as zeros
+            tma_load_3d(dst, &m0, bar, pr.x0t - 4, pr.y0t - 1, pr.p);
+            tma_load_3d(dst + ARR_BYTES, &m1, bar, pr.x0t - 4, pr.y0t - 1, pr.p);
+            tma_load_3d(dst + 2 * ARR_BYTES, &m2, bar, pr.x0t - 4, pr.y0t - 1, pr.p);
+            pr.next(sc, d.Z);
+        }
+        return;
     }
 
+    // ---- consumers ----
+    const int lx = lane % LX, ty = warp * RW + lane / LX;
+    const unsigned own_off = (unsigned)(((ty + 1) * SX + 4 * lx + 4) * 4);
+    // cross-halo cell served by this thread (threads 0 .. NHALO-1): position inside the staged box
+    int hx = -1, hy = -1;                      // box coordinates (floats / rows)
+    if (tid < TX) { hx = 4 + tid; hy = 0; }
+    else if (tid < 2 * TX) { hx = 4 + tid - TX; hy = TY + 1; }
+    else if (tid < 2 * TX + TY) { hx = 3; hy = 1 + tid - 2 * TX; }
+    else if (tid < NHALO) { hx = 4 + TX; hy = 1 + tid - 2 * TX - TY; }
+    const unsigned halo_off = (unsigned)((hy * SX + hx) * 4);
     float *__restrict__ G[3] = {a.gx, a.gy, a.gz};
+    const float *__restrict__ pn = a.pn;
     const GLayout gl = a.gl;
     unsigned q = 0;
     St cs;
@@ -286,26 +333,51 @@ __global__ void __launch_bounds__(NW * 32, 2)
         const bool active = x0 < X && y < d.Y;
         const int row = min(x0, X - 4) + X * min(y, d.Y - 1);
         const bool y_lo = (y == 0), y_hi = (y == d.Y - 1), by = y_lo || y_hi;
+        const int hgx = cs.x0t - 4 + hx, hgy = cs.y0t - 1 + hy;       // volume coordinates of the halo cell
+        const bool halo_on = hx >= 0 && hgx >= 0 && hgx < X && hgy >= 0 && hgy < d.Y;
+        // this thread's quads at planes z-1 and z: psi (3 components) and the warped TSDF
+        float4 zm[3], zc4[3], wm, wc;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) zm[k] = zc4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        wm = wc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int p = cs.p; p <= cs.p_last; ++p) {
             const unsigned slot = q % NSTAGE;
-            // phi_global of the plane that becomes the centre in this iteration: issue before the wait
-            const int zc = p - 1;
+            const int zc = p - 1;             // plane that becomes the centre when plane p has arrived
             float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (zc >= cs.zb) g4 = *reinterpret_cast<const float4 *>(a.pg + row + XY * zc);
             mbar_wait(full0 + 8 * slot, (q / NSTAGE) & 1u);
+            const unsigned wcur = wbuf0 + (q % 3u) * WBUF_BYTES;             // warped plane p   (written now)
+            const unsigned wctr = wbuf0 + ((q + 2u) % 3u) * WBUF_BYTES;      // warped plane p-1 (written last iteration)
             ++q;
+            const unsigned stP = smem + slot * STAGE_BYTES;                                  // plane p   (z+1)
+            const unsigned sC = smem + ((q + NSTAGE - 2u) % NSTAGE) * STAGE_BYTES + own_off; // plane p-1 (centre)
+            float4 zp[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) zp[k] = lds4(stP + own_off + k * ARR_BYTES);
+            // ---- phase 1: warp plane p (own quad + one cross-halo cell); planes outside the volume are never used ----
+            float4 wp = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p >= 0 && p < d.Z) {
+                if (active) {
+                    wp.x = warp_sample(pn, zp[0].x, zp[1].x, zp[2].x, d, X, XY);
+                    wp.y = warp_sample(pn, zp[0].y, zp[1].y, zp[2].y, d, X, XY);
+                    wp.z = warp_sample(pn, zp[0].z, zp[1].z, zp[2].z, d, X, XY);
+                    wp.w = warp_sample(pn, zp[0].w, zp[1].w, zp[2].w, d, X, XY);
+                }
+                sts4(wcur + own_off, wp);
+                if (halo_on) {
+                    const float hxv = lds1(stP + halo_off), hyv = lds1(stP + halo_off + ARR_BYTES), hzv = lds1(stP + halo_off + 2 * ARR_BYTES);
+                    sts1(wcur + halo_off, warp_sample(pn, hxv, hyv, hzv, d, X, XY));
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(NCONS) : "memory");     // warped plane p (and p-1) visible to all consumers
+            // ---- phase 2: nabla_U of the centre plane ----
             if (zc >= cs.zb) {
-                // stages: z+1 = plane q-1 (just arrived), centre = q-2, z-1 = q-3
-                const unsigned sP = smem + ((q - 1u) % NSTAGE) * STAGE_BYTES + own_off;
-                const unsigned sC = smem + ((q - 2u) % NSTAGE) * STAGE_BYTES + own_off;
-                const unsigned sM = smem + ((q + NSTAGE - 3u) % NSTAGE) * STAGE_BYTES + own_off;
                 const bool z_lo = (zc == 0), z_hi = (zc == d.Z - 1), bz = z_lo || z_hi;
-                // warped TSDF: central differences, both taps on the in-range neighbour at a boundary (-> +0)
+                // central differences of the warped TSDF; both taps on the in-range neighbour at a boundary (-> +0)
                 float nx[4], ny[4], nz[4], df[4];
                 {
-                    const unsigned w0 = sC + 3 * ARR_BYTES;
-                    const float4 C = lds4(w0), Ym = lds4(w0 - SX * 4), Yp = lds4(w0 + SX * 4);
-                    const float4 Zm = lds4(sM + 3 * ARR_BYTES), Zp = lds4(sP + 3 * ARR_BYTES);
+                    const unsigned w0 = wctr + own_off;
+                    const float4 C = wc, Ym = lds4(w0 - SX * 4), Yp = lds4(w0 + SX * 4);
                     const float xl = lds1(w0 - 4), xr = lds1(w0 + 16);
                     const float xm[4] = {xl, C.x, C.y, C.z}, xp[4] = {C.y, C.z, C.w, xr};
 #pragma unroll
@@ -313,7 +385,7 @@ __global__ void __launch_bounds__(NW * 32, 2)
                         const bool x_lo = (x0 + j == 0), x_hi = (x0 + j == X - 1);
                         const float a1 = x_hi ? xm[j] : xp[j], a2 = x_lo ? xp[j] : xm[j];
                         const float b1 = y_hi ? c4(Ym, j) : c4(Yp, j), b2 = y_lo ? c4(Yp, j) : c4(Ym, j);
-                        const float c1 = z_hi ? c4(Zm, j) : c4(Zp, j), c2 = z_lo ? c4(Zp, j) : c4(Zm, j);
+                        const float c1 = z_hi ? c4(wm, j) : c4(wp, j), c2 = z_lo ? c4(wp, j) : c4(wm, j);
                         nx[j] = mul(sub(a1, a2), 0.5f);      // __fdividef(., 2.f)
                         ny[j] = mul(sub(b1, b2), 0.5f);
                         nz[j] = mul(sub(c1, c2), 0.5f);
@@ -324,8 +396,7 @@ __global__ void __launch_bounds__(NW * 32, 2)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const unsigned p0 = sC + c * ARR_BYTES;
-                    const float4 C = lds4(p0), Ym = lds4(p0 - SX * 4), Yp = lds4(p0 + SX * 4);
-                    const float4 Zm = lds4(sM + c * ARR_BYTES), Zp = lds4(sP + c * ARR_BYTES);
+                    const float4 C = zc4[c], Ym = lds4(p0 - SX * 4), Yp = lds4(p0 + SX * 4);
                     const float xl = lds1(p0 - 4), xr = lds1(p0 + 16);
                     const float xm[4] = {xl, C.x, C.y, C.z}, xp[4] = {C.y, C.z, C.w, xr};
                     float u[4];
@@ -339,8 +410,8 @@ __global__ void __launch_bounds__(NW * 32, 2)
                         v = add(v, bx ? ctr : xm[j]);
                         v = add(v, by ? ctr : c4(Yp, j));
                         v = add(v, by ? ctr : c4(Ym, j));
-                        v = add(v, bz ? ctr : c4(Zp, j));
-                        v = add(v, bz ? ctr : c4(Zm, j));
+                        v = add(v, bz ? ctr : c4(zp[c], j));
+                        v = add(v, bz ? ctr : c4(zm[c], j));
                         const float Lv = mul(v, -1.f);
                         const float n = (c == 0) ? nx[j] : (c == 1 ? ny[j] : nz[j]);
                         u[j] = add(mul(n, df[j]), mul(Lv, a.w_reg));
@@ -371,10 +442,12 @@ __global__ void __launch_bounds__(NW * 32, 2)
                     }
                 }
             }
-            // the z-1 plane of this iteration (plane q-3, 0-based) is not needed any more
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { zm[k] = zc4[k]; zc4[k] = zp[k]; }
+            wm = wc; wc = wp;
+            // the stage of plane p-1 (the centre just used; its quads now live in registers) can be refilled
             __syncwarp();
-            if (lane == 0 && q >= 3u) mbar_arrive(empty0 + 8 * ((q - 3u) % NSTAGE));
-            if (tid == 0) produce();
+            if (lane == 0 && q >= 2u) mbar_arrive(empty0 + 8 * ((q - 2u) % NSTAGE));
         }
     }
 }
@@ -416,14 +489,17 @@ Sched make_sched(const Dims d, int TX, int TY, int halo_planes, double halo_cost
 
 }  // namespace
 
+// 16 B vector accesses and TMA row pitches need X % 4 == 0
+bool tiled_supported(const Dims d) { return d.X % 4 == 0 && d.X >= 32 && d.Y >= 8 && d.Z >= 8; }
+
 TmaMaps *tma_maps_create(const LoopArgs &a) {
     if (!get_tensor_map_encoder()) return nullptr;
     TmaMaps *m = new TmaMaps();
     float *g[3] = {a.gx, a.gy, a.gz};
-    const float *in[4] = {a.px, a.py, a.pz, a.w};
+    const float *in[3] = {a.px, a.py, a.pz};
     bool ok = true;
     for (int c = 0; c < 3; ++c) ok = ok && encode_map_3d(&m->g[c], g[c], a.gl.PX, a.gl.PY, a.gl.PZ, pb::SX, pb::SY);
-    for (int c = 0; c < 4; ++c) ok = ok && encode_map_3d(&m->in[c], in[c], a.d.X, a.d.Y, a.d.Z, pa::SX, pa::SY);
+    for (int c = 0; c < 3; ++c) ok = ok && encode_map_3d(&m->in[c], in[c], a.d.X, a.d.Y, a.d.Z, pa::SX, pa::SY);
     ok = ok && cudaFuncSetAttribute(pb::pass_b_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pb::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
     if (!ok) {
@@ -441,15 +517,19 @@ void launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, cudaStream_t
     const int ctas = sm_count();
     const Sched sc = make_sched(a.d, pb::TX, pb::TY, 6, 0.35, ctas);
     const int grid = sc.nitems < ctas ? sc.nitems : ctas;
-    pb::pass_b_tma_kernel<<<grid, pb::NW * 32, pb::SMEM_BYTES, st>>>(m->g[0], m->g[1], m->g[2], a, it, sc);
+    pb::pass_b_tma_kernel<<<grid, (pb::NW + 1) * 32, pb::SMEM_BYTES, st>>>(m->g[0], m->g[1], m->g[2], m->in[0], m->in[1], m->in[2], a, it, sc);
 }
 
 void launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, cudaStream_t st) {
-    if (log) { launch_pass_a_generic(a, it, 1, st); return; }   // logging iterations (rare) also accumulate the energies
+    if (log) {   // logging iterations (rare): materialise the warped plane, then the generic kernel that also sums the energies
+        launch_initial_warp(a, st);
+        launch_pass_a_generic(a, it, 1, st);
+        return;
+    }
     const int ctas = 2 * sm_count();
     const Sched sc = make_sched(a.d, pa::TX, pa::TY, 2, 0.5, ctas);
     const int grid = sc.nitems < ctas ? sc.nitems : ctas;
-    pa::pass_a_tma_kernel<<<grid, pa::NW * 32, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], m->in[3], a, it, sc);
+    pa::pass_a_tma_kernel<<<grid, (pa::NW + 1) * 32, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
 }
 
 }  // namespace sb

@@ -36,6 +36,10 @@ SB_DEVI void tma_load_3d(unsigned dst, const CUtensorMap *map, unsigned bar, int
         "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// L2 prefetch of a box (no shared-memory destination, no completion tracking): cp.async.bulk.prefetch.tensor
+SB_DEVI void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 SB_DEVI float4 lds4(unsigned saddr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));

@@ -228,7 +228,7 @@ def test_tiled_tma_kernels_match_oracle_and_generic(env, dims, iters):
     pg, pn, vs, trunc, eta = sphere_pair(dims, r=0.07)
     psi0 = wavy_psi(dims, amp=0.5)
     want = orc.estimate_psi(pg, pn, psi0, iters, -1.0, 7, 0.2, 0.02, 0.3)
-    for variant in (2, 3, 1):
+    for variant in (2, 1):
         got = run_solver(sf, torch, dims, pg, pn, psi0, vs, trunc, eta, iters, -1.0, 0.02, 0.3, variant=variant, lam=0.2)
         compare_solver(got, want, "variant %d %s" % (variant, dims))
 
