@@ -169,6 +169,10 @@ struct sobfu_b200_solver {
     cudaEvent_t ev_user = nullptr;
     int variant = 0;
     TmaMaps *tma = nullptr;
+    cudaArray_t pn_array = nullptr;           // phi_n.x gather4 atlas (see LoopArgs::pn_tex)
+    cudaTextureObject_t pn_tex = 0;
+    cudaSurfaceObject_t pn_surf = 0;
+    int ashift = 0, amask = 0;
     // host staging for the *_host entry point
     void *stage_dev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     void *stage_pinned[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -192,11 +196,43 @@ static void fill_args(sobfu_b200_solver *s) {
     a.state = s->state; a.maxkey = s->maxkey; a.e_data = s->energies; a.e_reg = s->energies + s->p.max_iter;
     a.rm = rank_map_for(s->N);
     a.check = 1;
+    a.pn_tex = s->pn_tex; a.pn_surf = s->pn_surf; a.ashift = s->ashift; a.amask = s->amask;
+}
+
+// phi_n.x as a 2-D atlas of Z slices (kx = 2^ashift per row) in a CUDA array that supports texture gather
+static void create_atlas(sobfu_b200_solver *s) {
+    if (getenv("SOBFU_B200_NO_TEX")) return;
+    int shift = 0;
+    while ((1 << (2 * shift)) < s->d.Z) ++shift;               // kx = 2^shift >= sqrt(Z)
+    const int kx = 1 << shift, ky = (s->d.Z + kx - 1) / kx;
+    const long long W = (long long)kx * s->d.X, H = (long long)ky * s->d.Y;
+    if (W > 32768 || H > 32768) return;                        // gather-capable 2-D arrays are limited to 32768 x 32768
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc<float>();
+    if (cudaMallocArray(&s->pn_array, &cd, (size_t)W, (size_t)H, cudaArrayTextureGather | cudaArraySurfaceLoadStore) != cudaSuccess) {
+        cudaGetLastError(); s->pn_array = nullptr; return;
+    }
+    cudaResourceDesc rd; memset(&rd, 0, sizeof rd);
+    rd.resType = cudaResourceTypeArray; rd.res.array.array = s->pn_array;
+    cudaTextureDesc td; memset(&td, 0, sizeof td);
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+    if (cudaCreateTextureObject(&s->pn_tex, &rd, &td, nullptr) != cudaSuccess || cudaCreateSurfaceObject(&s->pn_surf, &rd) != cudaSuccess) {
+        cudaGetLastError();
+        if (s->pn_tex) cudaDestroyTextureObject(s->pn_tex);
+        cudaFreeArray(s->pn_array);
+        s->pn_array = nullptr; s->pn_tex = 0; s->pn_surf = 0;
+        return;
+    }
+    s->ashift = shift; s->amask = kx - 1;
+    s->ws_bytes += (size_t)W * H * sizeof(float);
 }
 
 extern "C" int sobfu_b200_solver_destroy(sobfu_b200_solver *s) {
     if (!s) return 0;
     if (s->tma) tma_maps_destroy(s->tma);
+    if (s->pn_tex) cudaDestroyTextureObject(s->pn_tex);
+    if (s->pn_surf) cudaDestroySurfaceObject(s->pn_surf);
+    if (s->pn_array) cudaFreeArray(s->pn_array);
     cudaFree(s->planes); cudaFree(s->g); cudaFree(s->state); cudaFree(s->maxkey); cudaFree(s->energies);
     if (s->h_state) cudaFreeHost(s->h_state);
     for (int i = 0; i < 6; ++i) { if (s->stage_dev[i]) cudaFree(s->stage_dev[i]); if (s->stage_pinned[i]) cudaFreeHost(s->stage_pinned[i]); }
@@ -245,6 +281,7 @@ extern "C" int sobfu_b200_solver_create(sobfu_b200_solver **out, const sobfu_b20
     s->ws_bytes = 6 * s->N * sizeof(float) + 3 * s->gl.total * sizeof(float) + mi * 24 + sizeof(LoopState);
     s->h_maxkey.resize(mi);
     s->h_energies.resize(2 * mi);
+    if (tiled_supported(s->d)) create_atlas(s);
     fill_args(s);
     if (tiled_supported(s->d)) s->tma = tma_maps_create(s->args);   // nullptr if the driver entry point is unavailable
     // phi_n.x (4 B/voxel) is gathered by every iteration of pass B and never written during a solve: ask L2 to keep it

@@ -24,7 +24,13 @@ __global__ void unpack_kernel(const float4 *__restrict__ psi, const float2 *__re
         const float4 p = psi[i];
         a.px[i] = p.x; a.py[i] = p.y; a.pz[i] = p.z;
         const_cast<float *>(a.pg)[i] = phi_global[i].x;
-        const_cast<float *>(a.pn)[i] = phi_n[i].x;
+        const float v = phi_n[i].x;
+        const_cast<float *>(a.pn)[i] = v;
+        if (a.pn_surf) {   // same value into the gather4 atlas
+            const int XY = a.d.X * a.d.Y;
+            const int z = (int)(i / XY), r = (int)(i - (size_t)z * XY), y = r / a.d.X, x = r - y * a.d.X;
+            surf2Dwrite(v, a.pn_surf, (int)sizeof(float) * ((z & a.amask) * a.d.X + x), (z >> a.ashift) * a.d.Y + y);
+        }
     }
 }
 

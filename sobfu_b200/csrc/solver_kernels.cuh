@@ -44,6 +44,11 @@ struct LoopArgs {
     double *e_data, *e_reg;       // [max_iter] (sums, not yet halved)
     RankMap rm;
     int check;                    // 0: time_loop mode (no convergence logic)
+    // phi_n.x as a 2-D texture atlas (slice z at tile (z & amask, z >> ashift) of X x Y texels) for gather4 fetches of
+    // the trilinear footprint; 0 when unavailable (then phi_n.x is gathered from the pn plane with plain loads)
+    cudaTextureObject_t pn_tex;
+    cudaSurfaceObject_t pn_surf;
+    int ashift, amask;
 };
 
 // decision shared by every block of iteration `it` (0-based): has the loop already ended?

@@ -50,6 +50,25 @@ SB_DEVI float warp_sample(const float *__restrict__ pn, float px, float py, floa
                     __ldg(pn + r11 + t.gx), __ldg(pn + r10 + t.gx), __ldg(pn + r01 + t.gx), __ldg(pn + r00 + t.gx), t);
 }
 
+// Same value through the texture unit: two gather4 fetches (planes gz and z1) return the 2 x 2 x 2 footprint, with no
+// address arithmetic and no load instructions in the SM's LSU.  x1 / y1 equal gx / gy on the first and last planes
+// (utils.hpp:61-72); the neighbouring texel returned by the gather is then replaced by the base texel, so the value is
+// bit-identical to warp_sample() for every input.
+SB_DEVI float warp_sample_tex(cudaTextureObject_t tex, int ashift, int amask, float px, float py, float pz, const Dims d) {
+    const TriCoord t = tri_coord(px, py, pz, d);
+    const float u = (float)t.gx + 1.f, v = (float)t.gy + 1.f;     // footprint (gx, gx+1) x (gy, gy+1)
+    const float u0 = u + (float)((t.gz & amask) * d.X), v0 = v + (float)((t.gz >> ashift) * d.Y);
+    const float u1 = u + (float)((t.z1 & amask) * d.X), v1 = v + (float)((t.z1 >> ashift) * d.Y);
+    const float4 lo = tex2Dgather<float4>(tex, u0, v0, 0);          // .w (i,j) .z (i+1,j) .x (i,j+1) .y (i+1,j+1)
+    const float4 hi = tex2Dgather<float4>(tex, u1, v1, 0);
+    const bool sx = t.x1 == t.gx, sy = t.y1 == t.gy;
+    const float v000 = lo.w, v100 = sx ? lo.w : lo.z;
+    const float v010 = sy ? v000 : lo.x, v110 = sy ? v100 : (sx ? lo.x : lo.y);
+    const float v001 = hi.w, v101 = sx ? hi.w : hi.z;
+    const float v011 = sy ? v001 : hi.x, v111 = sy ? v101 : (sx ? hi.x : hi.y);
+    return tri_lerp(v111, v110, v101, v100, v011, v010, v001, v000, t);
+}
+
 // position of a CTA in its plane stream: work item -> tile origin and plane range [p, p_last]
 template <int TX, int TY, int LO, int HI>
 struct Stream {
@@ -243,7 +262,7 @@ constexpr int LX = 16, RW = 32 / LX, NW = 8;      // 8 consumer warps + 1 produc
 constexpr int NCONS = NW * 32;
 constexpr int TX = 4 * LX, TY = NW * RW;          // 64 x 16 outputs per plane
 constexpr int SX = TX + 8, SY = TY + 2;           // staged box 4|64|4 floats x 1|16|1 rows
-constexpr int NSTAGE = 6;                         // planes q-1, q live (z-1 is kept in registers), four in flight
+constexpr int NSTAGE = 4;                         // planes q-1, q live (z-1 is kept in registers), two in flight (+ L2 prefetch)
 constexpr int PF_AHEAD = 4;                       // L2 prefetch distance ahead of the shared-memory fill
 constexpr int ARR_BYTES = ((SX * SY * 4 + 127) / 128) * 128;
 constexpr int STAGE_BYTES = 3 * ARR_BYTES;        // psi x, y, z
@@ -257,6 +276,7 @@ SB_DEVI void sts4(unsigned saddr, float4 v) {
 }
 SB_DEVI void sts1(unsigned saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
 
+template <bool TEX>
 __global__ void __launch_bounds__((NW + 1) * 32, 2)
     pass_a_tma_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__ CUtensorMap m1,
                       const __grid_constant__ CUtensorMap m2, LoopArgs a, int it, Sched sc) {
@@ -358,15 +378,22 @@ __global__ void __launch_bounds__((NW + 1) * 32, 2)
             float4 wp = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p >= 0 && p < d.Z) {
                 if (active) {
-                    wp.x = warp_sample(pn, zp[0].x, zp[1].x, zp[2].x, d, X, XY);
-                    wp.y = warp_sample(pn, zp[0].y, zp[1].y, zp[2].y, d, X, XY);
-                    wp.z = warp_sample(pn, zp[0].z, zp[1].z, zp[2].z, d, X, XY);
-                    wp.w = warp_sample(pn, zp[0].w, zp[1].w, zp[2].w, d, X, XY);
+                    if (TEX) {
+                        wp.x = warp_sample_tex(a.pn_tex, a.ashift, a.amask, zp[0].x, zp[1].x, zp[2].x, d);
+                        wp.y = warp_sample_tex(a.pn_tex, a.ashift, a.amask, zp[0].y, zp[1].y, zp[2].y, d);
+                        wp.z = warp_sample_tex(a.pn_tex, a.ashift, a.amask, zp[0].z, zp[1].z, zp[2].z, d);
+                        wp.w = warp_sample_tex(a.pn_tex, a.ashift, a.amask, zp[0].w, zp[1].w, zp[2].w, d);
+                    } else {
+                        wp.x = warp_sample(pn, zp[0].x, zp[1].x, zp[2].x, d, X, XY);
+                        wp.y = warp_sample(pn, zp[0].y, zp[1].y, zp[2].y, d, X, XY);
+                        wp.z = warp_sample(pn, zp[0].z, zp[1].z, zp[2].z, d, X, XY);
+                        wp.w = warp_sample(pn, zp[0].w, zp[1].w, zp[2].w, d, X, XY);
+                    }
                 }
                 sts4(wcur + own_off, wp);
                 if (halo_on) {
                     const float hxv = lds1(stP + halo_off), hyv = lds1(stP + halo_off + ARR_BYTES), hzv = lds1(stP + halo_off + 2 * ARR_BYTES);
-                    sts1(wcur + halo_off, warp_sample(pn, hxv, hyv, hzv, d, X, XY));
+                    sts1(wcur + halo_off, TEX ? warp_sample_tex(a.pn_tex, a.ashift, a.amask, hxv, hyv, hzv, d) : warp_sample(pn, hxv, hyv, hzv, d, X, XY));
                 }
             }
             asm volatile("bar.sync 1, %0;" ::"r"(NCONS) : "memory");     // warped plane p (and p-1) visible to all consumers
@@ -501,7 +528,8 @@ TmaMaps *tma_maps_create(const LoopArgs &a) {
     for (int c = 0; c < 3; ++c) ok = ok && encode_map_3d(&m->g[c], g[c], a.gl.PX, a.gl.PY, a.gl.PZ, pb::SX, pb::SY);
     for (int c = 0; c < 3; ++c) ok = ok && encode_map_3d(&m->in[c], in[c], a.d.X, a.d.Y, a.d.Z, pa::SX, pa::SY);
     ok = ok && cudaFuncSetAttribute(pb::pass_b_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pb::SMEM_BYTES) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
     if (!ok) {
         fprintf(stderr, "sobfu_b200: TMA tensor maps unavailable; using the generic kernels\n");
         cudaGetLastError();
@@ -529,7 +557,8 @@ void launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, cud
     const int ctas = 2 * sm_count();
     const Sched sc = make_sched(a.d, pa::TX, pa::TY, 2, 0.5, ctas);
     const int grid = sc.nitems < ctas ? sc.nitems : ctas;
-    pa::pass_a_tma_kernel<<<grid, (pa::NW + 1) * 32, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
+    if (a.pn_tex) pa::pass_a_tma_kernel<true><<<grid, (pa::NW + 1) * 32, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
+    else pa::pass_a_tma_kernel<false><<<grid, (pa::NW + 1) * 32, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
 }
 
 }  // namespace sb
