@@ -151,6 +151,12 @@ int sobfu_b200_marching_cubes(const void *vol, int X, int Y, int Z, const float 
  * rank 0 obtains an id, the launcher broadcasts it (torch.distributed), every rank attaches. */
 #define SOBFU_B200_COMM_ID_BYTES 128
 int sobfu_b200_comm_unique_id(void *id128_host);
+/* slab of `rank`: planes [z0, z0 + nz); needs Z % nranks == 0 and >= 4 planes per rank */
+int sobfu_b200_slab_range(int Z, int rank, int nranks, int *z0, int *nz);
+/* switches the solver (created for the GLOBAL dims) to slab mode: afterwards estimate_psi takes the rank's slab of
+ * phi_global, phi_global_psi_inv, phi_n_psi, psi, psi_inv and the WHOLE phi_n (replicated: every rank integrates the
+ * depth frame itself).  Per iteration: nabla_U halo (3 planes) and psi halo (1 plane) exchanges with both neighbours
+ * and a scalar MAX all-reduce over NCCL; per frame: one all-gather of psi and phi_global for psi^-1 / phi_global o psi^-1. */
 int sobfu_b200_solver_attach_comm(sobfu_b200_solver *s, const void *id128_host, int rank, int nranks);
 
 #ifdef __cplusplus

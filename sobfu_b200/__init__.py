@@ -7,5 +7,7 @@ from ._capi import Sobfu200Error, lib  # noqa: F401
 from .api import (Affine3f, DeformationField, Intr, MarchingCubes, Params, SobFusion, Solver, TsdfVolume,  # noqa: F401
                   VectorField, computeDists, depthBilateralFilter, depthTruncation)
 
-__all__ = ["Params", "Intr", "Affine3f", "TsdfVolume", "VectorField", "DeformationField", "Solver", "MarchingCubes",
+from .parallel import SlabSolver, slab_range  # noqa: F401,E402
+
+__all__ = ["SlabSolver", "slab_range", "Params", "Intr", "Affine3f", "TsdfVolume", "VectorField", "DeformationField", "Solver", "MarchingCubes",
            "SobFusion", "depthBilateralFilter", "depthTruncation", "computeDists", "Sobfu200Error", "lib"]

@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include "nccl_dyn.h"
 #include "solver_kernels.cuh"
 
 namespace sb {
@@ -147,13 +148,23 @@ static float idx_as_ref_float(long long idx, const RankMap m) {
 // ------------------------------------------------------------------------------------------------------------
 struct sobfu_b200_solver {
     sobfu_b200_params p;
-    Dims d;
-    size_t N;
+    Dims dg;                       // global volume
+    Dims d;                        // local slab (== dg on a single GPU)
+    int z0 = 0;                    // global z of local plane 0
+    size_t Ng = 0, Nl = 0, XY = 0; // voxels: global, local, per plane
     float taps[7];
     GLayout gl;
+    // z-slab decomposition over ranks (one process per GPU)
+    int rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
+    float4 *psi_full = nullptr;    // all-gathered psi / phi_global for the once-per-frame tail (slab mode only)
+    float2 *phig_full = nullptr;
     // device scratch
-    float *planes = nullptr;       // px,py,pz,w,pg,pn (6N floats)
-    float *g = nullptr;            // 3 * gl.total floats
+    float *psi_alloc = nullptr;    // 3 x (nzl + 2) planes: psi x/y/z with one halo plane on either side
+    float *w_alloc = nullptr;      // (nzl + 2) planes: (phi_n o psi).x (generic kernels / logging / final output)
+    float *pg = nullptr;           // nzl planes: phi_global.x
+    float *pn = nullptr;           // Z planes: phi_n.x (whole volume, the warp gathers anywhere)
+    float *g = nullptr;            // 3 * gl.total floats: nabla_U, padded
     LoopState *state = nullptr;
     unsigned long long *maxkey = nullptr;
     double *energies = nullptr;    // e_data[max_iter], e_reg[max_iter]
@@ -187,14 +198,16 @@ static bool use_tiled(const sobfu_b200_solver *s) {
 
 static void fill_args(sobfu_b200_solver *s) {
     LoopArgs &a = s->args;
-    a.px = s->planes; a.py = s->planes + s->N; a.pz = s->planes + 2 * s->N; a.w = s->planes + 3 * s->N;
-    a.pg = s->planes + 4 * s->N; a.pn = s->planes + 5 * s->N;
+    const size_t pl = (size_t)(s->d.Z + 2) * s->XY;        // floats per psi component incl. the two halo planes
+    a.px = s->psi_alloc + s->XY; a.py = s->psi_alloc + pl + s->XY; a.pz = s->psi_alloc + 2 * pl + s->XY;
+    a.w = s->w_alloc + s->XY;
+    a.pg = s->pg; a.pn = s->pn;
     a.gx = s->g; a.gy = s->g + s->gl.total; a.gz = s->g + 2 * s->gl.total;
-    a.d = s->d; a.gl = s->gl;
+    a.d = s->d; a.dg = s->dg; a.z0 = s->z0; a.gl = s->gl;
     for (int i = 0; i < 7; ++i) a.S[i] = s->taps[i];
     a.alpha = s->p.alpha; a.w_reg = s->p.w_reg; a.thr = s->p.max_update_norm;
-    a.state = s->state; a.maxkey = s->maxkey; a.e_data = s->energies; a.e_reg = s->energies + s->p.max_iter;
-    a.rm = rank_map_for(s->N);
+    a.state = s->state; a.maxkey = s->maxkey; a.e_data = s->energies; a.e_reg = s->energies + (s->p.max_iter > 0 ? s->p.max_iter : 1);
+    a.rm = rank_map_for(s->Ng);
     a.check = 1;
     a.pn_tex = s->pn_tex; a.pn_surf = s->pn_surf; a.ashift = s->ashift; a.amask = s->amask;
 }
@@ -203,9 +216,9 @@ static void fill_args(sobfu_b200_solver *s) {
 static void create_atlas(sobfu_b200_solver *s) {
     if (getenv("SOBFU_B200_NO_TEX")) return;
     int shift = 0;
-    while ((1 << (2 * shift)) < s->d.Z) ++shift;               // kx = 2^shift >= sqrt(Z)
-    const int kx = 1 << shift, ky = (s->d.Z + kx - 1) / kx;
-    const long long W = (long long)kx * s->d.X, H = (long long)ky * s->d.Y;
+    while ((1 << (2 * shift)) < s->dg.Z) ++shift;              // kx = 2^shift >= sqrt(Z)
+    const int kx = 1 << shift, ky = (s->dg.Z + kx - 1) / kx;
+    const long long W = (long long)kx * s->dg.X, H = (long long)ky * s->dg.Y;
     if (W > 32768 || H > 32768) return;                        // gather-capable 2-D arrays are limited to 32768 x 32768
     cudaChannelFormatDesc cd = cudaCreateChannelDesc<float>();
     if (cudaMallocArray(&s->pn_array, &cd, (size_t)W, (size_t)H, cudaArrayTextureGather | cudaArraySurfaceLoadStore) != cudaSuccess) {
@@ -227,15 +240,64 @@ static void create_atlas(sobfu_b200_solver *s) {
     s->ws_bytes += (size_t)W * H * sizeof(float);
 }
 
+static void free_workspace(sobfu_b200_solver *s) {
+    if (s->tma) { tma_maps_destroy(s->tma); s->tma = nullptr; }
+    cudaFree(s->psi_alloc); cudaFree(s->w_alloc); cudaFree(s->pg); cudaFree(s->pn); cudaFree(s->g);
+    cudaFree(s->psi_full); cudaFree(s->phig_full);
+    s->psi_alloc = s->w_alloc = s->pg = s->pn = s->g = nullptr;
+    s->psi_full = nullptr; s->phig_full = nullptr;
+    for (int i = 0; i < 6; ++i) {
+        if (s->stage_dev[i]) { cudaFree(s->stage_dev[i]); s->stage_dev[i] = nullptr; }
+        if (s->stage_pinned[i]) { cudaFreeHost(s->stage_pinned[i]); s->stage_pinned[i] = nullptr; }
+    }
+    s->have_state = false;
+}
+
+// scratch for the slab [z0, z0 + nzl): 36 B/voxel of the slab + 4 B/voxel of the whole volume (phi_n.x)
+static int alloc_workspace(sobfu_b200_solver *s, int z0, int nzl) {
+    free_workspace(s);
+    s->z0 = z0;
+    s->d = Dims{s->dg.X, s->dg.Y, nzl};
+    s->XY = (size_t)s->dg.X * s->dg.Y;
+    s->Nl = s->XY * nzl;
+    s->gl.PX = s->d.X + 8; s->gl.PY = s->d.Y + 6; s->gl.PZ = nzl + 6;
+    s->gl.plane = (size_t)s->gl.PX * s->gl.PY;
+    s->gl.total = s->gl.plane * s->gl.PZ;
+    const size_t pl = (size_t)(nzl + 2) * s->XY;
+#define CKA(expr)                                                                                          \
+    do {                                                                                                   \
+        cudaError_t e__ = (expr);                                                                          \
+        if (e__ != cudaSuccess)                                                                            \
+            return fail(e__ == cudaErrorMemoryAllocation ? SOBFU_B200_ENOMEM : SOBFU_B200_ECUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+    CKA(cudaMalloc(&s->psi_alloc, 3 * pl * sizeof(float)));
+    CKA(cudaMalloc(&s->w_alloc, pl * sizeof(float)));
+    CKA(cudaMalloc(&s->pg, s->Nl * sizeof(float)));
+    CKA(cudaMalloc(&s->pn, s->Ng * sizeof(float)));
+    CKA(cudaMalloc(&s->g, 3 * s->gl.total * sizeof(float)));
+    CKA(cudaMemset(s->psi_alloc, 0, 3 * pl * sizeof(float)));
+    CKA(cudaMemset(s->w_alloc, 0, pl * sizeof(float)));
+    CKA(cudaMemset(s->g, 0, 3 * s->gl.total * sizeof(float)));
+    s->ws_bytes = (4 * pl + s->Nl + s->Ng + 3 * s->gl.total) * sizeof(float);
+    if (s->nranks > 1) {
+        CKA(cudaMalloc(&s->psi_full, s->Ng * sizeof(float4)));
+        CKA(cudaMalloc(&s->phig_full, s->Ng * sizeof(float2)));
+        s->ws_bytes += s->Ng * 24;
+    }
+    fill_args(s);
+    if (tiled_supported(s->d)) s->tma = tma_maps_create(s->args);   // nullptr if the driver entry point is unavailable
+    return 0;
+}
+
 extern "C" int sobfu_b200_solver_destroy(sobfu_b200_solver *s) {
     if (!s) return 0;
-    if (s->tma) tma_maps_destroy(s->tma);
+    free_workspace(s);
+    if (s->comm && nccl_api().ok) nccl_api().CommDestroy(s->comm);
     if (s->pn_tex) cudaDestroyTextureObject(s->pn_tex);
     if (s->pn_surf) cudaDestroySurfaceObject(s->pn_surf);
     if (s->pn_array) cudaFreeArray(s->pn_array);
-    cudaFree(s->planes); cudaFree(s->g); cudaFree(s->state); cudaFree(s->maxkey); cudaFree(s->energies);
+    cudaFree(s->state); cudaFree(s->maxkey); cudaFree(s->energies);
     if (s->h_state) cudaFreeHost(s->h_state);
-    for (int i = 0; i < 6; ++i) { if (s->stage_dev[i]) cudaFree(s->stage_dev[i]); if (s->stage_pinned[i]) cudaFreeHost(s->stage_pinned[i]); }
     for (auto &e : s->ev) if (e) cudaEventDestroy(e);
     if (s->ev_user) cudaEventDestroy(s->ev_user);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -253,11 +315,8 @@ extern "C" int sobfu_b200_solver_create(sobfu_b200_solver **out, const sobfu_b20
     s->p = *p;
     int rc = sobfu_b200_sobolev_taps(p->s, p->lambda, s->taps);
     if (rc) { delete s; return rc; }
-    s->d = Dims{p->dims[0], p->dims[1], p->dims[2]};
-    s->N = (size_t)s->d.X * s->d.Y * s->d.Z;
-    s->gl.PX = s->d.X + 8; s->gl.PY = s->d.Y + 6; s->gl.PZ = s->d.Z + 6;
-    s->gl.plane = (size_t)s->gl.PX * s->gl.PY;
-    s->gl.total = s->gl.plane * s->gl.PZ;
+    s->dg = Dims{p->dims[0], p->dims[1], p->dims[2]};
+    s->Ng = (size_t)s->dg.X * s->dg.Y * s->dg.Z;
     const int mi = p->max_iter > 0 ? p->max_iter : 1;
 #define CKD(expr)                                                                                          \
     do {                                                                                                   \
@@ -268,9 +327,6 @@ extern "C" int sobfu_b200_solver_create(sobfu_b200_solver **out, const sobfu_b20
             return c__;                                                                                    \
         }                                                                                                  \
     } while (0)
-    CKD(cudaMalloc(&s->planes, 6 * s->N * sizeof(float)));
-    CKD(cudaMalloc(&s->g, 3 * s->gl.total * sizeof(float)));
-    CKD(cudaMemset(s->g, 0, 3 * s->gl.total * sizeof(float)));
     CKD(cudaMalloc(&s->state, sizeof(LoopState)));
     CKD(cudaMalloc(&s->maxkey, mi * sizeof(unsigned long long)));
     CKD(cudaMalloc(&s->energies, 2 * mi * sizeof(double)));
@@ -278,35 +334,11 @@ extern "C" int sobfu_b200_solver_create(sobfu_b200_solver **out, const sobfu_b20
     CKD(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (auto &e : s->ev) CKD(cudaEventCreate(&e));
     CKD(cudaEventCreateWithFlags(&s->ev_user, cudaEventDisableTiming));
-    s->ws_bytes = 6 * s->N * sizeof(float) + 3 * s->gl.total * sizeof(float) + mi * 24 + sizeof(LoopState);
     s->h_maxkey.resize(mi);
     s->h_energies.resize(2 * mi);
-    if (tiled_supported(s->d)) create_atlas(s);
-    fill_args(s);
-    if (tiled_supported(s->d)) s->tma = tma_maps_create(s->args);   // nullptr if the driver entry point is unavailable
-    // phi_n.x (4 B/voxel) is gathered by every iteration of pass B and never written during a solve: ask L2 to keep it
-    // resident (persisting access-policy window on the solver stream).  Best effort: failures are ignored.
-    if (getenv("SOBFU_B200_L2_PERSIST")) {   // measured slower on B200 (r1): off unless asked for
-        int dev = 0, max_persist = 0, max_window = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-        const size_t want = s->N * sizeof(float);
-        if (max_persist > 0 && max_window > 0) {
-            const size_t win = want < (size_t)max_window ? want : (size_t)max_window;
-            const size_t carve = win < (size_t)max_persist ? win : (size_t)max_persist;
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
-            cudaStreamAttrValue av;
-            memset(&av, 0, sizeof av);
-            av.accessPolicyWindow.base_ptr = const_cast<float *>(s->args.pn);
-            av.accessPolicyWindow.num_bytes = win;
-            av.accessPolicyWindow.hitRatio = carve >= win ? 1.0f : (float)carve / (float)win;
-            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &av);
-        }
-        cudaGetLastError();
-    }
+    if (tiled_supported(s->dg)) create_atlas(s);
+    rc = alloc_workspace(s, 0, s->dg.Z);
+    if (rc) { sobfu_b200_solver_destroy(s); return rc; }
     *out = s;
     return 0;
 }
@@ -319,8 +351,91 @@ extern "C" int sobfu_b200_solver_get_taps(sobfu_b200_solver *s, float *t) {
 }
 extern "C" int sobfu_b200_solver_set_variant(sobfu_b200_solver *s, int v) {
     if (!s || v < 0 || v > 2) return fail(SOBFU_B200_EINVAL, "variant must be 0, 1 or 2");
-    if (v >= 2 && !(tiled_supported(s->d) && s->tma)) return fail(SOBFU_B200_EINVAL, "tiled/TMA kernels do not support dims %dx%dx%d", s->d.X, s->d.Y, s->d.Z);
+    if (v == 2 && !(tiled_supported(s->d) && s->tma)) return fail(SOBFU_B200_EINVAL, "tiled/TMA kernels do not support dims %dx%dx%d", s->d.X, s->d.Y, s->d.Z);
     s->variant = v;
+    return 0;
+}
+
+// ---- multi-GPU: z-slab partition, one process per GPU ----------------------------------------------
+extern "C" int sobfu_b200_comm_unique_id(void *id128) {
+    if (!id128) return fail(SOBFU_B200_EINVAL, "null argument");
+    NcclApi &n = nccl_api();
+    if (!n.ok) return fail(SOBFU_B200_ECOMM, "%s", n.err.c_str());
+    static_assert(sizeof(ncclUniqueId) == SOBFU_B200_COMM_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    ncclResult_t r = n.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(SOBFU_B200_ECOMM, "ncclGetUniqueId: %s", n.GetErrorString(r));
+    memcpy(id128, &id, sizeof id);
+    return 0;
+}
+extern "C" int sobfu_b200_slab_range(int Z, int rank, int nranks, int *z0, int *nz) {
+    if (Z <= 0 || nranks <= 0 || rank < 0 || rank >= nranks || Z % nranks != 0 || Z / nranks < 4)
+        return fail(SOBFU_B200_EINVAL, "slab partition needs Z %% nranks == 0 and at least 4 planes per rank (Z=%d, nranks=%d)", Z, nranks);
+    if (z0) *z0 = rank * (Z / nranks);
+    if (nz) *nz = Z / nranks;
+    return 0;
+}
+extern "C" int sobfu_b200_solver_attach_comm(sobfu_b200_solver *s, const void *id128, int rank, int nranks) {
+    if (!s || !id128) return fail(SOBFU_B200_EINVAL, "null argument");
+    if (s->comm) return fail(SOBFU_B200_EINVAL, "a communicator is already attached");
+    int z0 = 0, nz = 0;
+    int rc = sobfu_b200_slab_range(s->dg.Z, rank, nranks, &z0, &nz);
+    if (rc) return rc;
+    if (nranks == 1) return 0;
+    NcclApi &n = nccl_api();
+    if (!n.ok) return fail(SOBFU_B200_ECOMM, "%s", n.err.c_str());
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    ncclResult_t r = n.CommInitRank(&s->comm, nranks, id, rank);
+    if (r != ncclSuccess) { s->comm = nullptr; return fail(SOBFU_B200_ECOMM, "ncclCommInitRank: %s", n.GetErrorString(r)); }
+    s->rank = rank; s->nranks = nranks;
+    return alloc_workspace(s, z0, nz);
+}
+
+#define CKN(expr)                                                                                   \
+    do {                                                                                            \
+        ncclResult_t r__ = (expr);                                                                  \
+        if (r__ != ncclSuccess) return fail(SOBFU_B200_ECOMM, "%s: %s", #expr, nccl_api().GetErrorString(r__)); \
+    } while (0)
+
+// one halo plane of each psi component to / from both neighbours (pass A reads psi at z +- 1)
+static int exchange_psi(sobfu_b200_solver *s) {
+    if (s->nranks == 1) return 0;
+    NcclApi &n = nccl_api();
+    float *P[3] = {s->args.px, s->args.py, s->args.pz};
+    const size_t XY = s->XY, nzl = s->d.Z;
+    CKN(n.GroupStart());
+    for (int c = 0; c < 3; ++c) {
+        if (s->rank > 0) {
+            CKN(n.Send(P[c], XY, ncclFloat, s->rank - 1, s->comm, s->stream));
+            CKN(n.Recv(P[c] - XY, XY, ncclFloat, s->rank - 1, s->comm, s->stream));
+        }
+        if (s->rank < s->nranks - 1) {
+            CKN(n.Send(P[c] + (nzl - 1) * XY, XY, ncclFloat, s->rank + 1, s->comm, s->stream));
+            CKN(n.Recv(P[c] + nzl * XY, XY, ncclFloat, s->rank + 1, s->comm, s->stream));
+        }
+    }
+    CKN(n.GroupEnd());
+    return 0;
+}
+// three (padded) halo planes of each nabla_U component to / from both neighbours (the filter reads nabla_U at z +- 3)
+static int exchange_g(sobfu_b200_solver *s) {
+    if (s->nranks == 1) return 0;
+    NcclApi &n = nccl_api();
+    float *G[3] = {s->args.gx, s->args.gy, s->args.gz};
+    const size_t pl = s->gl.plane, nzl = s->d.Z;
+    CKN(n.GroupStart());
+    for (int c = 0; c < 3; ++c) {
+        if (s->rank > 0) {
+            CKN(n.Send(G[c] + 3 * pl, 3 * pl, ncclFloat, s->rank - 1, s->comm, s->stream));             // owned planes 0..2
+            CKN(n.Recv(G[c], 3 * pl, ncclFloat, s->rank - 1, s->comm, s->stream));                      // halo planes -3..-1
+        }
+        if (s->rank < s->nranks - 1) {
+            CKN(n.Send(G[c] + nzl * pl, 3 * pl, ncclFloat, s->rank + 1, s->comm, s->stream));           // owned planes nzl-3..nzl-1
+            CKN(n.Recv(G[c] + (nzl + 3) * pl, 3 * pl, ncclFloat, s->rank + 1, s->comm, s->stream));     // halo planes nzl..nzl+2
+        }
+    }
+    CKN(n.GroupEnd());
     return 0;
 }
 
@@ -336,10 +451,21 @@ static void run_pass_b(sobfu_b200_solver *s, int it) {
     if (!use_tiled(s)) launch_pass_b_generic(s->args, it, s->stream);
     else launch_pass_b_tma(s->args, s->tma, it, s->stream);
 }
-static void launch_iteration(sobfu_b200_solver *s, int it, int log, int *launches) {
+// one gradient-descent iteration: pass A, [nabla_U halo exchange], pass B, [psi halo exchange, global max]
+static int launch_iteration(sobfu_b200_solver *s, int it, int log, int *launches) {
     run_pass_a(s, it, log);
+    int rc = exchange_g(s);
+    if (rc) return rc;
     run_pass_b(s, it);
     *launches += 2;
+    if (s->nranks > 1) {
+        rc = exchange_psi(s);
+        if (rc) return rc;
+        if (!use_tiled(s)) { launch_initial_warp(s->args, s->stream); ++*launches; }   // generic pass A reads w on the halo planes
+        if (s->args.check)   // the convergence test of the next iteration must see the global maximum
+            CKN(nccl_api().AllReduce(s->maxkey + it, s->maxkey + it, 1, ncclUint64, ncclMax, s->comm, s->stream));
+    }
+    return 0;
 }
 
 static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *phi_global_psi_inv, const float2 *phi_n,
@@ -347,7 +473,7 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
     const sobfu_b200_params &p = s->p;
     const int mi = p.max_iter;
     cudaStream_t st = s->stream;
-    int launches = 0;
+    int launches = 0, rc = 0;
     if (order_with_user) {   // everything the caller enqueued on its stream happens-before the solve
         CK(cudaEventRecord(s->ev_user, g_stream));
         CK(cudaStreamWaitEvent(st, s->ev_user, 0));
@@ -360,6 +486,7 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
         CK(cudaMemsetAsync(s->energies, 0, 2 * mi * sizeof(double), st));
     }
     launch_unpack(psi, phi_global, phi_n, s->args, st);
+    if ((rc = exchange_psi(s))) return rc;
     launch_initial_warp(s->args, st);
     launches += 2;
     CK_LAST();
@@ -370,7 +497,8 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
     int converged = 0, iters = mi;
     for (int it0 = 0; it0 < mi && !converged; it0 += CHUNK) {
         const int it1 = it0 + CHUNK < mi ? it0 + CHUNK : mi;
-        for (int it = it0; it < it1; ++it) launch_iteration(s, it, log_iter(p, it + 1) ? 1 : 0, &launches);
+        for (int it = it0; it < it1; ++it)
+            if ((rc = launch_iteration(s, it, log_iter(p, it + 1) ? 1 : 0, &launches))) return rc;
         CK_LAST();
         if (it1 < mi) {   // peek at the sticky flag (it is raised by pass A of the iteration after the converged one)
             CK(cudaMemcpyAsync(s->h_state, s->state, sizeof(LoopState), cudaMemcpyDeviceToHost, st));
@@ -383,8 +511,18 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
     // tail (solver.cu:195-199): write back psi / phi_n o psi, psi^-1 from identity (48 fixed-point steps), phi_global o psi^-1
     if (use_tiled(s) && mi > 0) { launch_initial_warp(s->args, st); ++launches; }   // the TMA loop keeps phi_n o psi on chip
     launch_pack(psi, phi_n_psi, phi_n, s->args, st);
-    launch_estimate_inverse(psi, psi_inv, s->d, 48, true, st);
-    launch_apply(phi_global, phi_global_psi_inv, psi_inv, s->d, st);
+    if (s->nranks == 1) {
+        launch_estimate_inverse(psi, psi_inv, s->dg, 48, true, st);
+        launch_apply(phi_global, phi_global_psi_inv, psi_inv, s->dg, st);
+    } else {
+        // psi^-1 and phi_global o psi^-1 gather anywhere in the volume: all-gather psi and phi_global once per frame
+        NcclApi &n = nccl_api();
+        CKN(n.AllGather(psi, s->psi_full, s->Nl * 4, ncclFloat, s->comm, st));
+        CKN(n.AllGather(phi_global, s->phig_full, s->Nl * 2, ncclFloat, s->comm, st));
+        launch_estimate_inverse_slab(s->psi_full, psi_inv, s->dg, s->z0, s->d.Z, 48, st);
+        launch_apply_slab(s->phig_full, phi_global_psi_inv, psi_inv, s->dg, s->z0, s->d.Z, st);
+        if (mi > 0) CKN(n.AllReduce(s->energies, s->energies, 2 * mi, ncclDouble, ncclSum, s->comm, st));
+    }
     launches += 3;
     CK_LAST();
     CK(cudaEventRecord(s->ev[3], st));
@@ -422,9 +560,9 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
         cudaEventElapsedTime(&info->total_ms, s->ev[0], s->ev[3]);
         info->launches = launches;
     }
-    // the reference's console output (solver.cu:115-117,140-141,179-190), same text and cadence
+    // the reference's console output (solver.cu:115-117,140-141,179-190), same text and cadence (rank 0 only)
     static const bool quiet = getenv("SOBFU_B200_QUIET") != nullptr;   // the reference always prints; tests/bench may silence
-    if (!quiet) {
+    if (!quiet && s->rank == 0) {
         for (int it = 0; it < iters; ++it) {
             const int iter1 = it + 1;
             if (iter1 == 1 || iter1 % 50 == 0) printf("iter. no. %d\n", iter1);
@@ -432,9 +570,9 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
                 const float e = s->log[it].e_data + p.w_reg * s->log[it].e_reg;
                 printf("data energy + w_reg * reg energy = %g + %g * %g = %g\n", s->log[it].e_data, p.w_reg, s->log[it].e_reg, e);
                 const float yf = s->log[it].max_idx_f;
-                const int ix = (int)(yf / (s->d.X * s->d.Y));
-                const int iy = (int)((yf - ix * s->d.X * s->d.Y) / s->d.X);
-                const int iz = (int)(yf - s->d.X * (iy + s->d.Y * ix));
+                const int ix = (int)(yf / (s->dg.X * s->dg.Y));
+                const int iy = (int)((yf - ix * s->dg.X * s->dg.Y) / s->dg.X);
+                const int iz = (int)(yf - s->dg.X * (iy + s->dg.Y * ix));
                 printf("max. update norm %g at voxel (%d, %d, %d)\n", s->log[it].max_norm, iz, iy, ix);
             }
             if (iter1 == iters && converged) printf("SOLVER CONVERGED AFTER %d ITERATIONS\n", iter1);
@@ -457,8 +595,9 @@ extern "C" int sobfu_b200_solver_estimate_psi_host(sobfu_b200_solver *s, const v
                                                    const void *phi_n_h, void *phi_n_psi_h, void *psi_h, void *psi_inv_h,
                                                    sobfu_b200_solve_info *info) {
     if (!s || !phi_global_h || !phi_n_h || !psi_h) return fail(SOBFU_B200_EINVAL, "null argument");
-    const size_t b2 = s->N * sizeof(float2), b4 = s->N * sizeof(float4);
-    const size_t bytes[6] = {b2, b2, b2, b2, b4, b4};   // phi_global, phi_global_psi_inv, phi_n, phi_n_psi, psi, psi_inv
+    // slab mode: every buffer covers the rank's slab except phi_n, which covers the whole volume
+    const size_t b2 = s->Nl * sizeof(float2), b4 = s->Nl * sizeof(float4), b2g = s->Ng * sizeof(float2);
+    const size_t bytes[6] = {b2, b2, b2g, b2, b4, b4};   // phi_global, phi_global_psi_inv, phi_n, phi_n_psi, psi, psi_inv
     for (int i = 0; i < 6; ++i) {
         if (!s->stage_dev[i]) CK(cudaMalloc(&s->stage_dev[i], bytes[i]));
         if (!s->stage_pinned[i]) CK(cudaMallocHost(&s->stage_pinned[i], bytes[i]));
@@ -497,17 +636,17 @@ extern "C" int sobfu_b200_solver_time_loop(sobfu_b200_solver *s, int iters, floa
     cudaStream_t st = s->stream;
     s->args.check = 0;
     const int slot = 0;   // partial maxima land in maxkey[0]; irrelevant here
-    auto run_a = [&]() { run_pass_a(s, slot, 0); };
-    auto run_b = [&]() { run_pass_b(s, slot); };
     float ta = 0.f, tb = 0.f, tl = 0.f;
-    // whole loop
+    int launches = 0, rc = 0;
+    // whole iterations (with the halo exchanges in slab mode)
     CK(cudaEventRecord(s->ev[0], st));
-    for (int i = 0; i < iters; ++i) { run_a(); run_b(); }
+    for (int i = 0; i < iters; ++i)
+        if ((rc = launch_iteration(s, slot, 0, &launches))) { s->args.check = 1; return rc; }
     CK(cudaEventRecord(s->ev[1], st));
-    // pass A alone / pass B alone (B keeps descending, which is fine for timing)
-    for (int i = 0; i < iters; ++i) run_a();
+    // pass A alone / pass B alone (no exchanges; B keeps descending, which is fine for timing)
+    for (int i = 0; i < iters; ++i) run_pass_a(s, slot, 0);
     CK(cudaEventRecord(s->ev[2], st));
-    for (int i = 0; i < iters; ++i) run_b();
+    for (int i = 0; i < iters; ++i) run_pass_b(s, slot);
     CK(cudaEventRecord(s->ev[3], st));
     CK_LAST();
     CK(cudaStreamSynchronize(st));
@@ -680,8 +819,3 @@ extern "C" int sobfu_b200_marching_cubes(const void *vol, int X, int Y, int Z, c
     return 0;
 }
 
-// ---- multi-GPU ------------------------------------------------------------------------------------------------
-extern "C" int sobfu_b200_comm_unique_id(void *) { return fail(SOBFU_B200_ECOMM, "multi-GPU slab mode is not built into this library yet"); }
-extern "C" int sobfu_b200_solver_attach_comm(sobfu_b200_solver *, const void *, int, int) {
-    return fail(SOBFU_B200_ECOMM, "multi-GPU slab mode is not built into this library yet");
-}

@@ -23,16 +23,17 @@ __global__ void init_identity_kernel(float4 *__restrict__ psi, Dims d) {
     psi[x + (size_t)d.X * (y + (size_t)d.Y * z)] = make_float4((float)x, (float)y, (float)z, 0.f);
 }
 
-// apply_kernel, vector_fields.cu:81-100 + interpolate_tsdf, utils.hpp:50-86
+// apply_kernel, vector_fields.cu:81-100 + interpolate_tsdf, utils.hpp:50-86.  phi covers the whole volume `dg`;
+// psi and out cover the z-slab [z0, z0 + nzl) (the whole volume on a single GPU).
 __global__ void apply_kernel(const float2 *__restrict__ phi, float2 *__restrict__ out, const float4 *__restrict__ psi,
-                             Dims d) {
+                             Dims dg, int nzl) {
     int x, y, z;
-    if (!voxel_of_thread(d, x, y, z)) return;
-    const size_t i = x + (size_t)d.X * (y + (size_t)d.Y * z);
+    if (!voxel_of_thread(Dims{dg.X, dg.Y, nzl}, x, y, z)) return;
+    const size_t i = x + (size_t)dg.X * (y + (size_t)dg.Y * z);
     const float4 p = psi[i];
-    const TriCoord t = tri_coord(p.x, p.y, p.z, d);
-    const float v = sample_scalar<2>(reinterpret_cast<const float *>(phi), t, d);
-    const float wgt = phi[(size_t)t.gx + (size_t)d.X * ((size_t)t.gy + (size_t)d.Y * t.gz)].y;
+    const TriCoord t = tri_coord(p.x, p.y, p.z, dg);
+    const float v = sample_scalar<2>(reinterpret_cast<const float *>(phi), t, dg);
+    const float wgt = phi[(size_t)t.gx + (size_t)dg.X * ((size_t)t.gy + (size_t)dg.Y * t.gz)].y;
     out[i] = make_float2(v, wgt);
 }
 
@@ -43,12 +44,15 @@ SB_DEV float3 disp(const float4 *__restrict__ psi, int x, int y, int z, const Di
     const float4 p = __ldg(psi + (size_t)x + (size_t)d.X * ((size_t)y + (size_t)d.Y * z));
     return make_float3(sub(p.x, (float)x), sub(p.y, (float)y), sub(p.z, (float)z));   // get_displacement
 }
+// psi covers the whole volume `d`; psi_inv covers the z-slab [z0, z0 + nzl).  The fixed-point loop stops as soon as a
+// step reproduces its input bit for bit: every later step of the reference would return the same value.
 __global__ void __launch_bounds__(BX *BY *BZ) estimate_inverse_kernel(const float4 *__restrict__ psi,
-                                                                    float4 *__restrict__ psi_inv, Dims d, int iters,
-                                                                    int from_identity) {
-    int x, y, z;
-    if (!voxel_of_thread(d, x, y, z)) return;
-    const size_t i = x + (size_t)d.X * (y + (size_t)d.Y * z);
+                                                                    float4 *__restrict__ psi_inv, Dims d, int z0, int nzl,
+                                                                    int iters, int from_identity) {
+    int x, y, zl;
+    if (!voxel_of_thread(Dims{d.X, d.Y, nzl}, x, y, zl)) return;
+    const int z = z0 + zl;
+    const size_t i = x + (size_t)d.X * (y + (size_t)d.Y * zl);
     float vx, vy, vz, vw;
     if (from_identity) { vx = (float)x; vy = (float)y; vz = (float)z; vw = 0.f; }
     else { const float4 v = psi_inv[i]; vx = v.x; vy = v.y; vz = v.z; vw = v.w; }
@@ -61,10 +65,13 @@ __global__ void __launch_bounds__(BX *BY *BZ) estimate_inverse_kernel(const floa
         const float ix = tri_lerp(d111.x, d110.x, d101.x, d100.x, d011.x, d010.x, d001.x, d000.x, t);
         const float iy = tri_lerp(d111.y, d110.y, d101.y, d100.y, d011.y, d010.y, d001.y, d000.y, t);
         const float iz = tri_lerp(d111.z, d110.z, d101.z, d100.z, d011.z, d010.z, d001.z, d000.z, t);
-        vx = sub((float)x, mul(ix, 1.f));
-        vy = sub((float)y, mul(iy, 1.f));
-        vz = sub((float)z, mul(iz, 1.f));
-        vw = 0.f;
+        const float nx = sub((float)x, mul(ix, 1.f));
+        const float ny = sub((float)y, mul(iy, 1.f));
+        const float nz = sub((float)z, mul(iz, 1.f));
+        const bool same = __float_as_uint(nx) == __float_as_uint(vx) && __float_as_uint(ny) == __float_as_uint(vy) &&
+                          __float_as_uint(nz) == __float_as_uint(vz);
+        vx = nx; vy = ny; vz = nz; vw = 0.f;
+        if (same) break;
     }
     psi_inv[i] = make_float4(vx, vy, vz, vw);
 }
@@ -222,10 +229,17 @@ static int sgrid(size_t n) { size_t b = (n + 255) / 256; return (int)(b > 148 * 
 
 void launch_init_identity(float4 *psi, Dims d, cudaStream_t st) { init_identity_kernel<<<grid3(d), block3(), 0, st>>>(psi, d); }
 void launch_apply(const float2 *phi, float2 *out, const float4 *psi, Dims d, cudaStream_t st) {
-    apply_kernel<<<grid3(d), block3(), 0, st>>>(phi, out, psi, d);
+    apply_kernel<<<grid3(d), block3(), 0, st>>>(phi, out, psi, d, d.Z);
+}
+void launch_apply_slab(const float2 *phi_full, float2 *out_local, const float4 *psi_local, Dims dg, int z0, int nzl, cudaStream_t st) {
+    (void)z0;   // psi holds absolute coordinates: the slab offset only selects which voxels are written
+    apply_kernel<<<grid3(Dims{dg.X, dg.Y, nzl}), block3(), 0, st>>>(phi_full, out_local, psi_local, dg, nzl);
 }
 void launch_estimate_inverse(const float4 *psi, float4 *psi_inv, Dims d, int iters, bool from_identity, cudaStream_t st) {
-    estimate_inverse_kernel<<<grid3(d), block3(), 0, st>>>(psi, psi_inv, d, iters, from_identity ? 1 : 0);
+    estimate_inverse_kernel<<<grid3(d), block3(), 0, st>>>(psi, psi_inv, d, 0, d.Z, iters, from_identity ? 1 : 0);
+}
+void launch_estimate_inverse_slab(const float4 *psi_full, float4 *psi_inv_local, Dims dg, int z0, int nzl, int iters, cudaStream_t st) {
+    estimate_inverse_kernel<<<grid3(Dims{dg.X, dg.Y, nzl}), block3(), 0, st>>>(psi_full, psi_inv_local, dg, z0, nzl, iters, 1);
 }
 void launch_tsdf_gradient(const float2 *phi, float4 *grad, Dims d, cudaStream_t st) { tsdf_gradient_kernel<<<grid3(d), block3(), 0, st>>>(phi, grad, d); }
 void launch_laplacian(const float4 *psi, float4 *L, Dims d, cudaStream_t st) { laplacian_kernel<<<grid3(d), block3(), 0, st>>>(psi, L, d); }

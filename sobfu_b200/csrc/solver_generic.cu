@@ -17,29 +17,35 @@ SB_DEV bool voxel_of_thread(const Dims d, int &x, int &y, int &z) {
 inline dim3 grid_for(const Dims d) { return dim3((d.X + BX - 1) / BX, (d.Y + BY - 1) / BY, (d.Z + BZ - 1) / BZ); }
 
 // ---- prologue: AoS -> planes -------------------------------------------------------------------------------
+// psi / phi_global: the owned slab; phi_n: the whole volume (replicated on every rank) -> pn plane + gather4 atlas
 __global__ void unpack_kernel(const float4 *__restrict__ psi, const float2 *__restrict__ phi_global,
                               const float2 *__restrict__ phi_n, LoopArgs a) {
-    const size_t n = (size_t)a.d.X * a.d.Y * a.d.Z;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t nl = (size_t)a.d.X * a.d.Y * a.d.Z, ng = (size_t)a.dg.X * a.dg.Y * a.dg.Z;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, first = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = first; i < nl; i += stride) {
         const float4 p = psi[i];
         a.px[i] = p.x; a.py[i] = p.y; a.pz[i] = p.z;
         const_cast<float *>(a.pg)[i] = phi_global[i].x;
+    }
+    const int XY = a.dg.X * a.dg.Y;
+    for (size_t i = first; i < ng; i += stride) {
         const float v = phi_n[i].x;
         const_cast<float *>(a.pn)[i] = v;
         if (a.pn_surf) {   // same value into the gather4 atlas
-            const int XY = a.d.X * a.d.Y;
-            const int z = (int)(i / XY), r = (int)(i - (size_t)z * XY), y = r / a.d.X, x = r - y * a.d.X;
-            surf2Dwrite(v, a.pn_surf, (int)sizeof(float) * ((z & a.amask) * a.d.X + x), (z >> a.ashift) * a.d.Y + y);
+            const int z = (int)(i / XY), r = (int)(i - (size_t)z * XY), y = r / a.dg.X, x = r - y * a.dg.X;
+            surf2Dwrite(v, a.pn_surf, (int)sizeof(float) * ((z & a.amask) * a.dg.X + x), (z >> a.ashift) * a.dg.Y + y);
         }
     }
 }
 
-// phi_n o psi before the first iteration (solver.cu:106 -> apply_kernel, vector_fields.cu:81-100)
+// phi_n o psi before the first iteration (solver.cu:106 -> apply_kernel, vector_fields.cu:81-100), including the two
+// halo planes when they exist in the global volume
 __global__ void initial_warp_kernel(LoopArgs a) {
-    const size_t n = (size_t)a.d.X * a.d.Y * a.d.Z;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const TriCoord t = tri_coord(a.px[i], a.py[i], a.pz[i], a.d);
-        a.w[i] = sample_scalar<1>(a.pn, t, a.d);
+    const long XY = (long)a.d.X * a.d.Y;
+    const long lo = (a.z0 > 0) ? -XY : 0, hi = XY * a.d.Z + ((a.z0 + a.d.Z < a.dg.Z) ? XY : 0);
+    for (long i = lo + (long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long)gridDim.x * blockDim.x) {
+        const TriCoord t = tri_coord(a.px[i], a.py[i], a.pz[i], a.dg);
+        a.w[i] = sample_scalar<1>(a.pn, t, a.dg);
     }
 }
 
@@ -75,11 +81,13 @@ __global__ void __launch_bounds__(BX *BY *BZ) pass_a_generic_kernel(LoopArgs a, 
         const Dims d = a.d;
         const size_t sy = (size_t)d.X, sz = (size_t)d.X * d.Y;
         const size_t i = x + sy * y + sz * z;
-        const bool bx = (x == 0 || x == d.X - 1), by = (y == 0 || y == d.Y - 1), bz = (z == 0 || z == d.Z - 1);
+        const int zg = a.z0 + z;                  // boundary rules apply on the global faces only
+        const bool z_lo = (zg == 0), z_hi = (zg == a.dg.Z - 1);
+        const bool bx = (x == 0 || x == d.X - 1), by = (y == 0 || y == d.Y - 1), bz = z_lo || z_hi;
         // neighbour indices for the central differences (mirror onto the in-range neighbour at a boundary)
         const size_t gxa = (x == d.X - 1) ? i - 1 : i + 1, gxb = (x == 0) ? i + 1 : i - 1;
         const size_t gya = (y == d.Y - 1) ? i - sy : i + sy, gyb = (y == 0) ? i + sy : i - sy;
-        const size_t gza = (z == d.Z - 1) ? i - sz : i + sz, gzb = (z == 0) ? i + sz : i - sz;
+        const size_t gza = z_hi ? i - sz : i + sz, gzb = z_lo ? i + sz : i - sz;
         // neighbour indices for the Laplacian (self on a boundary plane)
         const size_t lxa = bx ? i : i + 1, lxb = bx ? i : i - 1;
         const size_t lya = by ? i : i + sy, lyb = by ? i : i - sy;
@@ -111,7 +119,7 @@ __global__ void __launch_bounds__(BX *BY *BZ) pass_a_generic_kernel(LoopArgs a, 
     }
         SB_HALO(x == 0, -1L) SB_HALO(x == d.X - 1, 1L)
         SB_HALO(y == 0, -(long)gl.PX) SB_HALO(y == d.Y - 1, (long)gl.PX)
-        SB_HALO(z == 0, -(long)gl.plane) SB_HALO(z == d.Z - 1, (long)gl.plane)
+        SB_HALO(z_lo, -(long)gl.plane) SB_HALO(z_hi, (long)gl.plane)
 #undef SB_HALO
 
         if (LOG) {
@@ -120,14 +128,14 @@ __global__ void __launch_bounds__(BX *BY *BZ) pass_a_generic_kernel(LoopArgs a, 
             const float *P[3] = {a.px, a.py, a.pz};
             const int cxa = (x == d.X - 1) ? x - 1 : x + 1, cxb = (x == 0) ? x + 1 : x - 1;
             const int cya = (y == d.Y - 1) ? y - 1 : y + 1, cyb = (y == 0) ? y + 1 : y - 1;
-            const int cza = (z == d.Z - 1) ? z - 1 : z + 1, czb = (z == 0) ? z + 1 : z - 1;
+            const int cza = z_hi ? zg - 1 : zg + 1, czb = z_lo ? zg + 1 : zg - 1;
             float rows = 0.f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float ox_a = (c == 0) ? (float)cxa : (c == 1 ? (float)y : (float)z);
-                const float ox_b = (c == 0) ? (float)cxb : (c == 1 ? (float)y : (float)z);
-                const float oy_a = (c == 0) ? (float)x : (c == 1 ? (float)cya : (float)z);
-                const float oy_b = (c == 0) ? (float)x : (c == 1 ? (float)cyb : (float)z);
+                const float ox_a = (c == 0) ? (float)cxa : (c == 1 ? (float)y : (float)zg);
+                const float ox_b = (c == 0) ? (float)cxb : (c == 1 ? (float)y : (float)zg);
+                const float oy_a = (c == 0) ? (float)x : (c == 1 ? (float)cya : (float)zg);
+                const float oy_b = (c == 0) ? (float)x : (c == 1 ? (float)cyb : (float)zg);
                 const float oz_a = (c == 0) ? (float)x : (c == 1 ? (float)y : (float)cza);
                 const float oz_b = (c == 0) ? (float)x : (c == 1 ? (float)y : (float)czb);
                 const float jx = mul(sub(sub(P[c][gxa], ox_a), sub(P[c][gxb], ox_b)), 0.5f);
@@ -185,10 +193,11 @@ __global__ void __launch_bounds__(BX *BY *BZ) pass_b_generic_kernel(LoopArgs a, 
         const float npx = sub(a.px[i], ux), npy = sub(a.py[i], uy), npz = sub(a.pz[i], uz);
         a.px[i] = npx; a.py[i] = npy; a.pz[i] = npz;
         const float nsq = add(add(mul(ux, ux), mul(uy, uy)), mul(uz, uz));
-        key = ((unsigned long long)__float_as_uint(nsq) << 32) | (unsigned long long)(0xffffffffu - rank_of((unsigned)i, a.rm));
+        const unsigned ig = (unsigned)(i + (size_t)a.z0 * d.X * d.Y);     // global voxel index
+        key = ((unsigned long long)__float_as_uint(nsq) << 32) | (unsigned long long)(0xffffffffu - rank_of(ig, a.rm));
         // NaN/negative never occur for a sum of squares; -0 cannot occur either
-        const TriCoord t = tri_coord(npx, npy, npz, d);
-        a.w[i] = sample_scalar<1>(a.pn, t, d);
+        const TriCoord t = tri_coord(npx, npy, npz, a.dg);
+        a.w[i] = sample_scalar<1>(a.pn, t, a.dg);
     }
     __shared__ unsigned long long sk[BX * BY * BZ / 32];
     const int tid = threadIdx.x + BX * (threadIdx.y + BY * threadIdx.z);
@@ -213,8 +222,8 @@ __global__ void pack_kernel(float4 *__restrict__ psi, float2 *__restrict__ phi_n
         float4 p = psi[i];
         p.x = x; p.y = y; p.z = z;
         psi[i] = p;
-        const TriCoord t = tri_coord(x, y, z, a.d);
-        const float wgt = phi_n[(size_t)t.gx + (size_t)a.d.X * ((size_t)t.gy + (size_t)a.d.Y * t.gz)].y;
+        const TriCoord t = tri_coord(x, y, z, a.dg);
+        const float wgt = phi_n[(size_t)t.gx + (size_t)a.dg.X * ((size_t)t.gy + (size_t)a.dg.Y * t.gz)].y;
         phi_n_psi[i] = make_float2(a.w[i], wgt);
     }
 }
@@ -226,11 +235,11 @@ static int stream_grid(size_t n) {
 }
 
 void launch_unpack(const float4 *psi, const float2 *phi_global, const float2 *phi_n, const LoopArgs &a, cudaStream_t st) {
-    const size_t n = (size_t)a.d.X * a.d.Y * a.d.Z;
+    const size_t n = (size_t)a.dg.X * a.dg.Y * a.dg.Z;
     unpack_kernel<<<stream_grid(n), 256, 0, st>>>(psi, phi_global, phi_n, a);
 }
 void launch_initial_warp(const LoopArgs &a, cudaStream_t st) {
-    const size_t n = (size_t)a.d.X * a.d.Y * a.d.Z;
+    const size_t n = (size_t)a.d.X * a.d.Y * (a.d.Z + 2);
     initial_warp_kernel<<<stream_grid(n), 256, 0, st>>>(a);
 }
 void launch_pass_a_generic(const LoopArgs &a, int it, int log, cudaStream_t st) {

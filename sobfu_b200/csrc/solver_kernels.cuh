@@ -33,7 +33,12 @@ struct LoopArgs {
     float *px, *py, *pz, *w;
     const float *pg, *pn;
     float *gx, *gy, *gz;
-    Dims d;
+    // z-slab decomposition: `d` is the LOCAL extent (X, Y, owned planes), `dg` the global volume and z0
+    // the global z of local plane 0.  px/py/pz/w point at local plane 0 and carry one valid halo plane on either side;
+    // pg holds the owned planes, pn the whole volume (the warp gathers anywhere); nabla_U has 3 halo planes (GLayout).
+    // Boundary rules (axis term dropped / clamp to edge) apply on GLOBAL faces only.  Single GPU: dg == d, z0 == 0.
+    Dims d, dg;
+    int z0;
     GLayout gl;
     // parameters
     float S[7];
@@ -61,6 +66,8 @@ SB_DEV bool loop_finished(const LoopArgs &a, int it) {
 }
 
 void launch_unpack(const float4 *psi, const float2 *phi_global, const float2 *phi_n, const LoopArgs &a, cudaStream_t st);
+void launch_estimate_inverse_slab(const float4 *psi_full, float4 *psi_inv_local, Dims dg, int z0, int nzl, int iters, cudaStream_t st);
+void launch_apply_slab(const float2 *phi_full, float2 *out_local, const float4 *psi_local, Dims dg, int z0, int nzl, cudaStream_t st);
 void launch_initial_warp(const LoopArgs &a, cudaStream_t st);
 void launch_pass_a_generic(const LoopArgs &a, int it, int log, cudaStream_t st);
 void launch_pass_b_generic(const LoopArgs &a, int it, cudaStream_t st);

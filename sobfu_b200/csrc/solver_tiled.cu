@@ -146,9 +146,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
             // it into L2 a few steps before that.  The psi maps carry pass A's box (72 x 18): two boxes cover 24 rows.
             const int r = pf.p - 3;
             if (r >= pf.zb) {
-                tma_prefetch_3d(&mpx, pf.x0t, pf.y0t, r); tma_prefetch_3d(&mpx, pf.x0t, pf.y0t + 12, r);
-                tma_prefetch_3d(&mpy, pf.x0t, pf.y0t, r); tma_prefetch_3d(&mpy, pf.x0t, pf.y0t + 12, r);
-                tma_prefetch_3d(&mpz, pf.x0t, pf.y0t, r); tma_prefetch_3d(&mpz, pf.x0t, pf.y0t + 12, r);
+                tma_prefetch_3d(&mpx, pf.x0t, pf.y0t, r + 1); tma_prefetch_3d(&mpx, pf.x0t, pf.y0t + 12, r + 1);
+                tma_prefetch_3d(&mpy, pf.x0t, pf.y0t, r + 1); tma_prefetch_3d(&mpy, pf.x0t, pf.y0t + 12, r + 1);
+                tma_prefetch_3d(&mpz, pf.x0t, pf.y0t, r + 1); tma_prefetch_3d(&mpz, pf.x0t, pf.y0t + 12, r + 1);
             }
             pf.next(sc, d.Z);
         };
@@ -172,6 +172,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
     float *__restrict__ P[3] = {a.px, a.py, a.pz};
     unsigned q = 0;                       // planes consumed so far
     unsigned best_bits = 0u, best_idx = 0u;
+    const unsigned zoff = (unsigned)a.z0 * (unsigned)XY;
     float4 win[7][3];                     // nabla_U of this thread's 4 voxels at planes c-3 .. c+3
     St cs;
     for (cs.open(blockIdx.x, sc, d.Z); cs.valid(sc); cs.open(cs.item + (int)gridDim.x, sc, d.Z)) {
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
                         *reinterpret_cast<float4 *>(P[c] + o) = make_float4(np[c][0], np[c][1], np[c][2], np[c][3]);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const unsigned bits = __float_as_uint(nsq[j]), idx = (unsigned)(o + j);
+                        const unsigned bits = __float_as_uint(nsq[j]), idx = (unsigned)(o + j) + zoff;   // global voxel index
                         if (bits > best_bits) { best_bits = bits; best_idx = idx; }
                         else if (bits == best_bits && bits != 0u && rank_of(idx, a.rm) < rank_of(best_idx, a.rm)) best_idx = idx;
                     }
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 2)
     __shared__ unsigned long long bars[2 * NSTAGE];
     const unsigned full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[NSTAGE]);
 
-    const Dims d = a.d;
+    const Dims d = a.d, dg = a.dg;           // local slab extent / global volume
     const int X = d.X, XY = d.X * d.Y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
@@ -312,9 +313,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 2)
         pf.open(blockIdx.x, sc, d.Z);
         auto prefetch = [&]() {
             if (!pf.valid(sc)) return;
-            tma_prefetch_3d(&m0, pf.x0t - 4, pf.y0t - 1, pf.p);
-            tma_prefetch_3d(&m1, pf.x0t - 4, pf.y0t - 1, pf.p);
-            tma_prefetch_3d(&m2, pf.x0t - 4, pf.y0t - 1, pf.p);
+            tma_prefetch_3d(&m0, pf.x0t - 4, pf.y0t - 1, pf.p + 1);
+            tma_prefetch_3d(&m1, pf.x0t - 4, pf.y0t - 1, pf.p + 1);
+            tma_prefetch_3d(&m2, pf.x0t - 4, pf.y0t - 1, pf.p + 1);
             pf.next(sc, d.Z);
         };
         for (int k = 0; k < PF_AHEAD; ++k) prefetch();
@@ -324,10 +325,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, 2)
             if (n > 0) mbar_wait(empty0 + 8 * slot, (n - 1) & 1u);
             const unsigned dst = smem + slot * STAGE_BYTES, bar = full0 + 8 * slot;
             mbar_expect_tx(bar, TX_BYTES);
-            // unpadded planes: the box starts 4 floats / 1 row before the tile; out-of-range elements arrive as zeros
-            tma_load_3d(dst, &m0, bar, pr.x0t - 4, pr.y0t - 1, pr.p);
-            tma_load_3d(dst + ARR_BYTES, &m1, bar, pr.x0t - 4, pr.y0t - 1, pr.p);
-            tma_load_3d(dst + 2 * ARR_BYTES, &m2, bar, pr.x0t - 4, pr.y0t - 1, pr.p);
+            // the box starts 4 floats / 1 row before the tile (out-of-range elements arrive as zeros); the psi planes are
+            // allocated with one halo plane on either side, so local plane p is plane p + 1 of the tensor map
+            tma_load_3d(dst, &m0, bar, pr.x0t - 4, pr.y0t - 1, pr.p + 1);
+            tma_load_3d(dst + ARR_BYTES, &m1, bar, pr.x0t - 4, pr.y0t - 1, pr.p + 1);
+            tma_load_3d(dst + 2 * ARR_BYTES, &m2, bar, pr.x0t - 4, pr.y0t - 1, pr.p + 1);
             pr.next(sc, d.Z);
         }
         return;
@@ -376,30 +378,30 @@ __global__ void __launch_bounds__((NW + 1) * 32, 2)
             for (int k = 0; k < 3; ++k) zp[k] = lds4(stP + own_off + k * ARR_BYTES);
             // ---- phase 1: warp plane p (own quad + one cross-halo cell); planes outside the volume are never used ----
             float4 wp = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p >= 0 && p < d.Z) {
+            if (a.z0 + p >= 0 && a.z0 + p < dg.Z) {
                 if (active) {
                     if (TEX) {
-                        wp.x = warp_sample_tex(a.pn_tex, a.ashift, a.amask, zp[0].x, zp[1].x, zp[2].x, d);
-                        wp.y = warp_sample_tex(a.pn_tex, a.ashift, a.amask, zp[0].y, zp[1].y, zp[2].y, d);
-                        wp.z = warp_sample_tex(a.pn_tex, a.ashift, a.amask, zp[0].z, zp[1].z, zp[2].z, d);
-                        wp.w = warp_sample_tex(a.pn_tex, a.ashift, a.amask, zp[0].w, zp[1].w, zp[2].w, d);
+                        wp.x = warp_sample_tex(a.pn_tex, a.ashift, a.amask, zp[0].x, zp[1].x, zp[2].x, dg);
+                        wp.y = warp_sample_tex(a.pn_tex, a.ashift, a.amask, zp[0].y, zp[1].y, zp[2].y, dg);
+                        wp.z = warp_sample_tex(a.pn_tex, a.ashift, a.amask, zp[0].z, zp[1].z, zp[2].z, dg);
+                        wp.w = warp_sample_tex(a.pn_tex, a.ashift, a.amask, zp[0].w, zp[1].w, zp[2].w, dg);
                     } else {
-                        wp.x = warp_sample(pn, zp[0].x, zp[1].x, zp[2].x, d, X, XY);
-                        wp.y = warp_sample(pn, zp[0].y, zp[1].y, zp[2].y, d, X, XY);
-                        wp.z = warp_sample(pn, zp[0].z, zp[1].z, zp[2].z, d, X, XY);
-                        wp.w = warp_sample(pn, zp[0].w, zp[1].w, zp[2].w, d, X, XY);
+                        wp.x = warp_sample(pn, zp[0].x, zp[1].x, zp[2].x, dg, X, XY);
+                        wp.y = warp_sample(pn, zp[0].y, zp[1].y, zp[2].y, dg, X, XY);
+                        wp.z = warp_sample(pn, zp[0].z, zp[1].z, zp[2].z, dg, X, XY);
+                        wp.w = warp_sample(pn, zp[0].w, zp[1].w, zp[2].w, dg, X, XY);
                     }
                 }
                 sts4(wcur + own_off, wp);
                 if (halo_on) {
                     const float hxv = lds1(stP + halo_off), hyv = lds1(stP + halo_off + ARR_BYTES), hzv = lds1(stP + halo_off + 2 * ARR_BYTES);
-                    sts1(wcur + halo_off, TEX ? warp_sample_tex(a.pn_tex, a.ashift, a.amask, hxv, hyv, hzv, d) : warp_sample(pn, hxv, hyv, hzv, d, X, XY));
+                    sts1(wcur + halo_off, TEX ? warp_sample_tex(a.pn_tex, a.ashift, a.amask, hxv, hyv, hzv, dg) : warp_sample(pn, hxv, hyv, hzv, dg, X, XY));
                 }
             }
             asm volatile("bar.sync 1, %0;" ::"r"(NCONS) : "memory");     // warped plane p (and p-1) visible to all consumers
             // ---- phase 2: nabla_U of the centre plane ----
             if (zc >= cs.zb) {
-                const bool z_lo = (zc == 0), z_hi = (zc == d.Z - 1), bz = z_lo || z_hi;
+                const bool z_lo = (a.z0 + zc == 0), z_hi = (a.z0 + zc == dg.Z - 1), bz = z_lo || z_hi;   // global faces only
                 // central differences of the warped TSDF; both taps on the in-range neighbour at a boundary (-> +0)
                 float nx[4], ny[4], nz[4], df[4];
                 {
@@ -523,10 +525,11 @@ TmaMaps *tma_maps_create(const LoopArgs &a) {
     if (!get_tensor_map_encoder()) return nullptr;
     TmaMaps *m = new TmaMaps();
     float *g[3] = {a.gx, a.gy, a.gz};
-    const float *in[3] = {a.px, a.py, a.pz};
+    const size_t XYp = (size_t)a.d.X * a.d.Y;
+    const float *in[3] = {a.px - XYp, a.py - XYp, a.pz - XYp};     // allocations start one halo plane before local plane 0
     bool ok = true;
     for (int c = 0; c < 3; ++c) ok = ok && encode_map_3d(&m->g[c], g[c], a.gl.PX, a.gl.PY, a.gl.PZ, pb::SX, pb::SY);
-    for (int c = 0; c < 3; ++c) ok = ok && encode_map_3d(&m->in[c], in[c], a.d.X, a.d.Y, a.d.Z, pa::SX, pa::SY);
+    for (int c = 0; c < 3; ++c) ok = ok && encode_map_3d(&m->in[c], in[c], a.d.X, a.d.Y, a.d.Z + 2, pa::SX, pa::SY);
     ok = ok && cudaFuncSetAttribute(pb::pass_b_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pb::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
