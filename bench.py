@@ -33,7 +33,10 @@ BOXING = dict(vol_size=0.75, trunc_vox=48.0, eta_vox=3.0, max_weight=128.0, fx=5
               trunc_depth=1.0, pose_tz=0.1, sigma_depth=0.005, sigma_spatial=4.5, ksz=7, start_frame=1,
               max_update_norm=1e-10, s=7, lam=0.1, alpha=0.001, w_reg=0.6)
 COLS, ROWS = 640, 480
-ALGO_BYTES_PASS_B = 64      # R nabla_U 16 + R psi 16 + W psi 16 + R phi_n 8 + W phi_n_psi 8   
+# algorithmic bytes per voxel-iteration in the reference's layouts; the warp of the live TSDF is fused
+# into pass A here (SURVEY fuses it into pass B), so its 16 B move with it: 48 + 16 | 48 = 112
+ALGO_BYTES_PASS_A = 64      # R psi 16 + R phi_n_psi 8 + R phi_global 8 + W nabla_U 16  +  warp: R phi_n 8 + W phi_n_psi 8
+ALGO_BYTES_PASS_B = 48      # R nabla_U 16 + R psi 16 + W psi 16   (Sobolev filter + psi update + max-norm partials)
 ALGO_BYTES_ITER = 112
 
 
@@ -103,7 +106,7 @@ def make_params(sf, dim, iters):
     return p
 
 
-def cpu_baseline(dim=96, iters=2):
+def cpu_baseline(dim=128, iters=6):
     """the oracle port (CPU restatement of the same iteration) on the host cores, bounded sample"""
     from oracle import pyoracle as orc
     from tests.common import sphere_pair
@@ -124,11 +127,10 @@ def cpu_baseline(dim=96, iters=2):
 
 def run_ours(args, rank, world, torch, dist):
     import sobfu_b200 as sf
+    from sobfu_b200.parallel import SlabFusion
     dim, iters = args.dim, args.iters
-    if world > 1:
-        raise SystemExit("z-slab multi-GPU mode is not wired into bench.py yet")
     p = make_params(sf, dim, iters)
-    fusion = sf.SobFusion(p)
+    fusion = sf.SobFusion(p) if world == 1 else SlabFusion(p, dist)   # z-slab over the ranks
     frames = [torch.from_numpy(synth_depth(f).view(np.int16)).pin_memory() for f in range(1 + 2 * (args.warmup + args.steps))]
     dev_depth = torch.empty((ROWS, COLS), dtype=torch.int16, device="cuda")
 
@@ -186,7 +188,16 @@ def run_ours(args, rank, world, torch, dist):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = ALGO_BYTES_PASS_B * N / (ms_b * 1e-3) / 1e9
+    Nl = N // world                                   # voxels per GPU (z-slab)
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json"))).get("%d^3" % dim, {}) if world == 1 else {}
+    except Exception:
+        pass
+    dom, dom_ms, dom_bytes = ("pass_a", ms_a, ALGO_BYTES_PASS_A) if ms_a >= ms_b else ("pass_b", ms_b, ALGO_BYTES_PASS_B)
+    achieved = dom_bytes * Nl / (dom_ms * 1e-3) / 1e9
+    desc = {"pass_a": "pass_a (warp of the live TSDF + SDF-difference data-term gradient + Laplacian -> nabla_U)",
+            "pass_b": "pass_b (Sobolev filter + psi update + max-norm partials)"}
     out = {
         "metric": "solver_gvoxel_iters_per_s", "value": N * iters * args.steps / (ms * 1e-3) / 1e9, "unit": "Gvoxel-iter/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -196,16 +207,22 @@ def run_ours(args, rank, world, torch, dist):
                    "parallelism": "1 GPU" if world == 1 else "z-slab x%d" % world},
         "solver_iters_per_s": iters * args.steps / (ms * 1e-3), "loop_ms_per_iter": loop_ms / (args.steps * iters),
         "kernel_ms": {"pass_a": ms_a, "pass_b": ms_b, "iteration": ms_it},
-        "iteration_roofline_frac": ALGO_BYTES_ITER * N / (ms_it * 1e-3) / 1e9 / peak,
+        "iteration_roofline_frac": ALGO_BYTES_ITER * Nl / (ms_it * 1e-3) / 1e9 / peak,
+        "pass_b_roofline_frac": ALGO_BYTES_PASS_B * Nl / (ms_b * 1e-3) / 1e9 / peak,
+        "pass_a_roofline_frac": ALGO_BYTES_PASS_A * Nl / (ms_a * 1e-3) / 1e9 / peak,
         "clocks": clk,
         "e2e": {"value": N * iters * args.steps / (ms_e2e * 1e-3) / 1e9, "unit": "Gvoxel-iter/s", "frames_per_s": args.steps / (ms_e2e * 1e-3),
                 "h2d_bytes_per_step": COLS * ROWS * 2, "d2h_bytes_per_step": 4 + iters * 24 + 16},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "pass_b (Sobolev filter + psi update + warp + max partials)", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": desc[dom], "achieved": achieved,
                      "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                     "unit": "GB/s", "frac": achieved / peak, "algorithmic_bytes_per_voxel": ALGO_BYTES_PASS_B, "traffic": None},
+                     "unit": "GB/s", "frac": achieved / peak, "algorithmic_bytes_per_voxel": dom_bytes,
+                     "traffic": traffic.get(dom), "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"},
     }
     if rank == 0:
+        if world > 1:
+            out["config"]["multi_gpu"] = ("z-slab of %d planes per GPU; per iteration: nabla_U halo (3 planes) + psi halo (1 plane) with both "
+                                          "neighbours and a scalar MAX all-reduce over NCCL/NVLink" % (dim // world))
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out), flush=True)

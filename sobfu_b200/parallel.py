@@ -45,3 +45,62 @@ class SlabSolver(Solver):
     def slab_dims(self):
         X, Y, _ = self.params.volume_dims
         return (X, Y, self.nz)
+
+
+class SlabFusion:
+    """SobFusion::operator() (src/sobfu/sob_fusion.cpp:71-145) with the volume partitioned along z over the ranks.
+
+    Every rank pre-processes the depth frame and integrates the whole live TSDF phi_n itself (0.3 Mpixel of input against
+    a gather that may reach anywhere in the volume); phi_global, psi, psi^-1 and the warped volumes exist only as slabs.
+    """
+
+    def __init__(self, params, dist):
+        import copy
+
+        from .api import Affine3f, DeformationField, TsdfVolume
+        self.params, self.dist = params, dist
+        self.rank, self.nranks = dist.get_rank(), dist.get_world_size()
+        self.z0, self.nz = slab_range(params.volume_dims[2], self.rank, self.nranks)
+        X, Y, Z = params.volume_dims
+        self.slab_params = copy.copy(params)
+        self.slab_params.volume_dims = (X, Y, self.nz)
+        self.slab_params.volume_size = (params.volume_size[0], params.volume_size[1], float(params.voxel_sizes()[2]) * self.nz)
+        self.frame_counter_ = 0
+        self.poses_ = [Affine3f()]
+        self._T, self._D = TsdfVolume, DeformationField
+        self.phi_global = self.phi_global_psi_inv = self.phi_n = self.phi_n_psi = None
+        self.psi = self.psi_inv = self.solver = None
+
+    def _slab_of(self, vol):
+        return vol.data()[self.z0:self.z0 + self.nz]
+
+    def __call__(self, depth):
+        from .api import computeDists, depthBilateralFilter, depthTruncation
+        p = self.params
+        d = depthBilateralFilter(depth, p.bilateral_kernel_size, p.bilateral_sigma_spatial, p.bilateral_sigma_depth)
+        depthTruncation(d, p.icp_truncate_depth_dist)
+        dists = computeDists(d, p.intr)
+        if self.frame_counter_ == 0:
+            self.phi_n = self._T(p)                                   # whole volume
+            self.phi_n.integrate(dists, self.poses_[-1], p.intr)
+            self.phi_global = self._T(self.slab_params)               # slabs
+            self.phi_global.data().copy_(self._slab_of(self.phi_n))
+            self.phi_global_psi_inv = self._T(self.slab_params)
+            self.phi_n_psi = self._T(self.slab_params)
+            self.psi = self._D(self.slab_params.volume_dims)
+            self.psi.get_data()[..., 2] += float(self.z0)             # identity in ABSOLUTE voxel coordinates
+            self.psi_inv = self._D(self.slab_params.volume_dims)
+            self.solver = SlabSolver(p, self.dist)
+            self.frame_counter_ += 1
+            return True
+        self.phi_n.clear()
+        self.phi_n.integrate(dists, self.poses_[-1], p.intr)
+        if self.frame_counter_ < p.start_frame:
+            self.phi_n_psi.data().copy_(self._slab_of(self.phi_n))
+            self.phi_global.integrate(self.phi_n_psi)
+            self.frame_counter_ += 1
+            return True
+        self.solver.estimate_psi(self.phi_global, self.phi_global_psi_inv, self.phi_n, self.phi_n_psi, self.psi, self.psi_inv)
+        self.phi_global.integrate(self.phi_n_psi)
+        self.frame_counter_ += 1
+        return True
