@@ -10,7 +10,9 @@ psi^-1 + the two warps).
   e2e    : the same metric through the frame call a user of the reference makes -- SobFusion::operator()(depth) with the
            depth frame in pinned HOST memory: H2D of the frame, bilateral/truncate/dists, TSDF integration, the solver,
            TSDF fusion, and a D2H read of the solve result, all inside the timed region
-  roofline: pass B (Sobolev filter + psi update + warp + max-norm partials), algorithmic 64 B/voxel
+  roofline: the longer of the two kernels of an iteration, with the algorithmic bytes of SURVEY.md 8d
+           (pass A incl. the warp 64 B/voxel, pass B = Sobolev filter + psi update + max partials 48 B/voxel);
+           both fractions are also reported as pass_a_roofline_frac / pass_b_roofline_frac
   --impl reference : the UNMODIFIED reference CUDA (oracle/_ref, built from /root/reference) on the same workload; the
            reference has no CPU solver path, so its own CUDA on one B200 is the baseline arm.
 """
@@ -106,8 +108,9 @@ def make_params(sf, dim, iters):
     return p
 
 
-def cpu_baseline(dim=128, iters=6):
-    """the oracle port (CPU restatement of the same iteration) on the host cores, bounded sample"""
+def cpu_baseline(dim=160, min_seconds=4.0):
+    """the oracle port (CPU restatement of the same iteration) on all host cores, bounded sample (a few seconds of wall
+    clock = minutes of core time on the GPU box's 128 cores)"""
     from oracle import pyoracle as orc
     from tests.common import sphere_pair
     dims = (dim, dim, dim)
@@ -118,8 +121,10 @@ def cpu_baseline(dim=128, iters=6):
     taps = orc.sobolev_taps(7, 0.1)
     orc.solver_iteration(pg, pn, pnp, psi, scratch, taps, 0.001, 0.6)      # warm-up (page faults, omp pool)
     t0 = time.perf_counter()
-    for _ in range(iters):
+    iters = 0
+    while time.perf_counter() - t0 < min_seconds:
         orc.solver_iteration(pg, pn, pnp, psi, scratch, taps, 0.001, 0.6)
+        iters += 1
     dt = time.perf_counter() - t0
     return {"value": dim ** 3 * iters / dt / 1e9, "unit": "Gvoxel-iter/s", "cores": os.cpu_count(), "kind": "port",
             "sample": "%d solver iterations at %d^3 (oracle/sobfu_oracle.c, OpenMP on all host cores), %.2f s" % (iters, dim, dt)}

@@ -300,3 +300,32 @@ class Reference:
         k = self.L.ref_marching_cubes(self.h, which, _p(v), _p(n), cap)
         k = min(k, cap)
         return v[:k].copy(), n[:k].copy()
+
+
+def mc_tables():
+    lib().orc_mc_num_verts_table.restype = C.POINTER(C.c_int)
+    lib().orc_mc_tri_table.restype = C.POINTER(C.c_int)
+    nv = np.ctypeslib.as_array(lib().orc_mc_num_verts_table(), shape=(256,)).copy()
+    tri = np.ctypeslib.as_array(lib().orc_mc_tri_table(), shape=(256, 16)).copy()
+    return nv, tri
+
+
+def mc_occupied(vol, cap=None):
+    X, Y, Z = dims_of(vol)
+    cap = cap or X * Y * Z
+    v, c, n = (np.zeros(cap, dtype=np.int32) for _ in range(3))
+    k = lib().orc_mc_occupied(_p(vol), X, Y, Z, _p(v), _p(c), _p(n), cap)
+    k = min(k, cap)
+    return v[:k], c[:k], n[:k]
+
+
+def mc_triangles(vol, size, R, t, voxel_idx, nverts_total):
+    X, Y, Z = dims_of(vol)
+    verts = np.zeros((max(nverts_total, 1), 4), dtype=np.float32)
+    normals = np.zeros_like(verts)
+    R = np.ascontiguousarray(R, dtype=np.float32).reshape(-1)
+    t = np.ascontiguousarray(t, dtype=np.float32)
+    vi = np.ascontiguousarray(voxel_idx, dtype=np.int32)
+    k = lib().orc_mc_triangles(_p(vol), X, Y, Z, C.c_float(size[0]), C.c_float(size[1]), C.c_float(size[2]), _p(R), _p(t), _p(vi), len(vi),
+                               _p(verts), _p(normals), len(verts))
+    return verts[:k], normals[:k]

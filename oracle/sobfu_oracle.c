@@ -655,3 +655,91 @@ void orc_compute_dists(const unsigned short *depth, float *dists, int cols, int 
             dists[y * cols + x] = depth[y * cols + x] * lambda * 0.001f;
         }
 }
+
+/* ================================================================================================ */
+/* marching cubes (marching_cubes.cu:40-276, tables marching_cubes.cpp:100-368)                       */
+#include "mc_tables.h"
+
+static int g_nv[256], g_tri[256 * 16], g_tables_ready = 0;
+static void mc_tables(void) {
+    if (g_tables_ready) return;
+    for (int c = 0; c < 256; ++c) {
+        const char *s = kMcTri[c];
+        int n = 0;
+        for (; s[n]; ++n) g_tri[c * 16 + n] = s[n] <= '9' ? s[n] - '0' : s[n] - 'a' + 10;
+        g_nv[c] = n;
+        for (int k = n; k < 16; ++k) g_tri[c * 16 + k] = -1;
+    }
+    g_tables_ready = 1;
+}
+const int *orc_mc_num_verts_table(void) { mc_tables(); return g_nv; }
+const int *orc_mc_tri_table(void) { mc_tables(); return g_tri; }
+
+/* computeCubeIndex, marching_cubes.cu:40-79 */
+static int cube_index(const orc_f2 *vol, int x, int y, int z, int X, int Y, float *f) {
+    const int ox[8] = {0, 1, 1, 0, 0, 1, 1, 0}, oy[8] = {0, 0, 1, 1, 0, 0, 1, 1}, oz[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+    for (int k = 0; k < 8; ++k) {
+        orc_f2 v = vol[IDX(x + ox[k], y + oy[k], z + oz[k])];
+        if (v.y == 0.f) return 0;
+        f[k] = v.x;
+    }
+    int c = 0;
+    for (int k = 0; k < 8; ++k) c += (f[k] < 0.f) << k;
+    return c;
+}
+
+/* OccupiedVoxels, marching_cubes.cu:81-144, in voxel-index order (the reference's order depends on its atomics) */
+int orc_mc_occupied(const orc_f2 *vol, int X, int Y, int Z, int *voxel_idx, int *cube_idx, int *num_verts, int cap) {
+    mc_tables();
+    int n = 0;
+    for (int z = 0; z < Z - 1; ++z)
+        for (int y = 0; y < Y - 1; ++y)
+            for (int x = 0; x < X - 1; ++x) {
+                float f[8];
+                int c = cube_index(vol, x, y, z, X, Y, f);
+                int nv = (c == 0 || c == 255) ? 0 : g_nv[c];
+                if (nv > 0) {
+                    if (n < cap) { voxel_idx[n] = (int)IDX(x, y, z); cube_idx[n] = c; num_verts[n] = nv; }
+                    ++n;
+                }
+            }
+    return n;
+}
+
+/* TrianglesGenerator, marching_cubes.cu:185-276 (approx: '/', rsqrt on the GPU) */
+int orc_mc_triangles(const orc_f2 *vol, int X, int Y, int Z, float sx, float sy, float sz, const float *R, const float *t,
+                     const int *voxel_idx, int count, orc_f4 *verts, orc_f4 *normals, int cap) {
+    mc_tables();
+    const float cs[3] = {sx / X, sy / Y, sz / Z};
+    const int ox[8] = {0, 1, 1, 0, 0, 1, 1, 0}, oy[8] = {0, 0, 1, 1, 0, 0, 1, 1}, oz[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+    const int e0[12] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3}, e1[12] = {1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7};
+    int out = 0;
+    for (int i = 0; i < count; ++i) {
+        int v = voxel_idx[i], z = v / (X * Y), y = (v - z * X * Y) / X, x = v - z * X * Y - y * X;
+        float f[8], p[8][3], vl[12][3];
+        int c = cube_index(vol, x, y, z, X, Y, f);
+        for (int k = 0; k < 8; ++k) {
+            p[k][0] = ((float)(x + ox[k]) + 0.5f) * cs[0]; p[k][1] = ((float)(y + oy[k]) + 0.5f) * cs[1]; p[k][2] = ((float)(z + oz[k]) + 0.5f) * cs[2];
+        }
+        for (int e = 0; e < 12; ++e) {
+            float tt = (0.f - f[e0[e]]) / (f[e1[e]] - f[e0[e]] + 1e-15f);
+            for (int q = 0; q < 3; ++q) vl[e][q] = fmaf(tt, p[e1[e]][q] - p[e0[e]][q], p[e0[e]][q]);
+        }
+        for (int k = 0; k < g_nv[c]; k += 3) {
+            const float *p1 = vl[g_tri[c * 16 + k]], *p2 = vl[g_tri[c * 16 + k + 1]], *p3 = vl[g_tri[c * 16 + k + 2]];
+            float a[3] = {p3[0] - p1[0], p3[1] - p1[1], p3[2] - p1[2]}, b[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+            float n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+            float inv = 1.f / sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            const float *ps[3] = {p1, p2, p3};
+            for (int q = 0; q < 3; ++q, ++out) {
+                if (out >= cap) continue;
+                float w[3];
+                for (int r = 0; r < 3; ++r) w[r] = fmaf(R[3 * r], ps[q][0], fmaf(R[3 * r + 1], ps[q][1], R[3 * r + 2] * ps[q][2])) + t[r];
+                orc_f4 vv = {w[0], -w[1], -w[2], 1.f}, nn = {n[0] * inv, -n[1] * inv, -n[2] * inv, 1.f};
+                verts[out] = vv;
+                if (normals) normals[out] = nn;
+            }
+        }
+    }
+    return out;
+}

@@ -1,0 +1,107 @@
+"""marching cubes: table identity, oracle sanity (CPU) and GPU parity (cube indices / vertex counts / voxel ids bit-exact,
+vertex positions within a float tolerance), plus the reference's own CUDA when oracle/_ref is present."""
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as orc
+from tests.common import f32, sphere_pair
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TABLE_SHA = "ee3d7a3bdb23973c2dc0e403b98032875fd68972589929561ee06b6897426323"
+
+
+def table_rows(path):
+    txt = open(path).read()
+    body = txt[txt.index("kMcTri[256] = {"):]
+    return re.findall(r'"([0-9a-b]*)"', body)[:256]
+
+
+def test_tables_are_the_canonical_bourke_tables():
+    for rel in ("sobfu_b200/csrc/mc_tables.h", "oracle/mc_tables.h"):
+        rows = table_rows(os.path.join(ROOT, rel))
+        assert len(rows) == 256 and hashlib.sha256("\n".join(rows).encode()).hexdigest() == TABLE_SHA, rel
+    nv, tri = orc.mc_tables()
+    assert nv[0] == 0 and nv[255] == 0 and nv.max() == 15 and (nv % 3 == 0).all()
+    assert all((tri[c, :nv[c]] >= 0).all() and (tri[c, :nv[c]] < 12).all() and (tri[c, nv[c]:] == -1).all() for c in range(256))
+    ref = "/root/reference/src/kfusion/marching_cubes.cpp"
+    if os.path.exists(ref):                    # build container only: same content as the reference's triTable / numVertsTable
+        src = open(ref).read()
+        body = re.search(r"const int triTable\[256\]\[16\] = \{(.*?)\};\s*\n\s*/\* number", src, re.S).group(1)
+        rows = ["".join("%x" % int(x) for x in r.replace("\n", " ").split(",") if x.strip() and int(x) >= 0) for r in re.findall(r"\{([^{}]*)\}", body)]
+        assert hashlib.sha256("\n".join(rows).encode()).hexdigest() == TABLE_SHA
+
+
+def sphere_volume(dims=(32, 32, 32)):
+    pg, _, vs, trunc, eta = sphere_pair(dims, r=0.07)
+    return pg, vs
+
+
+def test_oracle_mesh_lies_on_the_sphere():
+    dims = (32, 32, 32)
+    vol, vs = sphere_volume(dims)
+    vox, cube, nvt = orc.mc_occupied(vol)
+    assert len(vox) > 500 and (np.diff(vox) > 0).all()
+    size = tuple(float(vs[i]) * dims[i] for i in range(3))
+    verts, normals = orc.mc_triangles(vol, size, np.eye(3), np.zeros(3), vox, int(nvt.sum()))
+    assert len(verts) == nvt.sum()
+    p = verts[:, :3] * np.array([1, -1, -1], dtype=f32)         # undo the y/z negation of store_point
+    r = np.linalg.norm(p - 0.125, axis=1)
+    assert np.abs(r - 0.07).max() < 1.0 * vs[0]                  # within a voxel of the analytic radius
+    assert np.abs(np.linalg.norm(normals[:, :3], axis=1) - 1).max() < 1e-4
+
+
+@pytest.mark.gpu
+def test_gpu_marching_cubes_matches_the_oracle(built):
+    import torch
+    import sobfu_b200 as sf
+    dims = (40, 36, 32)
+    vol, vs = sphere_volume(dims)
+    vol[5:9, 5:9, 5:9, 1] = 0          # some zero-weight voxels inside the band: cubes touching them produce nothing
+    size = tuple(float(vs[i]) * dims[i] for i in range(3))
+    p = sf.Params(volume_dims=dims, volume_size=size, tsdf_trunc_dist=1.0, eta=1.0, tsdf_max_weight=1.0)
+    v = sf.TsdfVolume(p)
+    v.data().copy_(torch.from_numpy(vol))
+    mc = sf.MarchingCubes()
+    mc.setPose(sf.Affine3f().translate((-0.1, 0.05, 0.3)))
+    verts, normals, occ = mc.run(v, return_occupied=True)
+    vox, cube, nvt = orc.mc_occupied(vol)
+    occ = occ.cpu().numpy()
+    assert np.array_equal(occ[0], vox) and np.array_equal(occ[1], cube) and np.array_equal(occ[2], nvt)   # bit-exact indexing
+    ov, on = orc.mc_triangles(vol, size, np.eye(3), np.array([-0.1, 0.05, 0.3], dtype=f32), vox, int(nvt.sum()))
+    assert verts.shape[0] == len(ov)
+    assert np.abs(verts.cpu().numpy() - ov).max() < 2e-6          # approximate division on the GPU
+    assert np.abs(normals.cpu().numpy() - on).max() < 2e-3        # rsqrt.approx on nearly degenerate triangles
+    again = mc.run(v)[0]
+    assert torch.equal(again, verts)                                # deterministic output order
+
+
+@pytest.mark.gpu
+def test_gpu_marching_cubes_matches_the_reference_cuda(built):
+    if not os.path.exists(orc.REF):
+        pytest.skip("oracle/_ref not built")
+    import torch
+    import sobfu_b200 as sf
+    dims = (32, 32, 32)
+    size = (0.25, 0.25, 0.25)
+    vs = f32(0.25) / f32(32)
+    ref = orc.Reference(dims, size, float(5 * vs), float(2 * vs), 64.0, 0, 1, 7, -1.0, 0.1, 0.01, 0.4, pose_t=(-0.125, -0.125, 0.1))
+    ref.init_sphere(ref.GLOBAL, (0.125, 0.12, 0.13), 0.06)
+    vol = ref.download_tsdf(ref.GLOBAL)
+    rv, rn = ref.marching_cubes(ref.GLOBAL)
+    ref.close()
+    p = sf.Params(volume_dims=dims, volume_size=size, tsdf_trunc_dist=1.0, eta=1.0, tsdf_max_weight=1.0)
+    v = sf.TsdfVolume(p)
+    v.data().copy_(torch.from_numpy(vol))
+    mc = sf.MarchingCubes()
+    mc.setPose(sf.Affine3f().translate((-0.125, -0.125, 0.1)))
+    verts, normals = mc.run(v)
+    a, b = verts.cpu().numpy(), rv
+    assert a.shape == b.shape and a.shape[0] > 1000
+    # the reference's triangle order depends on its atomics: compare as sorted triangle lists
+    ka = np.sort(a.reshape(-1, 12).view([("", a.dtype)] * 12), axis=0).view(a.dtype).reshape(-1, 12)
+    kb = np.sort(b.reshape(-1, 12).view([("", b.dtype)] * 12), axis=0).view(b.dtype).reshape(-1, 12)
+    assert np.abs(ka - kb).max() < 1e-6
