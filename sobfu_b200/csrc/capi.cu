@@ -178,6 +178,10 @@ struct sobfu_b200_solver {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_user = nullptr;
+    // overlapped slab mode: halo exchanges run on their own stream while the planes away from the slab faces are computed
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_g = nullptr, ev_b = nullptr, ev_p = nullptr;
+    bool psi_exchange_pending = false;   // ev_p has been recorded and not yet waited for by the compute stream
     int variant = 0;
     TmaMaps *tma = nullptr;
     cudaArray_t pn_array = nullptr;           // phi_n.x gather4 atlas (see LoopArgs::pn_tex)
@@ -209,6 +213,7 @@ static void fill_args(sobfu_b200_solver *s) {
     a.state = s->state; a.maxkey = s->maxkey; a.e_data = s->energies; a.e_reg = s->energies + (s->p.max_iter > 0 ? s->p.max_iter : 1);
     a.rm = rank_map_for(s->Ng);
     a.check = 1;
+    a.a_uses_max = 1;
     a.pn_tex = s->pn_tex; a.pn_surf = s->pn_surf; a.ashift = s->ashift; a.amask = s->amask;
 }
 
@@ -300,6 +305,8 @@ extern "C" int sobfu_b200_solver_destroy(sobfu_b200_solver *s) {
     if (s->h_state) cudaFreeHost(s->h_state);
     for (auto &e : s->ev) if (e) cudaEventDestroy(e);
     if (s->ev_user) cudaEventDestroy(s->ev_user);
+    for (cudaEvent_t e : {s->ev_a, s->ev_g, s->ev_b, s->ev_p}) if (e) cudaEventDestroy(e);
+    if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return 0;
@@ -389,6 +396,8 @@ extern "C" int sobfu_b200_solver_attach_comm(sobfu_b200_solver *s, const void *i
     ncclResult_t r = n.CommInitRank(&s->comm, nranks, id, rank);
     if (r != ncclSuccess) { s->comm = nullptr; return fail(SOBFU_B200_ECOMM, "ncclCommInitRank: %s", n.GetErrorString(r)); }
     s->rank = rank; s->nranks = nranks;
+    CK(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t *e : {&s->ev_a, &s->ev_g, &s->ev_b, &s->ev_p}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     return alloc_workspace(s, z0, nz);
 }
 
@@ -399,7 +408,7 @@ extern "C" int sobfu_b200_solver_attach_comm(sobfu_b200_solver *s, const void *i
     } while (0)
 
 // one halo plane of each psi component to / from both neighbours (pass A reads psi at z +- 1)
-static int exchange_psi(sobfu_b200_solver *s) {
+static int exchange_psi(sobfu_b200_solver *s, cudaStream_t st) {
     if (s->nranks == 1) return 0;
     NcclApi &n = nccl_api();
     float *P[3] = {s->args.px, s->args.py, s->args.pz};
@@ -407,19 +416,19 @@ static int exchange_psi(sobfu_b200_solver *s) {
     CKN(n.GroupStart());
     for (int c = 0; c < 3; ++c) {
         if (s->rank > 0) {
-            CKN(n.Send(P[c], XY, ncclFloat, s->rank - 1, s->comm, s->stream));
-            CKN(n.Recv(P[c] - XY, XY, ncclFloat, s->rank - 1, s->comm, s->stream));
+            CKN(n.Send(P[c], XY, ncclFloat, s->rank - 1, s->comm, st));
+            CKN(n.Recv(P[c] - XY, XY, ncclFloat, s->rank - 1, s->comm, st));
         }
         if (s->rank < s->nranks - 1) {
-            CKN(n.Send(P[c] + (nzl - 1) * XY, XY, ncclFloat, s->rank + 1, s->comm, s->stream));
-            CKN(n.Recv(P[c] + nzl * XY, XY, ncclFloat, s->rank + 1, s->comm, s->stream));
+            CKN(n.Send(P[c] + (nzl - 1) * XY, XY, ncclFloat, s->rank + 1, s->comm, st));
+            CKN(n.Recv(P[c] + nzl * XY, XY, ncclFloat, s->rank + 1, s->comm, st));
         }
     }
     CKN(n.GroupEnd());
     return 0;
 }
 // three (padded) halo planes of each nabla_U component to / from both neighbours (the filter reads nabla_U at z +- 3)
-static int exchange_g(sobfu_b200_solver *s) {
+static int exchange_g(sobfu_b200_solver *s, cudaStream_t st) {
     if (s->nranks == 1) return 0;
     NcclApi &n = nccl_api();
     float *G[3] = {s->args.gx, s->args.gy, s->args.gz};
@@ -427,12 +436,12 @@ static int exchange_g(sobfu_b200_solver *s) {
     CKN(n.GroupStart());
     for (int c = 0; c < 3; ++c) {
         if (s->rank > 0) {
-            CKN(n.Send(G[c] + 3 * pl, 3 * pl, ncclFloat, s->rank - 1, s->comm, s->stream));             // owned planes 0..2
-            CKN(n.Recv(G[c], 3 * pl, ncclFloat, s->rank - 1, s->comm, s->stream));                      // halo planes -3..-1
+            CKN(n.Send(G[c] + 3 * pl, 3 * pl, ncclFloat, s->rank - 1, s->comm, st));             // owned planes 0..2
+            CKN(n.Recv(G[c], 3 * pl, ncclFloat, s->rank - 1, s->comm, st));                      // halo planes -3..-1
         }
         if (s->rank < s->nranks - 1) {
-            CKN(n.Send(G[c] + nzl * pl, 3 * pl, ncclFloat, s->rank + 1, s->comm, s->stream));           // owned planes nzl-3..nzl-1
-            CKN(n.Recv(G[c] + (nzl + 3) * pl, 3 * pl, ncclFloat, s->rank + 1, s->comm, s->stream));     // halo planes nzl..nzl+2
+            CKN(n.Send(G[c] + nzl * pl, 3 * pl, ncclFloat, s->rank + 1, s->comm, st));           // owned planes nzl-3..nzl-1
+            CKN(n.Recv(G[c] + (nzl + 3) * pl, 3 * pl, ncclFloat, s->rank + 1, s->comm, st));     // halo planes nzl..nzl+2
         }
     }
     CKN(n.GroupEnd());
@@ -443,24 +452,65 @@ static inline bool log_iter(const sobfu_b200_params &p, int iter1) {   // iter1 
     return p.verbosity == 2 || (p.verbosity == 1 && (iter1 == 1 || iter1 % 50 == 0 || iter1 == p.max_iter));
 }
 
+static ZRanges whole_slab(const sobfu_b200_solver *s) { return ZRanges{1, {0, 0}, {s->d.Z, 0}}; }
 static void run_pass_a(sobfu_b200_solver *s, int it, int log) {
     if (!use_tiled(s)) launch_pass_a_generic(s->args, it, log, s->stream);
-    else launch_pass_a_tma(s->args, s->tma, it, log, s->stream);
+    else launch_pass_a_tma(s->args, s->tma, it, log, whole_slab(s), s->stream);
 }
 static void run_pass_b(sobfu_b200_solver *s, int it) {
     if (!use_tiled(s)) launch_pass_b_generic(s->args, it, s->stream);
-    else launch_pass_b_tma(s->args, s->tma, it, s->stream);
+    else launch_pass_b_tma(s->args, s->tma, it, whole_slab(s), s->stream);
+}
+// the compute stream catches up with a psi halo exchange that was left running on the communication stream
+static int join_psi_exchange(sobfu_b200_solver *s) {
+    if (s->psi_exchange_pending) {
+        CK(cudaStreamWaitEvent(s->stream, s->ev_p, 0));
+        s->psi_exchange_pending = false;
+    }
+    return 0;
 }
 // one gradient-descent iteration: pass A, [nabla_U halo exchange], pass B, [psi halo exchange, global max]
 static int launch_iteration(sobfu_b200_solver *s, int it, int log, int *launches) {
+    int rc = 0;
+    const int n = s->d.Z;
+    static const bool no_overlap = getenv("SOBFU_B200_NO_OVERLAP") != nullptr;
+    if (s->nranks > 1 && use_tiled(s) && !log && n >= 12 && !no_overlap) {
+        // Overlapped slab iteration.  "edge" = the 3 planes next to each slab face (their nabla_U is what the neighbours
+        // need, and their filter needs the neighbours' nabla_U), "mid" = the rest.
+        //   compute: A_mid | wait psi halos | A_edge | B_mid            | wait nabla_U halos | B_edge
+        //   comm   :                         nabla_U exchange (after A_edge)                  psi exchange + global max
+        // Pass A only writes scratch, so A_mid may run before the previous iteration's global maximum is known: it honours
+        // the sticky flag only (a_uses_max = 0); pass B, which changes psi, always sees the reduced maximum.
+        const ZRanges mid{1, {3, 0}, {n - 3, 0}}, edge{2, {0, n - 3}, {3, n}};
+        LoopArgs a = s->args;
+        a.a_uses_max = 0;
+        launch_pass_a_tma(a, s->tma, it, 0, mid, s->stream);
+        if ((rc = join_psi_exchange(s))) return rc;
+        launch_pass_a_tma(a, s->tma, it, 0, edge, s->stream);
+        CK(cudaEventRecord(s->ev_a, s->stream));
+        CK(cudaStreamWaitEvent(s->comm_stream, s->ev_a, 0));
+        if ((rc = exchange_g(s, s->comm_stream))) return rc;
+        CK(cudaEventRecord(s->ev_g, s->comm_stream));
+        launch_pass_b_tma(a, s->tma, it, mid, s->stream);
+        CK(cudaStreamWaitEvent(s->stream, s->ev_g, 0));
+        launch_pass_b_tma(a, s->tma, it, edge, s->stream);
+        CK(cudaEventRecord(s->ev_b, s->stream));
+        CK(cudaStreamWaitEvent(s->comm_stream, s->ev_b, 0));
+        if ((rc = exchange_psi(s, s->comm_stream))) return rc;
+        if (s->args.check)
+            CKN(nccl_api().AllReduce(s->maxkey + it, s->maxkey + it, 1, ncclUint64, ncclMax, s->comm, s->comm_stream));
+        CK(cudaEventRecord(s->ev_p, s->comm_stream));
+        s->psi_exchange_pending = true;
+        *launches += 4;
+        return 0;
+    }
+    if ((rc = join_psi_exchange(s))) return rc;
     run_pass_a(s, it, log);
-    int rc = exchange_g(s);
-    if (rc) return rc;
+    if ((rc = exchange_g(s, s->stream))) return rc;
     run_pass_b(s, it);
     *launches += 2;
     if (s->nranks > 1) {
-        rc = exchange_psi(s);
-        if (rc) return rc;
+        if ((rc = exchange_psi(s, s->stream))) return rc;
         if (!use_tiled(s)) { launch_initial_warp(s->args, s->stream); ++*launches; }   // generic pass A reads w on the halo planes
         if (s->args.check)   // the convergence test of the next iteration must see the global maximum
             CKN(nccl_api().AllReduce(s->maxkey + it, s->maxkey + it, 1, ncclUint64, ncclMax, s->comm, s->stream));
@@ -486,7 +536,7 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
         CK(cudaMemsetAsync(s->energies, 0, 2 * mi * sizeof(double), st));
     }
     launch_unpack(psi, phi_global, phi_n, s->args, st);
-    if ((rc = exchange_psi(s))) return rc;
+    if ((rc = exchange_psi(s, st))) return rc;
     launch_initial_warp(s->args, st);
     launches += 2;
     CK_LAST();
@@ -499,6 +549,7 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
         const int it1 = it0 + CHUNK < mi ? it0 + CHUNK : mi;
         for (int it = it0; it < it1; ++it)
             if ((rc = launch_iteration(s, it, log_iter(p, it + 1) ? 1 : 0, &launches))) return rc;
+        if ((rc = join_psi_exchange(s))) return rc;
         CK_LAST();
         if (it1 < mi) {   // peek at the sticky flag (it is raised by pass A of the iteration after the converged one)
             CK(cudaMemcpyAsync(s->h_state, s->state, sizeof(LoopState), cudaMemcpyDeviceToHost, st));
@@ -642,6 +693,7 @@ extern "C" int sobfu_b200_solver_time_loop(sobfu_b200_solver *s, int iters, floa
     CK(cudaEventRecord(s->ev[0], st));
     for (int i = 0; i < iters; ++i)
         if ((rc = launch_iteration(s, slot, 0, &launches))) { s->args.check = 1; return rc; }
+    if ((rc = join_psi_exchange(s))) { s->args.check = 1; return rc; }
     CK(cudaEventRecord(s->ev[1], st));
     // pass A alone / pass B alone (no exchanges; B keeps descending, which is fine for timing)
     for (int i = 0; i < iters; ++i) run_pass_a(s, slot, 0);

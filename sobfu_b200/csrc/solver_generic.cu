@@ -176,7 +176,14 @@ SB_DEV float tap7(const float *__restrict__ g, size_t o, long stride, const floa
 }
 
 __global__ void __launch_bounds__(BX *BY *BZ) pass_b_generic_kernel(LoopArgs a, int it) {
-    if (loop_finished(a, it)) return;
+    if (loop_finished(a, it)) {
+        if (a.check && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0 &&
+            !a.state->converged) {
+            a.state->iters = it;
+            a.state->converged = 1;
+        }
+        return;
+    }
     int x, y, z;
     const bool in = voxel_of_thread(a.d, x, y, z);
     unsigned long long key = 0ull;

@@ -49,11 +49,19 @@ struct LoopArgs {
     double *e_data, *e_reg;       // [max_iter] (sums, not yet halved)
     RankMap rm;
     int check;                    // 0: time_loop mode (no convergence logic)
+    int a_uses_max;               // 0: pass A may run before the global maximum of the previous iteration is known
+                                  //    (overlapped slab mode): it then only honours the sticky flag, which pass B raises
     // phi_n.x as a 2-D texture atlas (slice z at tile (z & amask, z >> ashift) of X x Y texels) for gather4 fetches of
     // the trilinear footprint; 0 when unavailable (then phi_n.x is gathered from the pn plane with plain loads)
     cudaTextureObject_t pn_tex;
     cudaSurfaceObject_t pn_surf;
     int ashift, amask;
+};
+
+// z ranges (local planes) a launch works on: the whole slab, or the planes next to / away from the slab faces
+struct ZRanges {
+    int n;
+    int lo[2], hi[2];
 };
 
 // decision shared by every block of iteration `it` (0-based): has the loop already ended?
@@ -78,8 +86,8 @@ bool tiled_supported(const Dims d);
 struct TmaMaps;   // opaque: CUtensorMaps of the nabla_U components (pass B) and of the psi / w planes (pass A)
 TmaMaps *tma_maps_create(const LoopArgs &a);
 void tma_maps_destroy(TmaMaps *m);
-void launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, cudaStream_t st);
-void launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, cudaStream_t st);
+void launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, const ZRanges &zr, cudaStream_t st);
+void launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, const ZRanges &zr, cudaStream_t st);
 
 // free-standing field kernels (field_ops.cu)
 void launch_init_identity(float4 *psi, Dims d, cudaStream_t st);

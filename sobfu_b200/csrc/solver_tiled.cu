@@ -35,8 +35,11 @@ struct TmaMaps {
 
 namespace {
 
+// work items = (x tile, y tile, z chunk) over up to two z ranges of the slab
 struct Sched {
-    int tiles_x, tiles_y, nz, zchunk, nitems;
+    int tiles_x, tiles_y, nitems;
+    int nr;
+    int zlo[2], zhi[2], nz[2], zchunk[2];
 };
 
 SB_DEVI float c4(const float4 &v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
@@ -77,12 +80,16 @@ struct Stream {
         item = it;
         if (item >= sc.nitems) return;
         const int xy = sc.tiles_x * sc.tiles_y;
-        const int tz = item / xy, rem = item - tz * xy;
+        int tz = item / xy;
+        const int rem = item - tz * xy;
         const int tyi = rem / sc.tiles_x;
         x0t = (rem - tyi * sc.tiles_x) * TX;
         y0t = tyi * TY;
-        zb = tz * sc.zchunk;
-        ze = min(zb + sc.zchunk, Z);
+        const int r = (tz >= sc.nz[0]) ? 1 : 0;
+        tz -= r ? sc.nz[0] : 0;
+        zb = sc.zlo[r] + tz * sc.zchunk[r];
+        ze = min(zb + sc.zchunk[r], sc.zhi[r]);
+        (void)Z;
         p = zb - LO;
         p_last = ze - 1 + HI;
     }
@@ -111,7 +118,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
                       const __grid_constant__ CUtensorMap mapz, const __grid_constant__ CUtensorMap mpx,
                       const __grid_constant__ CUtensorMap mpy, const __grid_constant__ CUtensorMap mpz, LoopArgs a, int it,
                       Sched sc) {
-    if (loop_finished(a, it)) return;
+    if (loop_finished(a, it)) {
+        if (a.check && blockIdx.x == 0 && threadIdx.x == 0 && !a.state->converged) {
+            a.state->iters = it;
+            a.state->converged = 1;
+        }
+        return;
+    }
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned smem = (smem_u32(smem_raw) + 127u) & ~127u;
     __shared__ unsigned long long bars[2 * NSTAGE];
@@ -281,7 +294,7 @@ template <bool TEX>
 __global__ void __launch_bounds__((NW + 1) * 32, 2)
     pass_a_tma_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__ CUtensorMap m1,
                       const __grid_constant__ CUtensorMap m2, LoopArgs a, int it, Sched sc) {
-    if (loop_finished(a, it)) {
+    if (a.a_uses_max ? loop_finished(a, it) : (a.check && a.state->converged)) {
         if (a.check && blockIdx.x == 0 && threadIdx.x == 0 && !a.state->converged) {
             a.state->iters = it;
             a.state->converged = 1;
@@ -493,26 +506,34 @@ int sm_count() {
     return sms;
 }
 
-// number of z chunks: fill whole rounds of `ctas` CTAs, chunks of >= 16 planes, few halo planes per chunk
-Sched make_sched(const Dims d, int TX, int TY, int halo_planes, double halo_cost, int ctas) {
+// number of z chunks per range: fill whole rounds of `ctas` CTAs, chunks of >= 16 planes, few halo planes per chunk
+Sched make_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_planes, double halo_cost, int ctas) {
     Sched s;
     s.tiles_x = (d.X + TX - 1) / TX;
     s.tiles_y = (d.Y + TY - 1) / TY;
     const int xy = s.tiles_x * s.tiles_y;
-    int best_nz = 1;
-    double best_score = -1.0;
-    for (int nz = 1; nz <= 64; ++nz) {
-        const int chunk = (d.Z + nz - 1) / nz;
-        if (chunk < 16 && nz > 1) break;
-        const int n = xy * ((d.Z + chunk - 1) / chunk);
-        const int rounds = (n + ctas - 1) / ctas;
-        const double balance = (double)n / ((double)rounds * ctas);
-        const double overlap = (double)chunk / (chunk + halo_planes * halo_cost);
-        if (balance * overlap > best_score) { best_score = balance * overlap; best_nz = nz; }
+    s.nr = zr.n;
+    s.nitems = 0;
+    for (int r = 0; r < 2; ++r) { s.zlo[r] = s.zhi[r] = 0; s.nz[r] = 0; s.zchunk[r] = 1; }
+    for (int r = 0; r < zr.n; ++r) {
+        const int Z = zr.hi[r] - zr.lo[r];
+        s.zlo[r] = zr.lo[r]; s.zhi[r] = zr.hi[r];
+        if (Z <= 0) continue;
+        int best_nz = 1;
+        double best_score = -1.0;
+        for (int nz = 1; nz <= 64; ++nz) {
+            const int chunk = (Z + nz - 1) / nz;
+            if (chunk < 16 && nz > 1) break;
+            const int n = xy * ((Z + chunk - 1) / chunk);
+            const int rounds = (n + ctas - 1) / ctas;
+            const double balance = (double)n / ((double)rounds * ctas);
+            const double overlap = (double)chunk / (chunk + halo_planes * halo_cost);
+            if (balance * overlap > best_score) { best_score = balance * overlap; best_nz = nz; }
+        }
+        s.zchunk[r] = (Z + best_nz - 1) / best_nz;
+        s.nz[r] = (Z + s.zchunk[r] - 1) / s.zchunk[r];
+        s.nitems += xy * s.nz[r];
     }
-    s.zchunk = (d.Z + best_nz - 1) / best_nz;
-    s.nz = (d.Z + s.zchunk - 1) / s.zchunk;
-    s.nitems = xy * s.nz;
     return s;
 }
 
@@ -544,21 +565,23 @@ TmaMaps *tma_maps_create(const LoopArgs &a) {
 
 void tma_maps_destroy(TmaMaps *m) { delete m; }
 
-void launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, cudaStream_t st) {
+void launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, const ZRanges &zr, cudaStream_t st) {
     const int ctas = sm_count();
-    const Sched sc = make_sched(a.d, pb::TX, pb::TY, 6, 0.35, ctas);
+    const Sched sc = make_sched(a.d, zr, pb::TX, pb::TY, 6, 0.35, ctas);
+    if (sc.nitems == 0) return;
     const int grid = sc.nitems < ctas ? sc.nitems : ctas;
     pb::pass_b_tma_kernel<<<grid, (pb::NW + 1) * 32, pb::SMEM_BYTES, st>>>(m->g[0], m->g[1], m->g[2], m->in[0], m->in[1], m->in[2], a, it, sc);
 }
 
-void launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, cudaStream_t st) {
+void launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, const ZRanges &zr, cudaStream_t st) {
     if (log) {   // logging iterations (rare): materialise the warped plane, then the generic kernel that also sums the energies
         launch_initial_warp(a, st);
         launch_pass_a_generic(a, it, 1, st);
         return;
     }
     const int ctas = 2 * sm_count();
-    const Sched sc = make_sched(a.d, pa::TX, pa::TY, 2, 0.5, ctas);
+    const Sched sc = make_sched(a.d, zr, pa::TX, pa::TY, 2, 0.5, ctas);
+    if (sc.nitems == 0) return;
     const int grid = sc.nitems < ctas ? sc.nitems : ctas;
     if (a.pn_tex) pa::pass_a_tma_kernel<true><<<grid, (pa::NW + 1) * 32, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
     else pa::pass_a_tma_kernel<false><<<grid, (pa::NW + 1) * 32, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
