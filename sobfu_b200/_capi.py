@@ -2,7 +2,9 @@
 import ctypes as C
 import os
 
-from .build import LIB
+from .build import LIB as _DEFAULT_LIB
+
+LIB = os.environ.get("SOBFU_B200_LIB", _DEFAULT_LIB)   # tuning aid: load an alternative build of the same library
 
 
 class Sobfu200Error(RuntimeError):

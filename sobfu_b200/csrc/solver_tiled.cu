@@ -85,10 +85,11 @@ struct Stream {
         const int tyi = rem / sc.tiles_x;
         x0t = (rem - tyi * sc.tiles_x) * TX;
         y0t = tyi * TY;
-        const int r = (tz >= sc.nz[0]) ? 1 : 0;
+        const bool r = tz >= sc.nz[0];          // second range? (no dynamic indexing: the schedule stays in registers)
         tz -= r ? sc.nz[0] : 0;
-        zb = sc.zlo[r] + tz * sc.zchunk[r];
-        ze = min(zb + sc.zchunk[r], sc.zhi[r]);
+        const int chunk = r ? sc.zchunk[1] : sc.zchunk[0];
+        zb = (r ? sc.zlo[1] : sc.zlo[0]) + tz * chunk;
+        ze = min(zb + chunk, r ? sc.zhi[1] : sc.zhi[0]);
         (void)Z;
         p = zb - LO;
         p_last = ze - 1 + HI;
@@ -271,8 +272,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
 // =============================================================================================================
 // pass A
 // =============================================================================================================
+#ifndef PA_NW
+#define PA_NW 8
+#define PA_CTAS 2
+#endif
 namespace pa {
-constexpr int LX = 16, RW = 32 / LX, NW = 8;      // 8 consumer warps + 1 producer warp
+constexpr int LX = 16, RW = 32 / LX, NW = PA_NW;  // consumer warps (+ 1 producer warp)
 constexpr int NCONS = NW * 32;
 constexpr int TX = 4 * LX, TY = NW * RW;          // 64 x 16 outputs per plane
 constexpr int SX = TX + 8, SY = TY + 2;           // staged box 4|64|4 floats x 1|16|1 rows
@@ -291,7 +296,7 @@ SB_DEVI void sts4(unsigned saddr, float4 v) {
 SB_DEVI void sts1(unsigned saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
 
 template <bool TEX>
-__global__ void __launch_bounds__((NW + 1) * 32, 2)
+__global__ void __launch_bounds__((NW + 1) * 32, PA_CTAS)
     pass_a_tma_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__ CUtensorMap m1,
                       const __grid_constant__ CUtensorMap m2, LoopArgs a, int it, Sched sc) {
     if (a.a_uses_max ? loop_finished(a, it) : (a.check && a.state->converged)) {
@@ -351,13 +356,19 @@ __global__ void __launch_bounds__((NW + 1) * 32, 2)
     // ---- consumers ----
     const int lx = lane % LX, ty = warp * RW + lane / LX;
     const unsigned own_off = (unsigned)(((ty + 1) * SX + 4 * lx + 4) * 4);
-    // cross-halo cell served by this thread (threads 0 .. NHALO-1): position inside the staged box
-    int hx = -1, hy = -1;                      // box coordinates (floats / rows)
-    if (tid < TX) { hx = 4 + tid; hy = 0; }
-    else if (tid < 2 * TX) { hx = 4 + tid - TX; hy = TY + 1; }
-    else if (tid < 2 * TX + TY) { hx = 3; hy = 1 + tid - 2 * TX; }
-    else if (tid < NHALO) { hx = 4 + TX; hy = 1 + tid - 2 * TX - TY; }
-    const unsigned halo_off = (unsigned)((hy * SX + hx) * 4);
+    // cross-halo cells served by this thread (cells tid, tid + NCONS, ... < NHALO): position inside the staged box
+    constexpr int HPT = (NHALO + NCONS - 1) / NCONS;
+    int hxs[HPT], hys[HPT];
+#pragma unroll
+    for (int k = 0; k < HPT; ++k) {
+        const int h = tid + k * NCONS;
+        int hx = -1, hy = -1;                  // box coordinates (floats / rows)
+        if (h < TX) { hx = 4 + h; hy = 0; }
+        else if (h < 2 * TX) { hx = 4 + h - TX; hy = TY + 1; }
+        else if (h < 2 * TX + TY) { hx = 3; hy = 1 + h - 2 * TX; }
+        else if (h < NHALO) { hx = 4 + TX; hy = 1 + h - 2 * TX - TY; }
+        hxs[k] = hx; hys[k] = hy;
+    }
     float *__restrict__ G[3] = {a.gx, a.gy, a.gz};
     const float *__restrict__ pn = a.pn;
     const GLayout gl = a.gl;
@@ -368,8 +379,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, 2)
         const bool active = x0 < X && y < d.Y;
         const int row = min(x0, X - 4) + X * min(y, d.Y - 1);
         const bool y_lo = (y == 0), y_hi = (y == d.Y - 1), by = y_lo || y_hi;
-        const int hgx = cs.x0t - 4 + hx, hgy = cs.y0t - 1 + hy;       // volume coordinates of the halo cell
-        const bool halo_on = hx >= 0 && hgx >= 0 && hgx < X && hgy >= 0 && hgy < d.Y;
+        bool halo_on[HPT];
+#pragma unroll
+        for (int k = 0; k < HPT; ++k) {
+            const int hgx = cs.x0t - 4 + hxs[k], hgy = cs.y0t - 1 + hys[k];       // volume coordinates of the halo cell
+            halo_on[k] = hxs[k] >= 0 && hgx >= 0 && hgx < X && hgy >= 0 && hgy < d.Y;
+        }
         // this thread's quads at planes z-1 and z: psi (3 components) and the warped TSDF
         float4 zm[3], zc4[3], wm, wc;
 #pragma unroll
@@ -406,10 +421,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, 2)
                     }
                 }
                 sts4(wcur + own_off, wp);
-                if (halo_on) {
-                    const float hxv = lds1(stP + halo_off), hyv = lds1(stP + halo_off + ARR_BYTES), hzv = lds1(stP + halo_off + 2 * ARR_BYTES);
-                    sts1(wcur + halo_off, TEX ? warp_sample_tex(a.pn_tex, a.ashift, a.amask, hxv, hyv, hzv, dg) : warp_sample(pn, hxv, hyv, hzv, dg, X, XY));
-                }
+#pragma unroll
+                for (int k = 0; k < HPT; ++k)
+                    if (halo_on[k]) {
+                        const unsigned halo_off = (unsigned)((hys[k] * SX + hxs[k]) * 4);
+                        const float hxv = lds1(stP + halo_off), hyv = lds1(stP + halo_off + ARR_BYTES), hzv = lds1(stP + halo_off + 2 * ARR_BYTES);
+                        sts1(wcur + halo_off, TEX ? warp_sample_tex(a.pn_tex, a.ashift, a.amask, hxv, hyv, hzv, dg) : warp_sample(pn, hxv, hyv, hzv, dg, X, XY));
+                    }
             }
             asm volatile("bar.sync 1, %0;" ::"r"(NCONS) : "memory");     // warped plane p (and p-1) visible to all consumers
             // ---- phase 2: nabla_U of the centre plane ----
@@ -579,7 +597,7 @@ void launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, con
         launch_pass_a_generic(a, it, 1, st);
         return;
     }
-    const int ctas = 2 * sm_count();
+    const int ctas = PA_CTAS * sm_count();
     const Sched sc = make_sched(a.d, zr, pa::TX, pa::TY, 2, 0.5, ctas);
     if (sc.nitems == 0) return;
     const int grid = sc.nitems < ctas ? sc.nitems : ctas;
