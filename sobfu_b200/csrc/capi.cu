@@ -157,6 +157,7 @@ struct sobfu_b200_solver {
     // z-slab decomposition over ranks (one process per GPU)
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
+    ncclComm_t comm_max = nullptr;   // second communicator: the scalar MAX all-reduce runs concurrently with the halo exchange
     float4 *psi_full = nullptr;    // all-gathered psi / phi_global for the once-per-frame tail (slab mode only)
     float2 *phig_full = nullptr;
     // device scratch
@@ -179,9 +180,10 @@ struct sobfu_b200_solver {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_user = nullptr;
     // overlapped slab mode: halo exchanges run on their own stream while the planes away from the slab faces are computed
-    cudaStream_t comm_stream = nullptr;
-    cudaEvent_t ev_a = nullptr, ev_g = nullptr, ev_b = nullptr, ev_p = nullptr;
+    cudaStream_t comm_stream = nullptr, max_stream = nullptr;
+    cudaEvent_t ev_b = nullptr, ev_bm = nullptr, ev_p = nullptr, ev_m = nullptr;
     bool psi_exchange_pending = false;   // ev_p has been recorded and not yet waited for by the compute stream
+    bool max_pending = false;            // ev_m (global maximum of the previous iteration) likewise
     int variant = 0;
     TmaMaps *tma = nullptr;
     cudaArray_t pn_array = nullptr;           // phi_n.x gather4 atlas (see LoopArgs::pn_tex)
@@ -202,10 +204,11 @@ static bool use_tiled(const sobfu_b200_solver *s) {
 
 static void fill_args(sobfu_b200_solver *s) {
     LoopArgs &a = s->args;
-    const size_t pl = (size_t)(s->d.Z + 2) * s->XY;        // floats per psi component incl. the two halo planes
-    a.px = s->psi_alloc + s->XY; a.py = s->psi_alloc + pl + s->XY; a.pz = s->psi_alloc + 2 * pl + s->XY;
-    a.w = s->w_alloc + s->XY;
-    a.pg = s->pg; a.pn = s->pn;
+    const size_t pl = (size_t)(s->d.Z + 2 * PSI_HALO) * s->XY;   // floats per psi component incl. the halo planes
+    const size_t h = (size_t)PSI_HALO * s->XY;
+    a.px = s->psi_alloc + h; a.py = s->psi_alloc + pl + h; a.pz = s->psi_alloc + 2 * pl + h;
+    a.w = s->w_alloc + h;
+    a.pg = s->pg + (size_t)PG_HALO * s->XY; a.pn = s->pn;
     a.gx = s->g; a.gy = s->g + s->gl.total; a.gz = s->g + 2 * s->gl.total;
     a.d = s->d; a.dg = s->dg; a.z0 = s->z0; a.gl = s->gl;
     for (int i = 0; i < 7; ++i) a.S[i] = s->taps[i];
@@ -268,7 +271,7 @@ static int alloc_workspace(sobfu_b200_solver *s, int z0, int nzl) {
     s->gl.PX = s->d.X + 8; s->gl.PY = s->d.Y + 6; s->gl.PZ = nzl + 6;
     s->gl.plane = (size_t)s->gl.PX * s->gl.PY;
     s->gl.total = s->gl.plane * s->gl.PZ;
-    const size_t pl = (size_t)(nzl + 2) * s->XY;
+    const size_t pl = (size_t)(nzl + 2 * PSI_HALO) * s->XY, pgl = (size_t)(nzl + 2 * PG_HALO) * s->XY;
 #define CKA(expr)                                                                                          \
     do {                                                                                                   \
         cudaError_t e__ = (expr);                                                                          \
@@ -277,13 +280,14 @@ static int alloc_workspace(sobfu_b200_solver *s, int z0, int nzl) {
     } while (0)
     CKA(cudaMalloc(&s->psi_alloc, 3 * pl * sizeof(float)));
     CKA(cudaMalloc(&s->w_alloc, pl * sizeof(float)));
-    CKA(cudaMalloc(&s->pg, s->Nl * sizeof(float)));
+    CKA(cudaMalloc(&s->pg, pgl * sizeof(float)));
+    CKA(cudaMemset(s->pg, 0, pgl * sizeof(float)));
     CKA(cudaMalloc(&s->pn, s->Ng * sizeof(float)));
     CKA(cudaMalloc(&s->g, 3 * s->gl.total * sizeof(float)));
     CKA(cudaMemset(s->psi_alloc, 0, 3 * pl * sizeof(float)));
     CKA(cudaMemset(s->w_alloc, 0, pl * sizeof(float)));
     CKA(cudaMemset(s->g, 0, 3 * s->gl.total * sizeof(float)));
-    s->ws_bytes = (4 * pl + s->Nl + s->Ng + 3 * s->gl.total) * sizeof(float);
+    s->ws_bytes = (4 * pl + pgl + s->Ng + 3 * s->gl.total) * sizeof(float);
     if (s->nranks > 1) {
         CKA(cudaMalloc(&s->psi_full, s->Ng * sizeof(float4)));
         CKA(cudaMalloc(&s->phig_full, s->Ng * sizeof(float2)));
@@ -297,6 +301,7 @@ static int alloc_workspace(sobfu_b200_solver *s, int z0, int nzl) {
 extern "C" int sobfu_b200_solver_destroy(sobfu_b200_solver *s) {
     if (!s) return 0;
     free_workspace(s);
+    if (s->comm_max && nccl_api().ok) nccl_api().CommDestroy(s->comm_max);
     if (s->comm && nccl_api().ok) nccl_api().CommDestroy(s->comm);
     if (s->pn_tex) cudaDestroyTextureObject(s->pn_tex);
     if (s->pn_surf) cudaDestroySurfaceObject(s->pn_surf);
@@ -305,8 +310,9 @@ extern "C" int sobfu_b200_solver_destroy(sobfu_b200_solver *s) {
     if (s->h_state) cudaFreeHost(s->h_state);
     for (auto &e : s->ev) if (e) cudaEventDestroy(e);
     if (s->ev_user) cudaEventDestroy(s->ev_user);
-    for (cudaEvent_t e : {s->ev_a, s->ev_g, s->ev_b, s->ev_p}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {s->ev_b, s->ev_bm, s->ev_p, s->ev_m}) if (e) cudaEventDestroy(e);
     if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+    if (s->max_stream) cudaStreamDestroy(s->max_stream);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return 0;
@@ -396,8 +402,10 @@ extern "C" int sobfu_b200_solver_attach_comm(sobfu_b200_solver *s, const void *i
     ncclResult_t r = n.CommInitRank(&s->comm, nranks, id, rank);
     if (r != ncclSuccess) { s->comm = nullptr; return fail(SOBFU_B200_ECOMM, "ncclCommInitRank: %s", n.GetErrorString(r)); }
     s->rank = rank; s->nranks = nranks;
+    if (n.CommSplit && n.CommSplit(s->comm, 0, rank, &s->comm_max, nullptr) != ncclSuccess) s->comm_max = nullptr;
     CK(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
-    for (cudaEvent_t *e : {&s->ev_a, &s->ev_g, &s->ev_b, &s->ev_p}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&s->max_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t *e : {&s->ev_b, &s->ev_bm, &s->ev_p, &s->ev_m}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     return alloc_workspace(s, z0, nz);
 }
 
@@ -407,25 +415,35 @@ extern "C" int sobfu_b200_solver_attach_comm(sobfu_b200_solver *s, const void *i
         if (r__ != ncclSuccess) return fail(SOBFU_B200_ECOMM, "%s: %s", #expr, nccl_api().GetErrorString(r__)); \
     } while (0)
 
-// one halo plane of each psi component to / from both neighbours (pass A reads psi at z +- 1)
-static int exchange_psi(sobfu_b200_solver *s, cudaStream_t st) {
+// `depth` halo planes of `count` slab-local arrays (local plane 0 at ptr[k], `halo` planes allocated on either side) to /
+// from both neighbours, as one grouped send/recv
+static int exchange_planes(sobfu_b200_solver *s, float *const *ptr, int count, int depth, cudaStream_t st) {
     if (s->nranks == 1) return 0;
     NcclApi &n = nccl_api();
-    float *P[3] = {s->args.px, s->args.py, s->args.pz};
-    const size_t XY = s->XY, nzl = s->d.Z;
+    const size_t XY = s->XY, nzl = s->d.Z, cnt = (size_t)depth * XY;
     CKN(n.GroupStart());
-    for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < count; ++c) {
         if (s->rank > 0) {
-            CKN(n.Send(P[c], XY, ncclFloat, s->rank - 1, s->comm, st));
-            CKN(n.Recv(P[c] - XY, XY, ncclFloat, s->rank - 1, s->comm, st));
+            CKN(n.Send(ptr[c], cnt, ncclFloat, s->rank - 1, s->comm, st));                        // owned planes 0 .. depth-1
+            CKN(n.Recv(ptr[c] - cnt, cnt, ncclFloat, s->rank - 1, s->comm, st));                  // halo planes -depth .. -1
         }
         if (s->rank < s->nranks - 1) {
-            CKN(n.Send(P[c] + (nzl - 1) * XY, XY, ncclFloat, s->rank + 1, s->comm, st));
-            CKN(n.Recv(P[c] + nzl * XY, XY, ncclFloat, s->rank + 1, s->comm, st));
+            CKN(n.Send(ptr[c] + (nzl - depth) * XY, cnt, ncclFloat, s->rank + 1, s->comm, st));   // owned planes nzl-depth .. nzl-1
+            CKN(n.Recv(ptr[c] + nzl * XY, cnt, ncclFloat, s->rank + 1, s->comm, st));             // halo planes nzl .. nzl+depth-1
         }
     }
     CKN(n.GroupEnd());
     return 0;
+}
+// psi halos: PSI_HALO planes (pass A of the owner recomputes nabla_U on its 3 halo planes from them)
+static int exchange_psi(sobfu_b200_solver *s, cudaStream_t st) {
+    float *P[3] = {s->args.px, s->args.py, s->args.pz};
+    return exchange_planes(s, P, 3, PSI_HALO, st);
+}
+// phi_global.x halos: constant during a solve, once per estimate_psi
+static int exchange_pg(sobfu_b200_solver *s, cudaStream_t st) {
+    float *P[1] = {const_cast<float *>(s->args.pg)};
+    return exchange_planes(s, P, 1, PG_HALO, st);
 }
 // three (padded) halo planes of each nabla_U component to / from both neighbours (the filter reads nabla_U at z +- 3)
 static int exchange_g(sobfu_b200_solver *s, cudaStream_t st) {
@@ -461,7 +479,7 @@ static void run_pass_b(sobfu_b200_solver *s, int it) {
     if (!use_tiled(s)) launch_pass_b_generic(s->args, it, s->stream);
     else launch_pass_b_tma(s->args, s->tma, it, whole_slab(s), s->stream);
 }
-// the compute stream catches up with a psi halo exchange that was left running on the communication stream
+// the compute stream catches up with work that was left running on the communication streams
 static int join_psi_exchange(sobfu_b200_solver *s) {
     if (s->psi_exchange_pending) {
         CK(cudaStreamWaitEvent(s->stream, s->ev_p, 0));
@@ -469,42 +487,56 @@ static int join_psi_exchange(sobfu_b200_solver *s) {
     }
     return 0;
 }
-// one gradient-descent iteration: pass A, [nabla_U halo exchange], pass B, [psi halo exchange, global max]
+static int join_max(sobfu_b200_solver *s) {
+    if (s->max_pending) {
+        CK(cudaStreamWaitEvent(s->stream, s->ev_m, 0));
+        s->max_pending = false;
+    }
+    return 0;
+}
+// one gradient-descent iteration
 static int launch_iteration(sobfu_b200_solver *s, int it, int log, int *launches) {
     int rc = 0;
     const int n = s->d.Z;
     static const bool no_overlap = getenv("SOBFU_B200_NO_OVERLAP") != nullptr;
     if (s->nranks > 1 && use_tiled(s) && !log && n >= 12 && !no_overlap) {
-        // Overlapped slab iteration.  "edge" = the 3 planes next to each slab face (their nabla_U is what the neighbours
-        // need, and their filter needs the neighbours' nabla_U), "mid" = the rest.
-        //   compute: A_mid | wait psi halos | A_edge | B_mid            | wait nabla_U halos | B_edge
-        //   comm   :                         nabla_U exchange (after A_edge)                  psi exchange + global max
-        // Pass A only writes scratch, so A_mid may run before the previous iteration's global maximum is known: it honours
-        // the sticky flag only (a_uses_max = 0); pass B, which changes psi, always sees the reduced maximum.
-        const ZRanges mid{1, {3, 0}, {n - 3, 0}}, edge{2, {0, n - 3}, {3, n}};
+        // Slab iteration with ONE exchange.  psi carries 4 halo planes, so pass A also computes nabla_U on the 3 halo planes
+        // next to an interior face (same inputs as the owner -> same bits) and no nabla_U exchange is needed.
+        //   compute : A_mid [1,n-1) | wait psi halos | A_edge [-3,1) u [n-1,n+3) | wait global max | B_edge [0,4) u [n-4,n) | B_mid
+        //   comm    :   psi exchange (4 planes) of the previous iteration ........ |                 | after B_edge: psi exchange
+        //   max     :   MAX all-reduce of the previous iteration ................................... | after B_mid: MAX all-reduce
+        // Pass A only writes scratch, so it may run before the previous iteration's global maximum is known: it honours the
+        // sticky flag only (a_uses_max = 0); pass B, which changes psi, always sees the reduced maximum.
+        const int lo = s->rank > 0 ? -3 : 0, hi = s->rank < s->nranks - 1 ? n + 3 : n;
+        const ZRanges a_mid{1, {1, 0}, {n - 1, 0}}, a_edge{2, {lo, n - 1}, {1, hi}};
+        const ZRanges b_edge{2, {0, n - 4}, {4, n}}, b_mid{1, {4, 0}, {n - 4, 0}};
         LoopArgs a = s->args;
         a.a_uses_max = 0;
-        launch_pass_a_tma(a, s->tma, it, 0, mid, s->stream);
+        launch_pass_a_tma(a, s->tma, it, 0, a_mid, s->stream);
         if ((rc = join_psi_exchange(s))) return rc;
-        launch_pass_a_tma(a, s->tma, it, 0, edge, s->stream);
-        CK(cudaEventRecord(s->ev_a, s->stream));
-        CK(cudaStreamWaitEvent(s->comm_stream, s->ev_a, 0));
-        if ((rc = exchange_g(s, s->comm_stream))) return rc;
-        CK(cudaEventRecord(s->ev_g, s->comm_stream));
-        launch_pass_b_tma(a, s->tma, it, mid, s->stream);
-        CK(cudaStreamWaitEvent(s->stream, s->ev_g, 0));
-        launch_pass_b_tma(a, s->tma, it, edge, s->stream);
+        launch_pass_a_tma(a, s->tma, it, 0, a_edge, s->stream);
+        if ((rc = join_max(s))) return rc;
+        launch_pass_b_tma(a, s->tma, it, b_edge, s->stream);
         CK(cudaEventRecord(s->ev_b, s->stream));
         CK(cudaStreamWaitEvent(s->comm_stream, s->ev_b, 0));
         if ((rc = exchange_psi(s, s->comm_stream))) return rc;
-        if (s->args.check)
-            CKN(nccl_api().AllReduce(s->maxkey + it, s->maxkey + it, 1, ncclUint64, ncclMax, s->comm, s->comm_stream));
         CK(cudaEventRecord(s->ev_p, s->comm_stream));
         s->psi_exchange_pending = true;
+        launch_pass_b_tma(a, s->tma, it, b_mid, s->stream);
+        if (s->args.check) {
+            ncclComm_t cm = s->comm_max ? s->comm_max : s->comm;
+            cudaStream_t ms = s->comm_max ? s->max_stream : s->comm_stream;   // without a second communicator: behind the exchange
+            CK(cudaEventRecord(s->ev_bm, s->stream));
+            CK(cudaStreamWaitEvent(ms, s->ev_bm, 0));
+            CKN(nccl_api().AllReduce(s->maxkey + it, s->maxkey + it, 1, ncclUint64, ncclMax, cm, ms));
+            CK(cudaEventRecord(s->ev_m, ms));
+            s->max_pending = true;
+        }
         *launches += 4;
         return 0;
     }
-    if ((rc = join_psi_exchange(s))) return rc;
+    // serial form: pass A on the owned planes, nabla_U halo exchange, pass B, psi halo exchange, global max
+    if ((rc = join_psi_exchange(s)) || (rc = join_max(s))) return rc;
     run_pass_a(s, it, log);
     if ((rc = exchange_g(s, s->stream))) return rc;
     run_pass_b(s, it);
@@ -536,7 +568,7 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
         CK(cudaMemsetAsync(s->energies, 0, 2 * mi * sizeof(double), st));
     }
     launch_unpack(psi, phi_global, phi_n, s->args, st);
-    if ((rc = exchange_psi(s, st))) return rc;
+    if ((rc = exchange_psi(s, st)) || (rc = exchange_pg(s, st))) return rc;
     launch_initial_warp(s->args, st);
     launches += 2;
     CK_LAST();
@@ -549,7 +581,7 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
         const int it1 = it0 + CHUNK < mi ? it0 + CHUNK : mi;
         for (int it = it0; it < it1; ++it)
             if ((rc = launch_iteration(s, it, log_iter(p, it + 1) ? 1 : 0, &launches))) return rc;
-        if ((rc = join_psi_exchange(s))) return rc;
+        if ((rc = join_psi_exchange(s)) || (rc = join_max(s))) return rc;
         CK_LAST();
         if (it1 < mi) {   // peek at the sticky flag (it is raised by pass A of the iteration after the converged one)
             CK(cudaMemcpyAsync(s->h_state, s->state, sizeof(LoopState), cudaMemcpyDeviceToHost, st));
@@ -693,7 +725,7 @@ extern "C" int sobfu_b200_solver_time_loop(sobfu_b200_solver *s, int iters, floa
     CK(cudaEventRecord(s->ev[0], st));
     for (int i = 0; i < iters; ++i)
         if ((rc = launch_iteration(s, slot, 0, &launches))) { s->args.check = 1; return rc; }
-    if ((rc = join_psi_exchange(s))) { s->args.check = 1; return rc; }
+    if ((rc = join_psi_exchange(s)) || (rc = join_max(s))) { s->args.check = 1; return rc; }
     CK(cudaEventRecord(s->ev[1], st));
     // pass A alone / pass B alone (no exchanges; B keeps descending, which is fine for timing)
     for (int i = 0; i < iters; ++i) run_pass_a(s, slot, 0);

@@ -42,7 +42,8 @@ __global__ void unpack_kernel(const float4 *__restrict__ psi, const float2 *__re
 // halo planes when they exist in the global volume
 __global__ void initial_warp_kernel(LoopArgs a) {
     const long XY = (long)a.d.X * a.d.Y;
-    const long lo = (a.z0 > 0) ? -XY : 0, hi = XY * a.d.Z + ((a.z0 + a.d.Z < a.dg.Z) ? XY : 0);
+    const long hl = min(PSI_HALO, a.z0), hh = min(PSI_HALO, a.dg.Z - (a.z0 + a.d.Z));    // halo planes that exist in the volume
+    const long lo = -XY * hl, hi = XY * (a.d.Z + hh);
     for (long i = lo + (long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long)gridDim.x * blockDim.x) {
         const TriCoord t = tri_coord(a.px[i], a.py[i], a.pz[i], a.dg);
         a.w[i] = sample_scalar<1>(a.pn, t, a.dg);
@@ -246,7 +247,7 @@ void launch_unpack(const float4 *psi, const float2 *phi_global, const float2 *ph
     unpack_kernel<<<stream_grid(n), 256, 0, st>>>(psi, phi_global, phi_n, a);
 }
 void launch_initial_warp(const LoopArgs &a, cudaStream_t st) {
-    const size_t n = (size_t)a.d.X * a.d.Y * (a.d.Z + 2);
+    const size_t n = (size_t)a.d.X * a.d.Y * (a.d.Z + 2 * PSI_HALO);
     initial_warp_kernel<<<stream_grid(n), 256, 0, st>>>(a);
 }
 void launch_pass_a_generic(const LoopArgs &a, int it, int log, cudaStream_t st) {

@@ -12,6 +12,12 @@
 
 namespace sb {
 
+// halo depths (planes) of the slab-local arrays: one iteration depends on psi within 4 planes (1 for the stencils of pass A
+// + 3 for the filter of pass B), so with 4 halo planes of psi a rank can compute nabla_U on its own 3 halo planes itself
+// and the iteration needs ONE exchange (psi) instead of two (nabla_U and psi)
+constexpr int PSI_HALO = 4;
+constexpr int PG_HALO = 3;
+
 // padded layout of the nabla_U planes
 struct GLayout {
     int PX, PY, PZ;        // padded extents: X+8, Y+6, Z+6
@@ -34,8 +40,8 @@ struct LoopArgs {
     const float *pg, *pn;
     float *gx, *gy, *gz;
     // z-slab decomposition: `d` is the LOCAL extent (X, Y, owned planes), `dg` the global volume and z0
-    // the global z of local plane 0.  px/py/pz/w point at local plane 0 and carry one valid halo plane on either side;
-    // pg holds the owned planes, pn the whole volume (the warp gathers anywhere); nabla_U has 3 halo planes (GLayout).
+    // the global z of local plane 0.  px/py/pz/w point at local plane 0 and carry PSI_HALO halo planes on either side,
+    // pg PG_HALO; pn is the whole volume (the warp gathers anywhere); nabla_U has 3 halo planes (GLayout).
     // Boundary rules (axis term dropped / clamp to edge) apply on GLOBAL faces only.  Single GPU: dg == d, z0 == 0.
     Dims d, dg;
     int z0;

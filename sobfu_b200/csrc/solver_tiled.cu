@@ -160,9 +160,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
             // it into L2 a few steps before that.  The psi maps carry pass A's box (72 x 18): two boxes cover 24 rows.
             const int r = pf.p - 3;
             if (r >= pf.zb) {
-                tma_prefetch_3d(&mpx, pf.x0t, pf.y0t, r + 1); tma_prefetch_3d(&mpx, pf.x0t, pf.y0t + 12, r + 1);
-                tma_prefetch_3d(&mpy, pf.x0t, pf.y0t, r + 1); tma_prefetch_3d(&mpy, pf.x0t, pf.y0t + 12, r + 1);
-                tma_prefetch_3d(&mpz, pf.x0t, pf.y0t, r + 1); tma_prefetch_3d(&mpz, pf.x0t, pf.y0t + 12, r + 1);
+                tma_prefetch_3d(&mpx, pf.x0t, pf.y0t, r + PSI_HALO); tma_prefetch_3d(&mpx, pf.x0t, pf.y0t + 12, r + PSI_HALO);
+                tma_prefetch_3d(&mpy, pf.x0t, pf.y0t, r + PSI_HALO); tma_prefetch_3d(&mpy, pf.x0t, pf.y0t + 12, r + PSI_HALO);
+                tma_prefetch_3d(&mpz, pf.x0t, pf.y0t, r + PSI_HALO); tma_prefetch_3d(&mpz, pf.x0t, pf.y0t + 12, r + PSI_HALO);
             }
             pf.next(sc, d.Z);
         };
@@ -331,9 +331,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, PA_CTAS)
         pf.open(blockIdx.x, sc, d.Z);
         auto prefetch = [&]() {
             if (!pf.valid(sc)) return;
-            tma_prefetch_3d(&m0, pf.x0t - 4, pf.y0t - 1, pf.p + 1);
-            tma_prefetch_3d(&m1, pf.x0t - 4, pf.y0t - 1, pf.p + 1);
-            tma_prefetch_3d(&m2, pf.x0t - 4, pf.y0t - 1, pf.p + 1);
+            tma_prefetch_3d(&m0, pf.x0t - 4, pf.y0t - 1, pf.p + PSI_HALO);
+            tma_prefetch_3d(&m1, pf.x0t - 4, pf.y0t - 1, pf.p + PSI_HALO);
+            tma_prefetch_3d(&m2, pf.x0t - 4, pf.y0t - 1, pf.p + PSI_HALO);
             pf.next(sc, d.Z);
         };
         for (int k = 0; k < PF_AHEAD; ++k) prefetch();
@@ -344,10 +344,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, PA_CTAS)
             const unsigned dst = smem + slot * STAGE_BYTES, bar = full0 + 8 * slot;
             mbar_expect_tx(bar, TX_BYTES);
             // the box starts 4 floats / 1 row before the tile (out-of-range elements arrive as zeros); the psi planes are
-            // allocated with one halo plane on either side, so local plane p is plane p + 1 of the tensor map
-            tma_load_3d(dst, &m0, bar, pr.x0t - 4, pr.y0t - 1, pr.p + 1);
-            tma_load_3d(dst + ARR_BYTES, &m1, bar, pr.x0t - 4, pr.y0t - 1, pr.p + 1);
-            tma_load_3d(dst + 2 * ARR_BYTES, &m2, bar, pr.x0t - 4, pr.y0t - 1, pr.p + 1);
+            // allocated with PSI_HALO halo planes on either side, so local plane p is plane p + PSI_HALO of the tensor map
+            tma_load_3d(dst, &m0, bar, pr.x0t - 4, pr.y0t - 1, pr.p + PSI_HALO);
+            tma_load_3d(dst + ARR_BYTES, &m1, bar, pr.x0t - 4, pr.y0t - 1, pr.p + PSI_HALO);
+            tma_load_3d(dst + 2 * ARR_BYTES, &m2, bar, pr.x0t - 4, pr.y0t - 1, pr.p + PSI_HALO);
             pr.next(sc, d.Z);
         }
         return;
@@ -565,10 +565,10 @@ TmaMaps *tma_maps_create(const LoopArgs &a) {
     TmaMaps *m = new TmaMaps();
     float *g[3] = {a.gx, a.gy, a.gz};
     const size_t XYp = (size_t)a.d.X * a.d.Y;
-    const float *in[3] = {a.px - XYp, a.py - XYp, a.pz - XYp};     // allocations start one halo plane before local plane 0
+    const float *in[3] = {a.px - PSI_HALO * XYp, a.py - PSI_HALO * XYp, a.pz - PSI_HALO * XYp};   // allocations start PSI_HALO planes before local plane 0
     bool ok = true;
     for (int c = 0; c < 3; ++c) ok = ok && encode_map_3d(&m->g[c], g[c], a.gl.PX, a.gl.PY, a.gl.PZ, pb::SX, pb::SY);
-    for (int c = 0; c < 3; ++c) ok = ok && encode_map_3d(&m->in[c], in[c], a.d.X, a.d.Y, a.d.Z + 2, pa::SX, pa::SY);
+    for (int c = 0; c < 3; ++c) ok = ok && encode_map_3d(&m->in[c], in[c], a.d.X, a.d.Y, a.d.Z + 2 * PSI_HALO, pa::SX, pa::SY);
     ok = ok && cudaFuncSetAttribute(pb::pass_b_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pb::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
