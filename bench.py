@@ -211,7 +211,7 @@ def run_ours(args, rank, world, torch, dist):
                                "estimate_psi with %d iterations" % (dim, dim, iters, iters), "l2": "inputs exceed L2 (%.0f MB of solver state)" % (36 * N / 1e6),
                    "parallelism": "1 GPU" if world == 1 else "z-slab x%d" % world},
         "solver_iters_per_s": iters * args.steps / (ms * 1e-3), "loop_ms_per_iter": loop_ms / (args.steps * iters),
-        "kernel_ms": {"pass_a": ms_a, "pass_b": ms_b, "iteration": ms_it},
+        "kernel_ms": {"pass_a": ms_a, "pass_b": ms_b, "iteration": ms_it if world == 1 else loop_ms / (args.steps * iters)},
         # whole iteration incl. halo exchanges, from the loop of the timed estimate_psi calls (device events of the library)
         "iteration_roofline_frac": ALGO_BYTES_ITER * Nl / (loop_ms / (args.steps * iters) * 1e-3) / 1e9 / peak,
         "pass_b_roofline_frac": ALGO_BYTES_PASS_B * Nl / (ms_b * 1e-3) / 1e9 / peak,
@@ -227,8 +227,9 @@ def run_ours(args, rank, world, torch, dist):
     }
     if rank == 0:
         if world > 1:
-            out["config"]["multi_gpu"] = ("z-slab of %d planes per GPU; per iteration: nabla_U halo (3 planes) + psi halo (1 plane) with both "
-                                          "neighbours and a scalar MAX all-reduce over NCCL/NVLink" % (dim // world))
+            out["config"]["multi_gpu"] = ("z-slab of %d planes per GPU; per iteration ONE psi halo exchange (4 planes, grouped ncclSend/Recv with both "
+                                          "neighbours) behind the mid-slab kernels + a scalar MAX all-reduce on a second communicator; nabla_U on "
+                                          "the 3 halo planes is recomputed locally" % (dim // world))
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out), flush=True)
