@@ -30,7 +30,8 @@ namespace sb {
 
 struct TmaMaps {
     CUtensorMap g[3];      // nabla_U components (padded), pass B input
-    CUtensorMap in[3];     // psi x/y/z planes, pass A input
+    CUtensorMap in[3];     // psi x/y/z planes, pass A input (box with cross halo)
+    CUtensorMap pb_psi[3]; // psi x/y/z planes, pass B input (tile without halo)
 };
 
 namespace {
@@ -53,23 +54,43 @@ SB_DEVI float warp_sample(const float *__restrict__ pn, float px, float py, floa
                     __ldg(pn + r11 + t.gx), __ldg(pn + r10 + t.gx), __ldg(pn + r01 + t.gx), __ldg(pn + r00 + t.gx), t);
 }
 
-// Same value through the texture unit: two gather4 fetches (planes gz and z1) return the 2 x 2 x 2 footprint, with no
-// address arithmetic and no load instructions in the SM's LSU.  x1 / y1 equal gx / gy on the first and last planes
-// (utils.hpp:61-72); the neighbouring texel returned by the gather is then replaced by the base texel, so the value is
-// bit-identical to warp_sample() for every input.
+// Same value through the texture unit: two gather4 fetches (planes gz and z1 of the atlas) return the 2 x 2 x 2 footprint,
+// with no address arithmetic and no load instructions in the SM's LSU.  The sample is written in two halves so that a thread
+// can put the gathers of several samples in flight and do other work before it touches the first result.
+//   issue : tri_coord() of utils.hpp:50-75 without integer detours -- floor stays a float, slice -> atlas tile by exact fp32
+//           arithmetic (every value is an integer < 2^24) -- then the two fetches
+//   finish: x1 / y1 equal gx / gy on the first and last planes (utils.hpp:61-72); the neighbouring texel returned by the gather
+//           is then replaced by the base texel, so the value is bit-identical to warp_sample() for every input
+struct TexSample {
+    float4 lo, hi;       // texels of slices gz and z1: .w (i,j) .z (i+1,j) .x (i,j+1) .y (i+1,j+1)
+    float a, b, c;       // fractional weights
+    bool sx, sy;
+};
+SB_DEVI void tex_issue(TexSample &s, cudaTextureObject_t tex, int ashift, int amask, float px, float py, float pz, const Dims d) {
+    const float mx = (float)d.X - 1.f, my = (float)d.Y - 1.f, mz = (float)d.Z - 1.f;
+    const float cx = fminf(fmaxf(0.f, px), mx), cy = fminf(fmaxf(0.f, py), my), cz = fminf(fmaxf(0.f, pz), mz);
+    const float fx = floorf(cx), fy = floorf(cy), fz = floorf(cz);
+    s.sx = (cx == 0.f || cx == mx);
+    s.sy = (cy == 0.f || cy == my);
+    s.a = __fsub_rn(cx, fx); s.b = __fsub_rn(cy, fy); s.c = __fsub_rn(cz, fz);
+    const float kxf = (float)(amask + 1), ikx = __int_as_float((127 - ashift) << 23);      // kx = 2^ashift and 1 / kx
+    const float u = fx + 1.f, v = fy + 1.f;                           // footprint (gx, gx+1) x (gy, gy+1)
+    const float z1 = (cz == 0.f || cz == mz) ? fz : fz + 1.f;
+    const float r0 = floorf(fz * ikx), r1 = floorf(z1 * ikx);         // atlas row of the slice; column = z - row * kx
+    s.lo = tex2Dgather<float4>(tex, __fmaf_rn(__fmaf_rn(-r0, kxf, fz), (float)d.X, u), __fmaf_rn(r0, (float)d.Y, v), 0);
+    s.hi = tex2Dgather<float4>(tex, __fmaf_rn(__fmaf_rn(-r1, kxf, z1), (float)d.X, u), __fmaf_rn(r1, (float)d.Y, v), 0);
+}
+SB_DEVI float tex_finish(const TexSample &s) {
+    const float v000 = s.lo.w, v100 = s.sx ? s.lo.w : s.lo.z;
+    const float v010 = s.sy ? v000 : s.lo.x, v110 = s.sy ? v100 : (s.sx ? s.lo.x : s.lo.y);
+    const float v001 = s.hi.w, v101 = s.sx ? s.hi.w : s.hi.z;
+    const float v011 = s.sy ? v001 : s.hi.x, v111 = s.sy ? v101 : (s.sx ? s.hi.x : s.hi.y);
+    return lerp(lerp(lerp(v111, v110, s.c), lerp(v101, v100, s.c), s.b), lerp(lerp(v011, v010, s.c), lerp(v001, v000, s.c), s.b), s.a);
+}
 SB_DEVI float warp_sample_tex(cudaTextureObject_t tex, int ashift, int amask, float px, float py, float pz, const Dims d) {
-    const TriCoord t = tri_coord(px, py, pz, d);
-    const float u = (float)t.gx + 1.f, v = (float)t.gy + 1.f;     // footprint (gx, gx+1) x (gy, gy+1)
-    const float u0 = u + (float)((t.gz & amask) * d.X), v0 = v + (float)((t.gz >> ashift) * d.Y);
-    const float u1 = u + (float)((t.z1 & amask) * d.X), v1 = v + (float)((t.z1 >> ashift) * d.Y);
-    const float4 lo = tex2Dgather<float4>(tex, u0, v0, 0);          // .w (i,j) .z (i+1,j) .x (i,j+1) .y (i+1,j+1)
-    const float4 hi = tex2Dgather<float4>(tex, u1, v1, 0);
-    const bool sx = t.x1 == t.gx, sy = t.y1 == t.gy;
-    const float v000 = lo.w, v100 = sx ? lo.w : lo.z;
-    const float v010 = sy ? v000 : lo.x, v110 = sy ? v100 : (sx ? lo.x : lo.y);
-    const float v001 = hi.w, v101 = sx ? hi.w : hi.z;
-    const float v011 = sy ? v001 : hi.x, v111 = sy ? v101 : (sx ? hi.x : hi.y);
-    return tri_lerp(v111, v110, v101, v100, v011, v010, v001, v000, t);
+    TexSample s;
+    tex_issue(s, tex, ashift, amask, px, py, pz, d);
+    return tex_finish(s);
 }
 
 // position of a CTA in its plane stream: work item -> tile origin and plane range [p, p_last]
@@ -111,7 +132,10 @@ constexpr int NSTAGE = 6;                         // planes q-3..q live, two in 
 constexpr int PF_AHEAD = 4;                       // L2 prefetch distance (planes) ahead of the shared-memory fill
 constexpr int COMP_BYTES = ((SX * SY * 4 + 127) / 128) * 128;
 constexpr int STAGE_BYTES = 3 * COMP_BYTES;
-constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 128;
+constexpr int NPSI = 3;                           // psi ring: centre plane of this step + the next two
+constexpr int PSI_COMP_BYTES = TX * TY * 4;       // one component of the tile, no halo
+constexpr int PSI_STAGE_BYTES = 3 * PSI_COMP_BYTES;
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + NPSI * PSI_STAGE_BYTES + 128;
 constexpr unsigned TX_BYTES = 3u * SX * SY * 4u;
 
 __global__ void __launch_bounds__((NW + 1) * 32, 1)
@@ -137,6 +161,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lx = lane % LX, ty = warp * RW + lane / LX;
     const unsigned own_off = (unsigned)(((ty + 3) * SX + 4 * lx + 4) * 4);
+    const unsigned psi0 = smem + NSTAGE * STAGE_BYTES, psi_own = (unsigned)((ty * TX + 4 * lx) * 4);
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NW); }
@@ -156,13 +181,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
             tma_prefetch_3d(&mapx, pf.x0t, pf.y0t, pf.p + 3);
             tma_prefetch_3d(&mapy, pf.x0t, pf.y0t, pf.p + 3);
             tma_prefetch_3d(&mapz, pf.x0t, pf.y0t, pf.p + 3);
-            // psi of plane r is read with plain LDGs when r is the centre, i.e. 3 planes after nabla_U(r) arrives; pull
-            // it into L2 a few steps before that.  The psi maps carry pass A's box (72 x 18): two boxes cover 24 rows.
+            // psi of plane r is needed when r is the centre, i.e. 3 planes after nabla_U(r) arrives; pull it into L2 a few
+            // steps before that (the psi maps carry the TX x TY tile without halo)
             const int r = pf.p - 3;
             if (r >= pf.zb) {
-                tma_prefetch_3d(&mpx, pf.x0t, pf.y0t, r + PSI_HALO); tma_prefetch_3d(&mpx, pf.x0t, pf.y0t + 12, r + PSI_HALO);
-                tma_prefetch_3d(&mpy, pf.x0t, pf.y0t, r + PSI_HALO); tma_prefetch_3d(&mpy, pf.x0t, pf.y0t + 12, r + PSI_HALO);
-                tma_prefetch_3d(&mpz, pf.x0t, pf.y0t, r + PSI_HALO); tma_prefetch_3d(&mpz, pf.x0t, pf.y0t + 12, r + PSI_HALO);
+                tma_prefetch_3d(&mpx, pf.x0t, pf.y0t, r + PSI_HALO);
+                tma_prefetch_3d(&mpy, pf.x0t, pf.y0t, r + PSI_HALO);
+                tma_prefetch_3d(&mpz, pf.x0t, pf.y0t, r + PSI_HALO);
             }
             pf.next(sc, d.Z);
         };
@@ -172,11 +197,20 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
             const unsigned slot = qi % NSTAGE, n = qi / NSTAGE;
             if (n > 0) mbar_wait(empty0 + 8 * slot, (n - 1) & 1u);   // every warp released the previous plane of this slot
             const unsigned dst = smem + slot * STAGE_BYTES, bar = full0 + 8 * slot;
-            mbar_expect_tx(bar, TX_BYTES);
+            // psi of the plane that becomes the centre with this nabla_U plane rides on the same barrier; its slot (qi % 3) was
+            // last read in the step whose end released this nabla_U slot, so the wait above covers it too
+            const bool with_psi = pr.p - 3 >= pr.zb;
+            mbar_expect_tx(bar, TX_BYTES + (with_psi ? 3u * PSI_COMP_BYTES : 0u));
             // padded coordinates: plane z sits at z + 3; the box origin (x0t, y0t) is interior (x0t - 4, y0t - 3)
             tma_load_3d(dst, &mapx, bar, pr.x0t, pr.y0t, pr.p + 3);
             tma_load_3d(dst + COMP_BYTES, &mapy, bar, pr.x0t, pr.y0t, pr.p + 3);
             tma_load_3d(dst + 2 * COMP_BYTES, &mapz, bar, pr.x0t, pr.y0t, pr.p + 3);
+            if (with_psi) {
+                const unsigned pd = psi0 + (qi % NPSI) * PSI_STAGE_BYTES;
+                tma_load_3d(pd, &mpx, bar, pr.x0t, pr.y0t, pr.p - 3 + PSI_HALO);
+                tma_load_3d(pd + PSI_COMP_BYTES, &mpy, bar, pr.x0t, pr.y0t, pr.p - 3 + PSI_HALO);
+                tma_load_3d(pd + 2 * PSI_COMP_BYTES, &mpz, bar, pr.x0t, pr.y0t, pr.p - 3 + PSI_HALO);
+            }
             pr.next(sc, d.Z);
         }
         return;
@@ -195,6 +229,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
         const int row = min(x0, X - 4) + X * min(y, d.Y - 1);
         for (int p = cs.p; p <= cs.p_last; ++p) {
             const unsigned slot = q % NSTAGE;
+            const int zc = p - 3;         // centre plane whose window is complete with plane p
+            const int o = row + XY * zc;
+            const unsigned pslot = psi0 + (q % NPSI) * PSI_STAGE_BYTES + psi_own;
             mbar_wait(full0 + 8 * slot, (q / NSTAGE) & 1u);
             ++q;
 #pragma unroll
@@ -205,13 +242,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
             const unsigned sp = smem + slot * STAGE_BYTES + own_off;
 #pragma unroll
             for (int c = 0; c < 3; ++c) win[6][c] = lds4(sp + c * COMP_BYTES);
-            const int zc = p - 3;         // centre plane whose window is now complete
             if (zc >= cs.zb) {
                 const unsigned sc0 = smem + ((q - 4u) % NSTAGE) * STAGE_BYTES + own_off;   // stage of the centre plane
-                const int o = row + XY * zc;
+                // psi of the centre plane arrived with this step's nabla_U plane (a plain LDG here exposed its latency: the
+                // register budget of 13 warps/SM leaves no room to issue it early)
                 float4 psi4[3];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) psi4[c] = *reinterpret_cast<const float4 *>(P[c] + o);
+                for (int c = 0; c < 3; ++c) psi4[c] = lds4(pslot + c * PSI_COMP_BYTES);
                 float np[3][4], nsq[4];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -273,15 +310,16 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
 // pass A
 // =============================================================================================================
 #ifndef PA_NW
-#define PA_NW 8
-#define PA_CTAS 2
+#define PA_NW 4         // warps per CTA
+#define PA_CTAS 4       // CTAs per SM
+#define PA_LX 8         // lanes per tile row (4 voxels each)
 #endif
 namespace pa {
-constexpr int LX = 16, RW = 32 / LX, NW = PA_NW;  // consumer warps (+ 1 producer warp)
-constexpr int NCONS = NW * 32;
-constexpr int TX = 4 * LX, TY = NW * RW;          // 64 x 16 outputs per plane
-constexpr int SX = TX + 8, SY = TY + 2;           // staged box 4|64|4 floats x 1|16|1 rows
-constexpr int NSTAGE = 4;                         // planes q-1, q live (z-1 is kept in registers), two in flight (+ L2 prefetch)
+constexpr int LX = PA_LX, RW = 32 / LX, NW = PA_NW;
+constexpr int NTHREADS = NW * 32;
+constexpr int TX = 4 * LX, TY = NW * RW;          // outputs per plane
+constexpr int SX = TX + 8, SY = TY + 2;           // staged box 4|TX|4 floats x 1|TY|1 rows
+constexpr int NSTAGE = 4;                         // planes p-2, p-1, p live, one in flight (+ L2 prefetch)
 constexpr int PF_AHEAD = 4;                       // L2 prefetch distance ahead of the shared-memory fill
 constexpr int ARR_BYTES = ((SX * SY * 4 + 127) / 128) * 128;
 constexpr int STAGE_BYTES = 3 * ARR_BYTES;        // psi x, y, z
@@ -289,14 +327,24 @@ constexpr int WBUF_BYTES = ARR_BYTES;             // one plane of warped TSDF (t
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 3 * WBUF_BYTES + 128;
 constexpr unsigned TX_BYTES = 3u * SX * SY * 4u;
 constexpr int NHALO = 2 * TX + 2 * TY;            // cross halo cells of a plane: rows y0-1, y0+TY and columns x0-1, x0+TX
+static_assert(NHALO <= NTHREADS, "one halo cell per thread");
 
 SB_DEVI void sts4(unsigned saddr, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 SB_DEVI void sts1(unsigned saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
 
+// One CTA = NW warps marching a TX x TY column along z, all in lockstep (one block barrier per plane).  There is no producer
+// warp: after the barrier of step q the stage of plane q-3 is free by construction, and thread 0 refills it with plane q+1
+// (no "empty" barriers; a CTA of whole consumer warps lets PA_CTAS CTAs/SM keep 128 registers per thread).
+// Step for plane p (centre zc = p-1):
+//   w_reg * laplacian of psi at zc (psi planes zc-1, zc, zc+1 are read from the ring)
+//   w(p) = phi_n o psi at this thread's quad and at its cross-halo cell -> shared (triple buffer) | barrier |
+//   central differences of w at zc, nabla_U -> global (+ replicated halo)
+// Tried and measured slower (profiles/r1_tuning_log.md): a producer warp (caps the CTA at 96 registers), all gathers of a
+// step in flight before the first use / across the stencil (more instructions + spills, same stall time), bigger CTAs.
 template <bool TEX>
-__global__ void __launch_bounds__((NW + 1) * 32, PA_CTAS)
+__global__ void __launch_bounds__(NTHREADS, PA_CTAS)
     pass_a_tma_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__ CUtensorMap m1,
                       const __grid_constant__ CUtensorMap m2, LoopArgs a, int it, Sched sc) {
     if (a.a_uses_max ? loop_finished(a, it) : (a.check && a.state->converged)) {
@@ -309,66 +357,53 @@ __global__ void __launch_bounds__((NW + 1) * 32, PA_CTAS)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned smem = (smem_u32(smem_raw) + 127u) & ~127u;
     const unsigned wbuf0 = smem + NSTAGE * STAGE_BYTES;
-    __shared__ unsigned long long bars[2 * NSTAGE];
-    const unsigned full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[NSTAGE]);
+    __shared__ unsigned long long bars[NSTAGE];
+    const unsigned full0 = smem_u32(&bars[0]);
 
     const Dims d = a.d, dg = a.dg;           // local slab extent / global volume
     const int X = d.X, XY = d.X * d.Y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NW); }
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(full0 + 8 * s, 1);
         mbar_fence_init();
     }
     __syncthreads();
 
     typedef Stream<TX, TY, 1, 1> St;
-    if (warp == NW) {
-        // ---- producer warp: one lane streams psi planes into the ring and prefetches further ahead into L2 ----
-        if (lane != 0) return;
-        St pr, pf;
-        pr.open(blockIdx.x, sc, d.Z);
-        pf.open(blockIdx.x, sc, d.Z);
-        auto prefetch = [&]() {
-            if (!pf.valid(sc)) return;
-            tma_prefetch_3d(&m0, pf.x0t - 4, pf.y0t - 1, pf.p + PSI_HALO);
-            tma_prefetch_3d(&m1, pf.x0t - 4, pf.y0t - 1, pf.p + PSI_HALO);
-            tma_prefetch_3d(&m2, pf.x0t - 4, pf.y0t - 1, pf.p + PSI_HALO);
-            pf.next(sc, d.Z);
-        };
-        for (int k = 0; k < PF_AHEAD; ++k) prefetch();
-        for (unsigned qi = 0; pr.valid(sc); ++qi) {
-            prefetch();
-            const unsigned slot = qi % NSTAGE, n = qi / NSTAGE;
-            if (n > 0) mbar_wait(empty0 + 8 * slot, (n - 1) & 1u);
-            const unsigned dst = smem + slot * STAGE_BYTES, bar = full0 + 8 * slot;
-            mbar_expect_tx(bar, TX_BYTES);
-            // the box starts 4 floats / 1 row before the tile (out-of-range elements arrive as zeros); the psi planes are
-            // allocated with PSI_HALO halo planes on either side, so local plane p is plane p + PSI_HALO of the tensor map
-            tma_load_3d(dst, &m0, bar, pr.x0t - 4, pr.y0t - 1, pr.p + PSI_HALO);
-            tma_load_3d(dst + ARR_BYTES, &m1, bar, pr.x0t - 4, pr.y0t - 1, pr.p + PSI_HALO);
-            tma_load_3d(dst + 2 * ARR_BYTES, &m2, bar, pr.x0t - 4, pr.y0t - 1, pr.p + PSI_HALO);
-            pr.next(sc, d.Z);
+    St pr;                                    // position of the feeder (thread 0) in the CTA's plane stream
+    unsigned qi = 0;
+    auto feed = [&]() {
+        if (!pr.valid(sc)) return;
+        const unsigned slot = qi % NSTAGE, dst = smem + slot * STAGE_BYTES, bar = full0 + 8 * slot;
+        mbar_expect_tx(bar, TX_BYTES);
+        // the box starts 4 floats / 1 row before the tile (out-of-range elements arrive as zeros); the psi planes are
+        // allocated with PSI_HALO halo planes on either side, so local plane p is plane p + PSI_HALO of the tensor map
+        tma_load_3d(dst, &m0, bar, pr.x0t - 4, pr.y0t - 1, pr.p + PSI_HALO);
+        tma_load_3d(dst + ARR_BYTES, &m1, bar, pr.x0t - 4, pr.y0t - 1, pr.p + PSI_HALO);
+        tma_load_3d(dst + 2 * ARR_BYTES, &m2, bar, pr.x0t - 4, pr.y0t - 1, pr.p + PSI_HALO);
+        if (pr.p + PF_AHEAD <= pr.p_last) {         // L2 prefetch further down the same column
+            tma_prefetch_3d(&m0, pr.x0t - 4, pr.y0t - 1, pr.p + PF_AHEAD + PSI_HALO);
+            tma_prefetch_3d(&m1, pr.x0t - 4, pr.y0t - 1, pr.p + PF_AHEAD + PSI_HALO);
+            tma_prefetch_3d(&m2, pr.x0t - 4, pr.y0t - 1, pr.p + PF_AHEAD + PSI_HALO);
         }
-        return;
+        ++qi;
+        pr.next(sc, d.Z);
+    };
+    if (tid == 0) {
+        pr.open(blockIdx.x, sc, d.Z);
+        feed();
     }
 
-    // ---- consumers ----
     const int lx = lane % LX, ty = warp * RW + lane / LX;
     const unsigned own_off = (unsigned)(((ty + 1) * SX + 4 * lx + 4) * 4);
-    // cross-halo cells served by this thread (cells tid, tid + NCONS, ... < NHALO): position inside the staged box
-    constexpr int HPT = (NHALO + NCONS - 1) / NCONS;
-    int hxs[HPT], hys[HPT];
-#pragma unroll
-    for (int k = 0; k < HPT; ++k) {
-        const int h = tid + k * NCONS;
-        int hx = -1, hy = -1;                  // box coordinates (floats / rows)
-        if (h < TX) { hx = 4 + h; hy = 0; }
-        else if (h < 2 * TX) { hx = 4 + h - TX; hy = TY + 1; }
-        else if (h < 2 * TX + TY) { hx = 3; hy = 1 + h - 2 * TX; }
-        else if (h < NHALO) { hx = 4 + TX; hy = 1 + h - 2 * TX - TY; }
-        hxs[k] = hx; hys[k] = hy;
-    }
+    // cross-halo cell served by this thread (threads 0 .. NHALO-1): position inside the staged box
+    int hx = -1, hy = -1;
+    if (tid < TX) { hx = 4 + tid; hy = 0; }
+    else if (tid < 2 * TX) { hx = 4 + tid - TX; hy = TY + 1; }
+    else if (tid < 2 * TX + TY) { hx = 3; hy = 1 + tid - 2 * TX; }
+    else if (tid < NHALO) { hx = 4 + TX; hy = 1 + tid - 2 * TX - TY; }
+    const unsigned halo_off = (unsigned)((hy * SX + hx) * 4);
     float *__restrict__ G[3] = {a.gx, a.gy, a.gz};
     const float *__restrict__ pn = a.pn;
     const GLayout gl = a.gl;
@@ -379,34 +414,63 @@ __global__ void __launch_bounds__((NW + 1) * 32, PA_CTAS)
         const bool active = x0 < X && y < d.Y;
         const int row = min(x0, X - 4) + X * min(y, d.Y - 1);
         const bool y_lo = (y == 0), y_hi = (y == d.Y - 1), by = y_lo || y_hi;
-        bool halo_on[HPT];
-#pragma unroll
-        for (int k = 0; k < HPT; ++k) {
-            const int hgx = cs.x0t - 4 + hxs[k], hgy = cs.y0t - 1 + hys[k];       // volume coordinates of the halo cell
-            halo_on[k] = hxs[k] >= 0 && hgx >= 0 && hgx < X && hgy >= 0 && hgy < d.Y;
-        }
-        // this thread's quads at planes z-1 and z: psi (3 components) and the warped TSDF
-        float4 zm[3], zc4[3], wm, wc;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) zm[k] = zc4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        wm = wc = make_float4(0.f, 0.f, 0.f, 0.f);
+        // only the first / last voxel of a row can sit on an x face (X % 4 == 0)
+        const bool x_lo = (x0 == 0), x_hi = (x0 + 4 == X);
+        const int hgx = cs.x0t - 4 + hx, hgy = cs.y0t - 1 + hy;       // volume coordinates of the halo cell
+        const bool halo_on = hx >= 0 && hgx >= 0 && hgx < X && hgy >= 0 && hgy < d.Y;
+        float4 wm = make_float4(0.f, 0.f, 0.f, 0.f), wc = wm;        // this thread's quad of w at planes z-1 and z
         for (int p = cs.p; p <= cs.p_last; ++p) {
             const unsigned slot = q % NSTAGE;
             const int zc = p - 1;             // plane that becomes the centre when plane p has arrived
+            const bool centre_on = zc >= cs.zb;
             float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (zc >= cs.zb) g4 = *reinterpret_cast<const float4 *>(a.pg + row + XY * zc);
+            if (centre_on) g4 = *reinterpret_cast<const float4 *>(a.pg + row + XY * zc);
             mbar_wait(full0 + 8 * slot, (q / NSTAGE) & 1u);
             const unsigned wcur = wbuf0 + (q % 3u) * WBUF_BYTES;             // warped plane p   (written now)
-            const unsigned wctr = wbuf0 + ((q + 2u) % 3u) * WBUF_BYTES;      // warped plane p-1 (written last iteration)
+            const unsigned wctr = wbuf0 + ((q + 2u) % 3u) * WBUF_BYTES;      // warped plane p-1 (written in the last step)
             ++q;
             const unsigned stP = smem + slot * STAGE_BYTES;                                  // plane p   (z+1)
             const unsigned sC = smem + ((q + NSTAGE - 2u) % NSTAGE) * STAGE_BYTES + own_off; // plane p-1 (centre)
+            const unsigned sM = smem + ((q + NSTAGE - 3u) % NSTAGE) * STAGE_BYTES + own_off; // plane p-2 (z-1)
             float4 zp[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) zp[k] = lds4(stP + own_off + k * ARR_BYTES);
-            // ---- phase 1: warp plane p (own quad + one cross-halo cell); planes outside the volume are never used ----
+            const bool plane_on = (a.z0 + p >= 0 && a.z0 + p < dg.Z);        // planes outside the volume are never used
+            const bool z_lo = (a.z0 + zc == 0), z_hi = (a.z0 + zc == dg.Z - 1), bz = z_lo || z_hi;   // global faces only
+            const bool edge = by || bz;       // y / z faces are rare: their selects live in a branch interior threads skip
+
+            // ---- w_reg * laplacian(psi) at the centre plane (vector_fields.cu:291-337); on a boundary plane both neighbours
+            //      of that axis are the voxel itself ----
+            float Lw[3][4];
+            if (centre_on) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const unsigned p0 = sC + c * ARR_BYTES;
+                    const float4 C = lds4(p0);
+                    float4 Ym = lds4(p0 - SX * 4), Yp = lds4(p0 + SX * 4), Zp = zp[c], Zm = lds4(sM + c * ARR_BYTES);
+                    const float xl = lds1(p0 - 4), xr = lds1(p0 + 16);
+                    const float xm[4] = {x_lo ? C.x : xl, C.x, C.y, x_hi ? C.w : C.z}, xp[4] = {x_lo ? C.x : C.y, C.z, C.w, x_hi ? C.w : xr};
+                    if (edge) {
+                        if (by) Yp = Ym = C;
+                        if (bz) Zp = Zm = C;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float v = mul(c4(C, j), -6.f);
+                        v = add(v, xp[j]);
+                        v = add(v, xm[j]);
+                        v = add(v, c4(Yp, j));
+                        v = add(v, c4(Ym, j));
+                        v = add(v, c4(Zp, j));
+                        v = add(v, c4(Zm, j));
+                        Lw[c][j] = mul(mul(v, -1.f), a.w_reg);
+                    }
+                }
+            }
+
+            // ---- warp of plane p: own quad + this thread's cross-halo cell ----
             float4 wp = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.z0 + p >= 0 && a.z0 + p < dg.Z) {
+            if (plane_on) {
                 if (active) {
                     if (TEX) {
                         wp.x = warp_sample_tex(a.pn_tex, a.ashift, a.amask, zp[0].x, zp[1].x, zp[2].x, dg);
@@ -420,61 +484,48 @@ __global__ void __launch_bounds__((NW + 1) * 32, PA_CTAS)
                         wp.w = warp_sample(pn, zp[0].w, zp[1].w, zp[2].w, dg, X, XY);
                     }
                 }
+                if (halo_on) {
+                    const float hxv = lds1(stP + halo_off), hyv = lds1(stP + halo_off + ARR_BYTES), hzv = lds1(stP + halo_off + 2 * ARR_BYTES);
+                    sts1(wcur + halo_off, TEX ? warp_sample_tex(a.pn_tex, a.ashift, a.amask, hxv, hyv, hzv, dg) : warp_sample(pn, hxv, hyv, hzv, dg, X, XY));
+                }
                 sts4(wcur + own_off, wp);
-#pragma unroll
-                for (int k = 0; k < HPT; ++k)
-                    if (halo_on[k]) {
-                        const unsigned halo_off = (unsigned)((hys[k] * SX + hxs[k]) * 4);
-                        const float hxv = lds1(stP + halo_off), hyv = lds1(stP + halo_off + ARR_BYTES), hzv = lds1(stP + halo_off + 2 * ARR_BYTES);
-                        sts1(wcur + halo_off, TEX ? warp_sample_tex(a.pn_tex, a.ashift, a.amask, hxv, hyv, hzv, dg) : warp_sample(pn, hxv, hyv, hzv, dg, X, XY));
-                    }
             }
-            asm volatile("bar.sync 1, %0;" ::"r"(NCONS) : "memory");     // warped plane p (and p-1) visible to all consumers
-            // ---- phase 2: nabla_U of the centre plane ----
-            if (zc >= cs.zb) {
-                const bool z_lo = (a.z0 + zc == 0), z_hi = (a.z0 + zc == dg.Z - 1), bz = z_lo || z_hi;   // global faces only
-                // central differences of the warped TSDF; both taps on the in-range neighbour at a boundary (-> +0)
+            __syncthreads();                  // warped plane p (and p-1) visible to the CTA; ring stage of plane p-3 is free
+            if (tid == 0) feed();
+
+            // ---- nabla_U of the centre plane ----
+            if (centre_on) {
+                // central differences of the warped TSDF (vector_fields.cu:157-208); both taps on the in-range neighbour at a
+                // boundary (-> +0)
                 float nx[4], ny[4], nz[4], df[4];
                 {
                     const unsigned w0 = wctr + own_off;
                     const float4 C = wc, Ym = lds4(w0 - SX * 4), Yp = lds4(w0 + SX * 4);
                     const float xl = lds1(w0 - 4), xr = lds1(w0 + 16);
-                    const float xm[4] = {xl, C.x, C.y, C.z}, xp[4] = {C.y, C.z, C.w, xr};
+                    const float xm[4] = {x_lo ? C.y : xl, C.x, C.y, C.z}, xp[4] = {C.y, C.z, C.w, x_hi ? C.z : xr};
+                    float4 Y1 = Yp, Y2 = Ym, Z1 = wp, Z2 = wm;
+                    if (edge) {
+                        if (y_hi) Y1 = Ym;
+                        if (y_lo) Y2 = Yp;
+                        if (z_hi) Z1 = wm;
+                        if (z_lo) Z2 = wp;
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const bool x_lo = (x0 + j == 0), x_hi = (x0 + j == X - 1);
-                        const float a1 = x_hi ? xm[j] : xp[j], a2 = x_lo ? xp[j] : xm[j];
-                        const float b1 = y_hi ? c4(Ym, j) : c4(Yp, j), b2 = y_lo ? c4(Yp, j) : c4(Ym, j);
-                        const float c1 = z_hi ? c4(wm, j) : c4(wp, j), c2 = z_lo ? c4(wp, j) : c4(wm, j);
-                        nx[j] = mul(sub(a1, a2), 0.5f);      // __fdividef(., 2.f)
-                        ny[j] = mul(sub(b1, b2), 0.5f);
-                        nz[j] = mul(sub(c1, c2), 0.5f);
+                        nx[j] = mul(sub(xp[j], xm[j]), 0.5f);      // __fdividef(., 2.f)
+                        ny[j] = mul(sub(c4(Y1, j), c4(Y2, j)), 0.5f);
+                        nz[j] = mul(sub(c4(Z1, j), c4(Z2, j)), 0.5f);
                         df[j] = sub(c4(C, j), c4(g4, j));
                     }
                 }
                 const size_t o = gl.at(min(x0, X - 4), min(y, d.Y - 1), zc);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const unsigned p0 = sC + c * ARR_BYTES;
-                    const float4 C = zc4[c], Ym = lds4(p0 - SX * 4), Yp = lds4(p0 + SX * 4);
-                    const float xl = lds1(p0 - 4), xr = lds1(p0 + 16);
-                    const float xm[4] = {xl, C.x, C.y, C.z}, xp[4] = {C.y, C.z, C.w, xr};
                     float u[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const bool bx = (x0 + j == 0) || (x0 + j == X - 1);
-                        const float ctr = c4(C, j);
-                        // laplacian: on a boundary plane both neighbours are the voxel itself (vector_fields.cu:299-331)
-                        float v = mul(ctr, -6.f);
-                        v = add(v, bx ? ctr : xp[j]);
-                        v = add(v, bx ? ctr : xm[j]);
-                        v = add(v, by ? ctr : c4(Yp, j));
-                        v = add(v, by ? ctr : c4(Ym, j));
-                        v = add(v, bz ? ctr : c4(zp[c], j));
-                        v = add(v, bz ? ctr : c4(zm[c], j));
-                        const float Lv = mul(v, -1.f);
                         const float n = (c == 0) ? nx[j] : (c == 1 ? ny[j] : nz[j]);
-                        u[j] = add(mul(n, df[j]), mul(Lv, a.w_reg));
+                        u[j] = add(mul(n, df[j]), Lw[c][j]);       // solver.cu:15-33
                     }
                     if (active) {
                         float *__restrict__ g = G[c];
@@ -502,12 +553,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, PA_CTAS)
                     }
                 }
             }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { zm[k] = zc4[k]; zc4[k] = zp[k]; }
             wm = wc; wc = wp;
-            // the stage of plane p-1 (the centre just used; its quads now live in registers) can be refilled
-            __syncwarp();
-            if (lane == 0 && q >= 2u) mbar_arrive(empty0 + 8 * ((q - 2u) % NSTAGE));
         }
     }
 }
@@ -569,6 +615,7 @@ TmaMaps *tma_maps_create(const LoopArgs &a) {
     bool ok = true;
     for (int c = 0; c < 3; ++c) ok = ok && encode_map_3d(&m->g[c], g[c], a.gl.PX, a.gl.PY, a.gl.PZ, pb::SX, pb::SY);
     for (int c = 0; c < 3; ++c) ok = ok && encode_map_3d(&m->in[c], in[c], a.d.X, a.d.Y, a.d.Z + 2 * PSI_HALO, pa::SX, pa::SY);
+    for (int c = 0; c < 3; ++c) ok = ok && encode_map_3d(&m->pb_psi[c], in[c], a.d.X, a.d.Y, a.d.Z + 2 * PSI_HALO, pb::TX, pb::TY);
     ok = ok && cudaFuncSetAttribute(pb::pass_b_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pb::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
@@ -588,7 +635,7 @@ void launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, const ZRange
     const Sched sc = make_sched(a.d, zr, pb::TX, pb::TY, 6, 0.35, ctas);
     if (sc.nitems == 0) return;
     const int grid = sc.nitems < ctas ? sc.nitems : ctas;
-    pb::pass_b_tma_kernel<<<grid, (pb::NW + 1) * 32, pb::SMEM_BYTES, st>>>(m->g[0], m->g[1], m->g[2], m->in[0], m->in[1], m->in[2], a, it, sc);
+    pb::pass_b_tma_kernel<<<grid, (pb::NW + 1) * 32, pb::SMEM_BYTES, st>>>(m->g[0], m->g[1], m->g[2], m->pb_psi[0], m->pb_psi[1], m->pb_psi[2], a, it, sc);
 }
 
 void launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, const ZRanges &zr, cudaStream_t st) {
@@ -601,8 +648,8 @@ void launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, con
     const Sched sc = make_sched(a.d, zr, pa::TX, pa::TY, 2, 0.5, ctas);
     if (sc.nitems == 0) return;
     const int grid = sc.nitems < ctas ? sc.nitems : ctas;
-    if (a.pn_tex) pa::pass_a_tma_kernel<true><<<grid, (pa::NW + 1) * 32, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
-    else pa::pass_a_tma_kernel<false><<<grid, (pa::NW + 1) * 32, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
+    if (a.pn_tex) pa::pass_a_tma_kernel<true><<<grid, pa::NTHREADS, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
+    else pa::pass_a_tma_kernel<false><<<grid, pa::NTHREADS, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
 }
 
 }  // namespace sb
