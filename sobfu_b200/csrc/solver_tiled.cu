@@ -195,7 +195,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
         for (unsigned qi = 0; pr.valid(sc); ++qi) {
             prefetch();
             const unsigned slot = qi % NSTAGE, n = qi / NSTAGE;
-            if (n > 0) mbar_wait(empty0 + 8 * slot, (n - 1) & 1u);   // every warp released the previous plane of this slot
+            // every warp released the previous plane of this slot; polling with a 128 ns back-off leaves the issue slots of this
+            // scheduler to its three consumer warps (-2 % kernel time)
+            if (n > 0) mbar_wait_backoff(empty0 + 8 * slot, (n - 1) & 1u, 128u);
             const unsigned dst = smem + slot * STAGE_BYTES, bar = full0 + 8 * slot;
             // psi of the plane that becomes the centre with this nabla_U plane rides on the same barrier; its slot (qi % 3) was
             // last read in the step whose end released this nabla_U slot, so the wait above covers it too
@@ -319,7 +321,8 @@ constexpr int LX = PA_LX, RW = 32 / LX, NW = PA_NW;
 constexpr int NTHREADS = NW * 32;
 constexpr int TX = 4 * LX, TY = NW * RW;          // outputs per plane
 constexpr int SX = TX + 8, SY = TY + 2;           // staged box 4|TX|4 floats x 1|TY|1 rows
-constexpr int NSTAGE = 4;                         // planes p-2, p-1, p live, one in flight (+ L2 prefetch)
+constexpr int AHEAD = 1;                          // planes in flight ahead of the one being consumed (2 measured slower)
+constexpr int NSTAGE = 3 + AHEAD;                 // planes p-2, p-1, p live + AHEAD in flight (+ L2 prefetch)
 constexpr int PF_AHEAD = 4;                       // L2 prefetch distance ahead of the shared-memory fill
 constexpr int ARR_BYTES = ((SX * SY * 4 + 127) / 128) * 128;
 constexpr int STAGE_BYTES = 3 * ARR_BYTES;        // psi x, y, z
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
     };
     if (tid == 0) {
         pr.open(blockIdx.x, sc, d.Z);
-        feed();
+        for (int k = 0; k < AHEAD; ++k) feed();
     }
 
     const int lx = lane % LX, ty = warp * RW + lane / LX;

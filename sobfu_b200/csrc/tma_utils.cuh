@@ -29,6 +29,22 @@ SB_DEVI void mbar_wait(unsigned bar, unsigned parity) {
         "r"(parity)
         : "memory");
 }
+// same, sleeping `ns` nanoseconds between polls: for a producer lane whose polling would otherwise take issue slots from the
+// consumer warps of its scheduler
+SB_DEVI void mbar_wait_backoff(unsigned bar, unsigned parity, unsigned ns) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "nanosleep.u32 %2;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity), "r"(ns)
+        : "memory");
+}
 // cp.async.bulk.tensor.3d global -> shared, completion signalled on an mbarrier (SASS: UTMALDG.3D)
 SB_DEVI void tma_load_3d(unsigned dst, const CUtensorMap *map, unsigned bar, int c0, int c1, int c2) {
     asm volatile(
