@@ -155,9 +155,21 @@ int sobfu_b200_comm_unique_id(void *id128_host);
 int sobfu_b200_slab_range(int Z, int rank, int nranks, int *z0, int *nz);
 /* switches the solver (created for the GLOBAL dims) to slab mode: afterwards estimate_psi takes the rank's slab of
  * phi_global, phi_global_psi_inv, phi_n_psi, psi, psi_inv and the WHOLE phi_n (replicated: every rank integrates the
- * depth frame itself).  Per iteration: nabla_U halo (3 planes) and psi halo (1 plane) exchanges with both neighbours
- * and a scalar MAX all-reduce over NCCL; per frame: one all-gather of psi and phi_global for psi^-1 / phi_global o psi^-1. */
+ * depth frame itself).  Per iteration: ONE psi halo exchange (4 planes; nabla_U on the halo planes is recomputed) with both
+ * neighbours and a scalar MAX all-reduce over NCCL; per frame: one all-gather of psi and phi_global for psi^-1 /
+ * phi_global o psi^-1. */
 int sobfu_b200_solver_attach_comm(sobfu_b200_solver *s, const void *id128_host, int rank, int nranks);
+
+/* Peer mode (ranks on one NVLink / NVSwitch domain, e.g. the 8 GPUs of a B200 node): the per-iteration psi halo exchange
+ * and the convergence test leave NCCL.  Pass B on the slab faces stores its new psi planes straight into the neighbours'
+ * halo planes over NVLink (CUDA IPC mappings) and signals through counters in the neighbours' memory; every rank publishes
+ * its per-iteration maximum into every rank's table.  An iteration is then four kernels on one stream.
+ *   every rank: peer_export(block);  launcher: all-gather the blocks (rank-major);  every rank: peer_attach(all blocks).
+ * Optional: without it (or with SOBFU_B200_NO_PEER set, or when attach fails) the solver keeps exchanging over NCCL.
+ * Results are bit-identical in both modes.  Replaces nothing in the reference (single GPU, solver.cu:85-205). */
+#define SOBFU_B200_PEER_HANDLE_BYTES 128
+int sobfu_b200_solver_peer_export(sobfu_b200_solver *s, void *handle_block_host);
+int sobfu_b200_solver_peer_attach(sobfu_b200_solver *s, const void *all_handle_blocks_host);   /* NULL: detach */
 
 #ifdef __cplusplus
 }

@@ -64,6 +64,8 @@ SIGNATURES = {
     "sobfu_b200_marching_cubes": [_P, _I, _I, _I, _FP, _FP, _FP, _P, _P, _I, _IP, _P, _P, _P, _I, _IP],
     "sobfu_b200_comm_unique_id": [_P],
     "sobfu_b200_solver_attach_comm": [_P, _P, _I, _I],
+    "sobfu_b200_solver_peer_export": [_P, _P],
+    "sobfu_b200_solver_peer_attach": [_P, _P],
     "sobfu_b200_slab_range": [_I, _I, _I, _IP, _IP],
 }
 OTHER_SYMBOLS = ["sobfu_b200_last_error", "sobfu_b200_version", "sobfu_b200_solver_workspace_bytes"]

@@ -14,7 +14,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "nccl_dyn.h"
@@ -182,6 +184,16 @@ struct sobfu_b200_solver {
     // overlapped slab mode: halo exchanges run on their own stream while the planes away from the slab faces are computed
     cudaStream_t comm_stream = nullptr, max_stream = nullptr;
     cudaEvent_t ev_b = nullptr, ev_bm = nullptr, ev_p = nullptr, ev_m = nullptr;
+    // peer mode: neighbours' psi planes and every rank's control block mapped through CUDA IPC (see LoopArgs)
+    bool peer_on = false;
+    unsigned char *ctl = nullptr;                 // own control blocks: 2 epochs x (PeerCtl + allmax[max_iter * nranks])
+    size_t ctl_bytes = 0;                         // bytes of ONE epoch
+    void *peer_psi[2] = {nullptr, nullptr};       // psi_alloc of rank-1 / rank+1
+    void *peer_ctl[MAX_PEERS] = {};               // ctl of every rank (own entry: s->ctl)
+    int epoch = 0;                                // parity of the control block in use (flips every estimate_psi)
+    unsigned long long pushed = 0;                // CTAs of this rank's face launches of pass B so far in this epoch
+    unsigned long long push_grid = 0;             // CTAs of one such launch
+    unsigned long long acked = 0, ack_grid = 0;   // the same for the face launches of pass A (halo planes read)
     bool psi_exchange_pending = false;   // ev_p has been recorded and not yet waited for by the compute stream
     bool max_pending = false;            // ev_m (global maximum of the previous iteration) likewise
     int variant = 0;
@@ -218,6 +230,10 @@ static void fill_args(sobfu_b200_solver *s) {
     a.check = 1;
     a.a_uses_max = 1;
     a.pn_tex = s->pn_tex; a.pn_surf = s->pn_surf; a.ashift = s->ashift; a.amask = s->amask;
+    for (int c = 0; c < 3; ++c) a.peer_lo[c] = a.peer_hi[c] = nullptr;
+    a.cnt_lo = a.cnt_hi = nullptr; a.my_cnt = nullptr; a.expect_lo = a.expect_hi = 0ull;
+    a.ack_lo = a.ack_hi = nullptr; a.my_ack = nullptr; a.expect_ack = 0ull;
+    a.allmax = nullptr; a.peer_error = nullptr; a.peer_n = 0; a.push = 0; a.wait_halo = 0;
 }
 
 // phi_n.x as a 2-D atlas of Z slices (kx = 2^ashift per row) in a CUDA array that supports texture gather
@@ -298,8 +314,39 @@ static int alloc_workspace(sobfu_b200_solver *s, int z0, int nzl) {
     return 0;
 }
 
+// unmap the neighbours' buffers (local operation)
+static void peer_unmap(sobfu_b200_solver *s) {
+    for (int k = 0; k < 2; ++k) if (s->peer_psi[k]) { cudaIpcCloseMemHandle(s->peer_psi[k]); s->peer_psi[k] = nullptr; }
+    for (int r = 0; r < MAX_PEERS; ++r) {
+        if (s->peer_ctl[r] && r != s->rank) cudaIpcCloseMemHandle(s->peer_ctl[r]);
+        s->peer_ctl[r] = nullptr;
+    }
+    s->peer_on = false;
+    cudaGetLastError();
+}
+// Before a rank frees buffers it exported, every rank must have unmapped them: a barrier over the solver's communicator,
+// bounded to 5 s on the host (ranks destroy their solvers at the same program point; if one does not, the exported buffers
+// are leaked rather than freed under a peer's mapping).  Returns false when the barrier did not complete.
+static bool peer_release_barrier(sobfu_b200_solver *s) {
+    if (!s->comm || !nccl_api().ok) return false;
+    if (nccl_api().AllReduce(s->maxkey, s->maxkey, 1, ncclUint64, ncclMax, s->comm, s->stream) != ncclSuccess) return false;
+    const auto t0 = std::chrono::steady_clock::now();
+    while (cudaStreamQuery(s->stream) == cudaErrorNotReady) {
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5)) return false;
+        std::this_thread::yield();
+    }
+    cudaGetLastError();
+    return true;
+}
+
 extern "C" int sobfu_b200_solver_destroy(sobfu_b200_solver *s) {
     if (!s) return 0;
+    if (s->peer_on) {
+        cudaStreamSynchronize(s->stream);
+        peer_unmap(s);
+        if (!peer_release_barrier(s)) { s->psi_alloc = nullptr; s->ctl = nullptr; }   // leak instead of freeing mapped memory
+    }
+    cudaFree(s->ctl);
     free_workspace(s);
     if (s->comm_max && nccl_api().ok) nccl_api().CommDestroy(s->comm_max);
     if (s->comm && nccl_api().ok) nccl_api().CommDestroy(s->comm);
@@ -409,6 +456,66 @@ extern "C" int sobfu_b200_solver_attach_comm(sobfu_b200_solver *s, const void *i
     return alloc_workspace(s, z0, nz);
 }
 
+// ---- peer mode: halo exchange and convergence test over NVLink peer memory instead of NCCL (same node, CUDA IPC) ----
+// handle block of one rank = {cudaIpcMemHandle_t of the psi planes, cudaIpcMemHandle_t of the control block}
+static_assert(2 * sizeof(cudaIpcMemHandle_t) == SOBFU_B200_PEER_HANDLE_BYTES, "peer handle block size");
+extern "C" int sobfu_b200_solver_peer_export(sobfu_b200_solver *s, void *handle_block) {
+    if (!s || !handle_block) return fail(SOBFU_B200_EINVAL, "null argument");
+    if (s->nranks < 2 || !s->comm) return fail(SOBFU_B200_EINVAL, "peer mode needs an attached communicator (attach_comm first)");
+    if (s->nranks > MAX_PEERS) return fail(SOBFU_B200_EINVAL, "peer mode supports up to %d ranks", MAX_PEERS);
+    const int mi = s->p.max_iter > 0 ? s->p.max_iter : 1;
+    if (!s->ctl) {
+        s->ctl_bytes = ((sizeof(PeerCtl) + (size_t)mi * s->nranks * sizeof(unsigned long long)) + 255) / 256 * 256;
+        CK(cudaMalloc(&s->ctl, 2 * s->ctl_bytes));
+        CK(cudaMemset(s->ctl, 0, 2 * s->ctl_bytes));
+    }
+    cudaIpcMemHandle_t h[2];
+    CK(cudaIpcGetMemHandle(&h[0], s->psi_alloc));
+    CK(cudaIpcGetMemHandle(&h[1], s->ctl));
+    memcpy(handle_block, h, sizeof h);
+    return 0;
+}
+extern "C" int sobfu_b200_solver_peer_attach(sobfu_b200_solver *s, const void *all_handle_blocks) {
+    if (!s) return fail(SOBFU_B200_EINVAL, "null argument");
+    if (!all_handle_blocks) { peer_unmap(s); return 0; }      // detach: back to the NCCL exchange
+    if (!s->ctl) return fail(SOBFU_B200_EINVAL, "peer_export has to be called first");
+    const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *)all_handle_blocks;
+    auto open = [&](void **dst, const cudaIpcMemHandle_t &hd) {
+        cudaError_t e = cudaIpcOpenMemHandle(dst, hd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { *dst = nullptr; cudaGetLastError(); }
+        return e;
+    };
+    cudaError_t e = cudaSuccess;
+    for (int r = 0; r < s->nranks && e == cudaSuccess; ++r) {
+        if (r == s->rank) { s->peer_ctl[r] = s->ctl; continue; }
+        e = open(&s->peer_ctl[r], h[2 * r + 1]);
+        if (e == cudaSuccess && (r == s->rank - 1 || r == s->rank + 1)) e = open(&s->peer_psi[r < s->rank ? 0 : 1], h[2 * r]);
+    }
+    if (e != cudaSuccess) {
+        peer_unmap(s);
+        return fail(SOBFU_B200_ECOMM, "cudaIpcOpenMemHandle: %s (the ranks stay on the NCCL exchange)", cudaGetErrorString(e));
+    }
+    s->peer_on = true;
+    return 0;
+}
+
+// every rank writes its maximum of iteration `it` into slot [it][rank] of every rank's table (bit 63 marks it valid)
+struct PeerTables { unsigned long long *t[MAX_PEERS]; };
+__global__ void publish_max_kernel(const unsigned long long *maxkey_it, PeerTables tabs, size_t slot, int nranks) {
+    const int r = threadIdx.x;
+    if (r < nranks) {
+        const unsigned long long v = *maxkey_it | PEER_VALID;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(tabs.t[r] + slot), "l"(v) : "memory");
+    }
+}
+// waits until the neighbours' stores into this rank's halo planes have landed (end of a loop)
+__global__ void peer_wait_kernel(const LoopState *state, const unsigned long long *cnt, unsigned long long expect_lo,
+                                 unsigned long long expect_hi, unsigned long long *err) {
+    if (state->converged) return;   // the iterations enqueued after the converged one returned early on every rank: no stores to wait for
+    if (expect_lo) peer_wait_ge(cnt + 0, expect_lo, err);
+    if (expect_hi) peer_wait_ge(cnt + 1, expect_hi, err);
+}
+
 #define CKN(expr)                                                                                   \
     do {                                                                                            \
         ncclResult_t r__ = (expr);                                                                  \
@@ -494,11 +601,94 @@ static int join_max(sobfu_b200_solver *s) {
     }
     return 0;
 }
+// peer mode is used for a whole solve or not at all: tiled kernels, enough planes for the face / middle split and no logging
+// iterations (those run the generic kernels with the serial NCCL exchange)
+static bool peer_mode(const sobfu_b200_solver *s) {
+    static const bool off = getenv("SOBFU_B200_NO_PEER") != nullptr;
+    return s->peer_on && !off && s->nranks > 1 && use_tiled(s) && s->d.Z >= 12 && s->p.verbosity == 0;
+}
+// a new epoch of the control blocks: this solve uses the block the PREVIOUS solve cleared (nobody has written to it since:
+// every rank passed the all-gather that ends a solve before any rank started the next one) and clears the other one
+static int peer_begin(sobfu_b200_solver *s, cudaStream_t st) {
+    if (!peer_mode(s)) return 0;
+    s->epoch ^= 1;
+    s->pushed = s->acked = 0;
+    CK(cudaMemsetAsync(s->ctl + (size_t)(s->epoch ^ 1) * s->ctl_bytes, 0, s->ctl_bytes, st));
+    return 0;
+}
+// end of a loop: the neighbours' last stores into this rank's halo planes have landed; a timed-out wait becomes an error
+static int peer_end(sobfu_b200_solver *s, cudaStream_t st) {
+    if (!peer_mode(s)) return 0;
+    PeerCtl *mine = (PeerCtl *)(s->ctl + (size_t)s->epoch * s->ctl_bytes);
+    peer_wait_kernel<<<1, 1, 0, st>>>(s->state, mine->halo_cnt, s->rank > 0 ? s->pushed : 0ull, s->rank < s->nranks - 1 ? s->pushed : 0ull, &mine->error);
+    return 0;
+}
+static int peer_check_error(sobfu_b200_solver *s) {   // stream already synchronised
+    if (!peer_mode(s)) return 0;
+    unsigned long long err = 0;
+    CK(cudaMemcpy(&err, &((PeerCtl *)(s->ctl + (size_t)s->epoch * s->ctl_bytes))->error, sizeof err, cudaMemcpyDeviceToHost));
+    if (err) return fail(SOBFU_B200_ECOMM, "peer mode: a wait on a neighbour's halo stores / maxima timed out (rank %d)", s->rank);
+    return 0;
+}
 // one gradient-descent iteration
 static int launch_iteration(sobfu_b200_solver *s, int it, int log, int *launches) {
     int rc = 0;
     const int n = s->d.Z;
     static const bool no_overlap = getenv("SOBFU_B200_NO_OVERLAP") != nullptr;
+    if (peer_mode(s)) {
+        // Peer mode: the same split, ONE stream, no NCCL and no events inside the loop.  Pass B on the faces stores the new psi
+        // planes into the neighbours' halo planes itself and counts its CTAs there; pass A on the faces waits for the
+        // neighbours' counts of the previous iteration; every rank publishes its maximum to every rank and pass B reads all.
+        //   A_mid [1,n-1) | A_edge (waits halo counters) | B_edge (waits maxima it-1; pushes halos) | B_mid | publish max
+        const int lo = s->rank > 0 ? -3 : 0, hi = s->rank < s->nranks - 1 ? n + 3 : n;
+        const ZRanges a_mid{1, {1, 0}, {n - 1, 0}}, a_edge{2, {lo, n - 1}, {1, hi}};
+        const ZRanges b_edge{2, {0, n - 4}, {4, n}}, b_mid{1, {4, 0}, {n - 4, 0}};
+        LoopArgs a = s->args;
+        PeerCtl *mine = (PeerCtl *)(s->ctl + (size_t)s->epoch * s->ctl_bytes);
+        const size_t pl = (size_t)(n + 2 * PSI_HALO) * s->XY;
+        a.a_uses_max = 0;
+        a.peer_n = s->nranks;
+        a.allmax = (const unsigned long long *)(mine + 1);
+        a.peer_error = &mine->error;
+        a.my_cnt = mine->halo_cnt;
+        a.my_ack = mine->consumed;
+        a.expect_lo = s->rank > 0 ? s->pushed : 0ull;
+        a.expect_hi = s->rank < s->nranks - 1 ? s->pushed : 0ull;
+        if (s->rank > 0) {               // my planes [0, 4) are the lower neighbour's upper halo: its planes PSI_HALO + n + zc
+            float *base = (float *)s->peer_psi[0];
+            for (int c = 0; c < 3; ++c) a.peer_lo[c] = base + c * pl + (size_t)(PSI_HALO + n) * s->XY;
+            PeerCtl *nb = (PeerCtl *)((unsigned char *)s->peer_ctl[s->rank - 1] + (size_t)s->epoch * s->ctl_bytes);
+            a.cnt_lo = &nb->halo_cnt[1];
+            a.ack_lo = &nb->consumed[1];
+        }
+        if (s->rank < s->nranks - 1) {   // my planes [n-4, n) are the upper neighbour's lower halo: its planes zc - (n - 4)
+            float *base = (float *)s->peer_psi[1];
+            for (int c = 0; c < 3; ++c) a.peer_hi[c] = base + c * pl - (size_t)(n - PSI_HALO) * s->XY;
+            PeerCtl *nb = (PeerCtl *)((unsigned char *)s->peer_ctl[s->rank + 1] + (size_t)s->epoch * s->ctl_bytes);
+            a.cnt_hi = &nb->halo_cnt[0];
+            a.ack_hi = &nb->consumed[0];
+        }
+        launch_pass_a_tma(a, s->tma, it, 0, a_mid, s->stream);
+        a.wait_halo = 1;
+        s->ack_grid = (unsigned long long)launch_pass_a_tma(a, s->tma, it, 0, a_edge, s->stream);
+        s->acked += s->ack_grid;
+        a.wait_halo = 0;
+        a.push = 1;
+        a.expect_ack = s->acked;
+        s->push_grid = (unsigned long long)launch_pass_b_tma(a, s->tma, it, b_edge, s->stream);
+        s->pushed += s->push_grid;
+        a.push = 0;
+        launch_pass_b_tma(a, s->tma, it, b_mid, s->stream);
+        *launches += 4;
+        if (s->args.check) {
+            PeerTables tabs;
+            for (int r = 0; r < MAX_PEERS; ++r)
+                tabs.t[r] = r < s->nranks ? (unsigned long long *)((unsigned char *)s->peer_ctl[r] + (size_t)s->epoch * s->ctl_bytes + sizeof(PeerCtl)) : nullptr;
+            publish_max_kernel<<<1, 32, 0, s->stream>>>(s->maxkey + it, tabs, (size_t)it * s->nranks + s->rank, s->nranks);
+            ++*launches;
+        }
+        return 0;
+    }
     if (s->nranks > 1 && use_tiled(s) && !log && n >= 12 && !no_overlap) {
         // Slab iteration with ONE exchange.  psi carries 4 halo planes, so pass A also computes nabla_U on the 3 halo planes
         // next to an interior face (same inputs as the owner -> same bits) and no nabla_U exchange is needed.
@@ -567,6 +757,7 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
         CK(cudaMemsetAsync(s->maxkey, 0, mi * sizeof(unsigned long long), st));
         CK(cudaMemsetAsync(s->energies, 0, 2 * mi * sizeof(double), st));
     }
+    if ((rc = peer_begin(s, st))) return rc;
     launch_unpack(psi, phi_global, phi_n, s->args, st);
     if ((rc = exchange_psi(s, st)) || (rc = exchange_pg(s, st))) return rc;
     launch_initial_warp(s->args, st);
@@ -589,6 +780,7 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
             if (s->h_state->converged) { converged = 1; iters = s->h_state->iters; }
         }
     }
+    if ((rc = peer_end(s, st))) return rc;
     CK(cudaEventRecord(s->ev[2], st));
 
     // tail (solver.cu:195-199): write back psi / phi_n o psi, psi^-1 from identity (48 fixed-point steps), phi_global o psi^-1
@@ -605,6 +797,8 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
         launch_estimate_inverse_slab(s->psi_full, psi_inv, s->dg, s->z0, s->d.Z, 48, st);
         launch_apply_slab(s->phig_full, phi_global_psi_inv, psi_inv, s->dg, s->z0, s->d.Z, st);
         if (mi > 0) CKN(n.AllReduce(s->energies, s->energies, 2 * mi, ncclDouble, ncclSum, s->comm, st));
+        // peer mode keeps the per-rank maxima in maxkey[] (the global ones live in the allmax tables): reduce them for the log
+        if (mi > 0 && peer_mode(s)) CKN(n.AllReduce(s->maxkey, s->maxkey, mi, ncclUint64, ncclMax, s->comm, st));
     }
     launches += 3;
     CK_LAST();
@@ -615,6 +809,7 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
         CK(cudaMemcpyAsync(s->h_energies.data(), s->energies, 2 * mi * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
     CK(cudaStreamSynchronize(st));
+    if ((rc = peer_check_error(s))) return rc;
     s->have_state = true;
 
     if (s->h_state->converged) { converged = 1; iters = s->h_state->iters; }
@@ -622,6 +817,10 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
     // the last enqueued iteration has no successor to evaluate its convergence test: do it here (solver.cu:183)
     if (!converged && mi > 0 && norm_of(mi - 1) <= p.max_update_norm) { converged = 1; iters = mi; }
     s->last_iters = iters;
+    if (peer_mode(s)) {   // launches after the converged iteration returned early; pass A of the converged iteration itself still ran
+        s->pushed = s->push_grid * (unsigned long long)iters;
+        s->acked = s->ack_grid * (unsigned long long)(s->h_state->converged && iters < mi ? iters + 1 : iters);
+    }
     s->log.assign(iters, sobfu_b200_iter_log{0, 0, 0, 0});
     for (int it = 0; it < iters; ++it) {
         const long long idx = unrank(0xffffffffu - (unsigned)(s->h_maxkey[it] & 0xffffffffull), s->args.rm);
@@ -725,7 +924,7 @@ extern "C" int sobfu_b200_solver_time_loop(sobfu_b200_solver *s, int iters, floa
     CK(cudaEventRecord(s->ev[0], st));
     for (int i = 0; i < iters; ++i)
         if ((rc = launch_iteration(s, slot, 0, &launches))) { s->args.check = 1; return rc; }
-    if ((rc = join_psi_exchange(s)) || (rc = join_max(s))) { s->args.check = 1; return rc; }
+    if ((rc = join_psi_exchange(s)) || (rc = join_max(s)) || (rc = peer_end(s, st))) { s->args.check = 1; return rc; }
     CK(cudaEventRecord(s->ev[1], st));
     // pass A alone / pass B alone (no exchanges; B keeps descending, which is fine for timing)
     for (int i = 0; i < iters; ++i) run_pass_a(s, slot, 0);
@@ -738,6 +937,11 @@ extern "C" int sobfu_b200_solver_time_loop(sobfu_b200_solver *s, int iters, floa
     cudaEventElapsedTime(&ta, s->ev[1], s->ev[2]);
     cudaEventElapsedTime(&tb, s->ev[2], s->ev[3]);
     s->args.check = 1;
+    if (peer_mode(s)) {   // every rank has left the loop before any rank starts (and clears control blocks for) the next solve
+        CKN(nccl_api().AllReduce(s->maxkey, s->maxkey, 1, ncclUint64, ncclMax, s->comm, st));
+        CK(cudaStreamSynchronize(st));
+        if ((rc = peer_check_error(s))) return rc;
+    }
     if (ms_a) *ms_a = ta / iters;
     if (ms_b) *ms_b = tb / iters;
     if (ms_loop) *ms_loop = tl / iters;

@@ -62,7 +62,60 @@ struct LoopArgs {
     cudaTextureObject_t pn_tex;
     cudaSurfaceObject_t pn_surf;
     int ashift, amask;
+    // ---- peer mode (slab ranks on one NVLink / NVSwitch domain; the neighbours' buffers are mapped through CUDA IPC) ----
+    // Pass B stores the psi planes a neighbour needs straight into that neighbour's halo planes (the halo exchange is part
+    // of the kernel that produces the data) and counts its finished CTAs in the neighbour's control block; pass A of the
+    // next iteration waits on its own counters before it touches the halo planes.  The per-iteration maxima are published
+    // by every rank into every rank's `allmax` table: the convergence test of pass B reads all of them (bit 63 = valid).
+    float *peer_lo[3], *peer_hi[3];          // neighbour's psi components, offset so that [row + XY * zc] (my local zc) is its halo voxel; null: none
+    unsigned long long *cnt_lo, *cnt_hi;     // the neighbours' counters this rank bumps
+    const unsigned long long *my_cnt;        // own counters: [0] fed by the lower neighbour, [1] by the upper one
+    unsigned long long expect_lo, expect_hi; // pass A (wait_halo): proceed once my_cnt[k] >= expect
+    // flow control the other way: a rank may overwrite a neighbour's halo planes (pass B of iteration i) only after that
+    // neighbour's pass A of iteration i has read them -- pass A on the faces counts its CTAs in the neighbours' `consumed`
+    unsigned long long *ack_lo, *ack_hi;     // the neighbours' `consumed` counters this rank bumps at the end of pass A (faces)
+    const unsigned long long *my_ack;        // own: [0] bumped by the lower neighbour, [1] by the upper one
+    unsigned long long expect_ack;           // pass B (push): proceed once my_ack[k] >= expect_ack
+    const unsigned long long *allmax;        // own table [iteration][rank]
+    unsigned long long *peer_error;          // own control block: set when a wait timed out
+    int peer_n;                              // > 0: peer mode with this many ranks
+    int push;                                // pass B: this launch covers the slab faces (stores to the neighbours, bumps their counters)
+    int wait_halo;                           // pass A: this launch reads halo planes
 };
+
+// control block of one rank in peer mode, exported through CUDA IPC; `allmax[max_iter * nranks]` follows the header
+struct PeerCtl {
+    unsigned long long halo_cnt[2];
+    unsigned long long consumed[2];
+    unsigned long long error;
+    unsigned long long pad[3];
+};
+constexpr unsigned long long PEER_VALID = 1ull << 63;
+constexpr int MAX_PEERS = 16;
+
+SB_DEV unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+SB_DEV unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// spins until *p >= want (counters) -- bounded: after 4 s the error word of the control block is set and the caller goes on
+// (the host reports SOBFU_B200_ECOMM), so a lost peer cannot hang the GPU
+SB_DEV unsigned long long peer_wait_ge(const unsigned long long *p, unsigned long long want, unsigned long long *err) {
+    unsigned long long v = ld_acquire_sys(p);
+    if (v >= want) return v;
+    if (err && *reinterpret_cast<volatile unsigned long long *>(err)) return v;   // an earlier wait already gave up: drain quickly
+    const unsigned long long t0 = global_timer_ns();
+    while ((v = ld_acquire_sys(p)) < want) {
+        __nanosleep(64);
+        if (global_timer_ns() - t0 > 4000000000ull) { if (err) *err = 1ull; break; }
+    }
+    return v;
+}
 
 // z ranges (local planes) a launch works on: the whole slab, or the planes next to / away from the slab faces
 struct ZRanges {
@@ -78,6 +131,20 @@ SB_DEV bool loop_finished(const LoopArgs &a, int it) {
     const float s = __uint_as_float((unsigned)(a.maxkey[it - 1] >> 32));
     return __fsqrt_rd(s) <= a.thr;      // norm = __fsqrt_rd(sum of squares), utils.hpp:279-281
 }
+// same decision in peer mode: the maximum of iteration it-1 over all ranks, from the table the ranks publish into (ONE
+// thread per block calls this and broadcasts the result)
+SB_DEV bool loop_finished_peer(const LoopArgs &a, int it) {
+    if (!a.check) return false;
+    if (a.state->converged) return true;
+    if (it == 0) return false;
+    unsigned long long m = 0ull;
+    for (int r = 0; r < a.peer_n; ++r) {
+        const unsigned long long v = peer_wait_ge(a.allmax + (size_t)(it - 1) * a.peer_n + r, PEER_VALID, a.peer_error) & ~PEER_VALID;
+        m = v > m ? v : m;
+    }
+    const float s = __uint_as_float((unsigned)(m >> 32));
+    return __fsqrt_rd(s) <= a.thr;
+}
 
 void launch_unpack(const float4 *psi, const float2 *phi_global, const float2 *phi_n, const LoopArgs &a, cudaStream_t st);
 void launch_estimate_inverse_slab(const float4 *psi_full, float4 *psi_inv_local, Dims dg, int z0, int nzl, int iters, cudaStream_t st);
@@ -92,8 +159,8 @@ bool tiled_supported(const Dims d);
 struct TmaMaps;   // opaque: CUtensorMaps of the nabla_U components (pass B) and of the psi / w planes (pass A)
 TmaMaps *tma_maps_create(const LoopArgs &a);
 void tma_maps_destroy(TmaMaps *m);
-void launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, const ZRanges &zr, cudaStream_t st);
-void launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, const ZRanges &zr, cudaStream_t st);
+int launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, const ZRanges &zr, cudaStream_t st);   // returns the grid size
+int launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, const ZRanges &zr, cudaStream_t st);    // returns the grid size (0: generic path)
 
 // free-standing field kernels (field_ops.cu)
 void launch_init_identity(float4 *psi, Dims d, cudaStream_t st);

@@ -143,7 +143,16 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
                       const __grid_constant__ CUtensorMap mapz, const __grid_constant__ CUtensorMap mpx,
                       const __grid_constant__ CUtensorMap mpy, const __grid_constant__ CUtensorMap mpz, LoopArgs a, int it,
                       Sched sc) {
-    if (loop_finished(a, it)) {
+    bool fin;
+    if (a.peer_n > 0) {      // peer mode: one thread waits for the maxima every rank published, the block follows
+        __shared__ int s_fin;
+        if (threadIdx.x == 0) s_fin = loop_finished_peer(a, it) ? 1 : 0;
+        __syncthreads();
+        fin = s_fin != 0;
+    } else {
+        fin = loop_finished(a, it);
+    }
+    if (fin) {
         if (a.check && blockIdx.x == 0 && threadIdx.x == 0 && !a.state->converged) {
             a.state->iters = it;
             a.state->converged = 1;
@@ -166,6 +175,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
 #pragma unroll
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NW); }
         mbar_fence_init();
+        if (a.push) {   // peer mode: the neighbours have read the halo planes this launch is about to overwrite
+            if (a.peer_lo[0]) peer_wait_ge(a.my_ack + 0, a.expect_ack, a.peer_error);
+            if (a.peer_hi[0]) peer_wait_ge(a.my_ack + 1, a.expect_ack, a.peer_error);
+        }
     }
     __syncthreads();
 
@@ -282,6 +295,17 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
                         *reinterpret_cast<float4 *>(P[c] + o) = make_float4(np[c][0], np[c][1], np[c][2], np[c][3]);
+                    // peer mode: the planes next to a slab face also go straight into the neighbour's halo planes over NVLink
+                    if (a.peer_hi[0] && zc >= d.Z - PSI_HALO) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            *reinterpret_cast<float4 *>(a.peer_hi[c] + o) = make_float4(np[c][0], np[c][1], np[c][2], np[c][3]);
+                    }
+                    if (a.peer_lo[0] && zc < PSI_HALO) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            *reinterpret_cast<float4 *>(a.peer_lo[c] + o) = make_float4(np[c][0], np[c][1], np[c][2], np[c][3]);
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const unsigned bits = __float_as_uint(nsq[j]), idx = (unsigned)(o + j) + zoff;   // global voxel index
@@ -298,12 +322,17 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
     unsigned long long best = best_bits ? (((unsigned long long)best_bits << 32) | (unsigned long long)(0xffffffffu - rank_of(best_idx, a.rm))) : 0ull;
     best = warp_max_u64(best);
     if (lane == 0) skey[warp] = best;
+    if (a.push) __threadfence_system();                          // this thread's stores to the neighbours are performed ...
     asm volatile("bar.sync 1, %0;" ::"r"(NW * 32) : "memory");   // consumers only (the producer warp has left)
     if (tid == 0) {
         unsigned long long m = 0ull;
 #pragma unroll
         for (int k = 0; k < NW; ++k) m = skey[k] > m ? skey[k] : m;
         atomicMax(&a.maxkey[it], m);
+        if (a.push) {                                            // ... before the neighbours can see this CTA counted
+            if (a.cnt_hi) atomicAdd_system(a.cnt_hi, 1ull);
+            if (a.cnt_lo) atomicAdd_system(a.cnt_lo, 1ull);
+        }
     }
 }
 }  // namespace pb
@@ -370,6 +399,11 @@ __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
 #pragma unroll
         for (int s = 0; s < NSTAGE; ++s) mbar_init(full0 + 8 * s, 1);
         mbar_fence_init();
+        if (a.wait_halo) {   // peer mode: the neighbours' pass B of the previous iteration stored into this rank's halo planes
+            if (a.expect_lo) peer_wait_ge(a.my_cnt + 0, a.expect_lo, a.peer_error);
+            if (a.expect_hi) peer_wait_ge(a.my_cnt + 1, a.expect_hi, a.peer_error);
+            asm volatile("fence.proxy.async;" ::: "memory");     // the planes are read by TMA (async proxy)
+        }
     }
     __syncthreads();
 
@@ -559,6 +593,13 @@ __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
             wm = wc; wc = wp;
         }
     }
+    if (a.wait_halo) {   // peer mode: this CTA no longer reads the halo planes -- the neighbours may overwrite them
+        __syncthreads();
+        if (tid == 0) {
+            if (a.ack_lo) atomicAdd_system(a.ack_lo, 1ull);
+            if (a.ack_hi) atomicAdd_system(a.ack_hi, 1ull);
+        }
+    }
 }
 }  // namespace pa
 
@@ -633,26 +674,28 @@ TmaMaps *tma_maps_create(const LoopArgs &a) {
 
 void tma_maps_destroy(TmaMaps *m) { delete m; }
 
-void launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, const ZRanges &zr, cudaStream_t st) {
+int launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, const ZRanges &zr, cudaStream_t st) {
     const int ctas = sm_count();
     const Sched sc = make_sched(a.d, zr, pb::TX, pb::TY, 6, 0.35, ctas);
-    if (sc.nitems == 0) return;
+    if (sc.nitems == 0) return 0;
     const int grid = sc.nitems < ctas ? sc.nitems : ctas;
     pb::pass_b_tma_kernel<<<grid, (pb::NW + 1) * 32, pb::SMEM_BYTES, st>>>(m->g[0], m->g[1], m->g[2], m->pb_psi[0], m->pb_psi[1], m->pb_psi[2], a, it, sc);
+    return grid;
 }
 
-void launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, const ZRanges &zr, cudaStream_t st) {
+int launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, const ZRanges &zr, cudaStream_t st) {
     if (log) {   // logging iterations (rare): materialise the warped plane, then the generic kernel that also sums the energies
         launch_initial_warp(a, st);
         launch_pass_a_generic(a, it, 1, st);
-        return;
+        return 0;
     }
     const int ctas = PA_CTAS * sm_count();
     const Sched sc = make_sched(a.d, zr, pa::TX, pa::TY, 2, 0.5, ctas);
-    if (sc.nitems == 0) return;
+    if (sc.nitems == 0) return 0;
     const int grid = sc.nitems < ctas ? sc.nitems : ctas;
     if (a.pn_tex) pa::pass_a_tma_kernel<true><<<grid, pa::NTHREADS, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
     else pa::pass_a_tma_kernel<false><<<grid, pa::NTHREADS, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
+    return grid;
 }
 
 }  // namespace sb

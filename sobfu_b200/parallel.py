@@ -41,6 +41,29 @@ class SlabSolver(Solver):
             uid = broadcast_unique_id(dist)
             raw = (C.c_ubyte * 128).from_buffer_copy(uid)
             check(lib().sobfu_b200_solver_attach_comm(self._h, raw, self.rank, self.nranks))
+            self.peer = self._attach_peers(dist)
+
+    def _attach_peers(self, dist):
+        """NVLink peer mode (include/sobfu_b200.h): every rank exports CUDA IPC handles of its psi planes and control block,
+        the blocks are all-gathered, every rank maps its neighbours.  Returns False (NCCL exchange stays) when the ranks are
+        not all on one node / cannot map each other; the decision is collective so that all ranks run the same protocol."""
+        import os
+        if os.environ.get("SOBFU_B200_NO_PEER"):
+            return False
+        blk = (C.c_ubyte * 128)()
+        ok = lib().sobfu_b200_solver_peer_export(self._h, blk) == 0
+        blocks = [None] * self.nranks
+        dist.all_gather_object(blocks, bytes(blk) if ok else None)
+        if any(b is None for b in blocks):
+            return False
+        raw = (C.c_ubyte * (128 * self.nranks)).from_buffer_copy(b"".join(blocks))
+        ok = lib().sobfu_b200_solver_peer_attach(self._h, raw) == 0
+        oks = [None] * self.nranks
+        dist.all_gather_object(oks, bool(ok))
+        if not all(oks):
+            lib().sobfu_b200_solver_peer_attach(self._h, None)      # every rank falls back together
+            return False
+        return True
 
     def slab_dims(self):
         X, Y, _ = self.params.volume_dims

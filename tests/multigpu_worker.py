@@ -44,7 +44,7 @@ def main():
             assert a[0] == b[0] and a[1] == b[1]
             assert abs(a[2] - b[2]) <= 2e-5 * abs(b[2]) + 1e-6 and abs(a[3] - b[3]) <= 2e-5 * abs(b[3]) + 1e-6
         if rank == 0:
-            print("slab == single GPU, bit for bit:", dims, "iters", full["info"].iters, "ranks", world, flush=True)
+            print("slab == single GPU, bit for bit:", dims, "iters", full["info"].iters, "ranks", world, "peer mode:", slab["peer"], flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -72,7 +72,7 @@ def solve(p, dims, pg, pn, psi0, dist_or_none):
     _capi.check(_capi.lib().sobfu_b200_solver_estimate_psi(solver._h, ptr(d_pg), ptr(d_pgpi), ptr(d_pn), ptr(d_pnp), ptr(d_psi), ptr(d_inv), C.byref(info)))
     solver.info = info
     return dict(info=info, log=solver.get_log(), psi=d_psi.cpu().numpy(), psi_inv=d_inv.cpu().numpy(), phi_n_psi=d_pnp.cpu().numpy(),
-                phi_global_psi_inv=d_pgpi.cpu().numpy(), z0=z0, nz=nz)
+                phi_global_psi_inv=d_pgpi.cpu().numpy(), z0=z0, nz=nz, peer=bool(getattr(solver, "peer", False)))
 
 
 if __name__ == "__main__":

@@ -9,13 +9,21 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_slab_solve_matches_single_gpu(built):
+@pytest.mark.parametrize("mode", ["peer", "nccl"])
+def test_slab_solve_matches_single_gpu(built, mode):
+    """mode peer: halo stores + maxima over NVLink peer memory (CUDA IPC); mode nccl: the same iteration over NCCL"""
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs at least 2 GPUs (run: gpurun --gpus 2 -- python -m pytest tests -m gpu)")
     n = 2 if n < 4 else 4
+    env = dict(os.environ)
+    env.pop("SOBFU_B200_NO_PEER", None)
+    if mode == "nccl":
+        env["SOBFU_B200_NO_PEER"] = "1"
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % n, "--master-addr", "127.0.0.1",
-                        "--master-port", "29541", os.path.join(ROOT, "tests", "multigpu_worker.py")], capture_output=True, text=True, timeout=900)
+                        "--master-port", "29541" if mode == "peer" else "29543", os.path.join(ROOT, "tests", "multigpu_worker.py")],
+                       capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
     assert r.stdout.count("bit for bit") == 4
+    assert ("peer mode: True" in r.stdout) == (mode == "peer"), r.stdout[-2000:]
