@@ -231,8 +231,8 @@ def run_ours(args, rank, world, torch, dist):
             out["config"]["multi_gpu"] = ("z-slab of %d planes per GPU; nabla_U on the 3 halo planes is recomputed locally, so an iteration needs "
                                           "one psi halo exchange (4 planes) + one scalar MAX; " % (dim // world)) + (
                 "peer mode: pass B on the slab faces stores the planes straight into the neighbours' halo planes over NVLink (CUDA IPC) and "
-                "signals through counters, maxima are published to every rank's table; four kernels per iteration on one stream, no NCCL in "
-                "the loop" if peer else
+                "signals through counters per work item (face items first), maxima are published to every rank's table by the last CTA; "
+                "two kernels per iteration on one stream, no NCCL in the loop" if peer else
                 "NCCL: grouped ncclSend/Recv with both neighbours behind the mid-slab kernels + MAX all-reduce on a second communicator")
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()

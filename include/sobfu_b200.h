@@ -146,6 +146,15 @@ int sobfu_b200_marching_cubes(const void *vol, int X, int Y, int Z, const float 
                               const float *t3, void *verts4, void *normals4, int vertex_cap, int *n_vertices,
                               int *occupied_voxel, int *occupied_cube, int *occupied_nverts, int voxel_cap,
                               int *n_voxels);
+/* z-slab form (marching cubes runs per slab): `vol_slab` holds planes [z0, z0 + nz_avail) of an X x Y x Z volume,
+ * nz_avail = nz + 1 when the first plane of the upper neighbour's slab has been appended (every rank but the last), else nz.
+ * Extracts the cells whose lower corner lies in [z0, z0 + nz); voxel ids and coordinates are GLOBAL, so the ranks' outputs
+ * concatenated in rank order equal the single-GPU output of sobfu_b200_marching_cubes bit for bit.  volume_size3 is the size
+ * of the whole volume.  The reference is single-GPU (marching_cubes.cpp:24-76); this replaces nothing there. */
+int sobfu_b200_marching_cubes_slab(const void *vol_slab, int X, int Y, int Z, int z0, int nz, int nz_avail,
+                                   const float *volume_size3, const float *R9, const float *t3, void *verts4, void *normals4,
+                                   int vertex_cap, int *n_vertices, int *occupied_voxel, int *occupied_cube,
+                                   int *occupied_nverts, int voxel_cap, int *n_voxels);
 
 /* ---- multi-GPU (z-slab partition): one process per GPU ----
  * rank 0 obtains an id, the launcher broadcasts it (torch.distributed), every rank attaches. */
@@ -163,7 +172,9 @@ int sobfu_b200_solver_attach_comm(sobfu_b200_solver *s, const void *id128_host, 
 /* Peer mode (ranks on one NVLink / NVSwitch domain, e.g. the 8 GPUs of a B200 node): the per-iteration psi halo exchange
  * and the convergence test leave NCCL.  Pass B on the slab faces stores its new psi planes straight into the neighbours'
  * halo planes over NVLink (CUDA IPC mappings) and signals through counters in the neighbours' memory; every rank publishes
- * its per-iteration maximum into every rank's table.  An iteration is then four kernels on one stream.
+ * its per-iteration maximum into every rank's table (last CTA of pass B).  An iteration is then TWO kernels on one stream:
+ * pass A does the middle of the slab first and the halo-reading work items last, pass B the face items first, so the halo
+ * planes travel while the middle of the slab is computed.
  *   every rank: peer_export(block);  launcher: all-gather the blocks (rank-major);  every rank: peer_attach(all blocks).
  * Optional: without it (or with SOBFU_B200_NO_PEER set, or when attach fails) the solver keeps exchanging over NCCL.
  * Results are bit-identical in both modes.  Replaces nothing in the reference (single GPU, solver.cu:85-205). */

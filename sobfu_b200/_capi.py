@@ -62,6 +62,7 @@ SIGNATURES = {
     "sobfu_b200_depth_truncate": [_P, _Z, _I, _I, _F],
     "sobfu_b200_compute_dists": [_P, _Z, _P, _Z, _I, _I, _F, _F, _F, _F],
     "sobfu_b200_marching_cubes": [_P, _I, _I, _I, _FP, _FP, _FP, _P, _P, _I, _IP, _P, _P, _P, _I, _IP],
+    "sobfu_b200_marching_cubes_slab": [_P, _I, _I, _I, _I, _I, _I, _FP, _FP, _FP, _P, _P, _I, _IP, _P, _P, _P, _I, _IP],
     "sobfu_b200_comm_unique_id": [_P],
     "sobfu_b200_solver_attach_comm": [_P, _P, _I, _I],
     "sobfu_b200_solver_peer_export": [_P, _P],

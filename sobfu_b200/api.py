@@ -305,6 +305,28 @@ class MarchingCubes:
             return verts[:n], normals[:n], occ[:, :nvox.value]
         return verts[:n], normals[:n]
 
+    def run_slab(self, slab, dims, size, z0, nz, vertex_cap=None, return_occupied=False):
+        """z-slab form (sobfu_b200_marching_cubes_slab): `slab` is a float2 tensor [nz_avail, Y, X, 2] holding planes
+        [z0, z0 + nz_avail) of a volume of `dims` / `size`, nz_avail = nz (+ 1: first plane of the upper neighbour).  The ranks'
+        outputs concatenated in rank order equal run() on the whole volume."""
+        cap = int(vertex_cap or self.DEFAULT_TRIANGLES_BUFFER_SIZE)
+        dev = slab.device
+        verts = torch.empty((cap, 4), dtype=torch.float32, device=dev)
+        normals = torch.empty((cap, 4), dtype=torch.float32, device=dev)
+        vcap = cap // 3
+        occ = torch.empty((3, vcap), dtype=torch.int32, device=dev)
+        nv, nvox = C.c_int(0), C.c_int(0)
+        X, Y, Z = dims
+        assert slab.is_contiguous() and slab.shape[1:] == (Y, X, 2), slab.shape
+        check(lib().sobfu_b200_marching_cubes_slab(_ptr(slab), X, Y, Z, int(z0), int(nz), int(slab.shape[0]), fvec(size),
+                                                   fvec(self.pose.R.reshape(-1)), fvec(self.pose.t), _ptr(verts), _ptr(normals), cap,
+                                                   C.byref(nv), C.c_void_p(occ[0].data_ptr()), C.c_void_p(occ[1].data_ptr()),
+                                                   C.c_void_p(occ[2].data_ptr()), vcap, C.byref(nvox)))
+        n = min(nv.value, cap)
+        if return_occupied:
+            return verts[:n], normals[:n], occ[:, :nvox.value]
+        return verts[:n], normals[:n]
+
 
 class SobFusion:
     """Per-frame pipeline, SobFusion::operator() (src/sobfu/sob_fusion.cpp:71-145)."""

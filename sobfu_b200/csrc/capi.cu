@@ -46,9 +46,9 @@ void launch_truncate(unsigned short *depth, size_t pitch, int cols, int rows, un
 void launch_dists(const unsigned short *depth, size_t dp, float *dists, size_t fp, int cols, int rows, float fix, float fiy,
                   float cx, float cy, cudaStream_t st);
 // marching_cubes.cu
-int marching_cubes_run(const float2 *vol, Dims d, float3 size, const float *R, const float *t, float4 *verts, float4 *normals,
-                       int vertex_cap, int *n_vertices, int *occ_voxel, int *occ_cube, int *occ_nverts, int voxel_cap,
-                       int *n_voxels, cudaStream_t st, std::string &err);
+int marching_cubes_run(const float2 *vol, Dims dg, int z0, int nz, int nz_avail, float3 size, const float *R, const float *t,
+                       float4 *verts, float4 *normals, int vertex_cap, int *n_vertices, int *occ_voxel, int *occ_cube,
+                       int *occ_nverts, int voxel_cap, int *n_voxels, cudaStream_t st, std::string &err);
 }  // namespace sb
 
 using namespace sb;
@@ -191,9 +191,10 @@ struct sobfu_b200_solver {
     void *peer_psi[2] = {nullptr, nullptr};       // psi_alloc of rank-1 / rank+1
     void *peer_ctl[MAX_PEERS] = {};               // ctl of every rank (own entry: s->ctl)
     int epoch = 0;                                // parity of the control block in use (flips every estimate_psi)
-    unsigned long long pushed = 0;                // CTAs of this rank's face launches of pass B so far in this epoch
-    unsigned long long push_grid = 0;             // CTAs of one such launch
-    unsigned long long acked = 0, ack_grid = 0;   // the same for the face launches of pass A (halo planes read)
+    unsigned long long pushed = 0;                // face items (per face) of this rank's pass B launches so far in this epoch
+    unsigned long long push_items = 0;            // face items (per face) of one launch
+    unsigned long long acked = 0, ack_items = 0;  // the same for pass A (items that read halo planes)
+    unsigned int *tickets = nullptr;              // [max_iter]: CTAs of pass B that have finished (the last one publishes the maximum)
     bool psi_exchange_pending = false;   // ev_p has been recorded and not yet waited for by the compute stream
     bool max_pending = false;            // ev_m (global maximum of the previous iteration) likewise
     int variant = 0;
@@ -234,6 +235,8 @@ static void fill_args(sobfu_b200_solver *s) {
     a.cnt_lo = a.cnt_hi = nullptr; a.my_cnt = nullptr; a.expect_lo = a.expect_hi = 0ull;
     a.ack_lo = a.ack_hi = nullptr; a.my_ack = nullptr; a.expect_ack = 0ull;
     a.allmax = nullptr; a.peer_error = nullptr; a.peer_n = 0; a.push = 0; a.wait_halo = 0;
+    a.tickets = nullptr; a.my_rank = 0;
+    for (int r = 0; r < MAX_PEERS; ++r) a.pub[r] = nullptr;
 }
 
 // phi_n.x as a 2-D atlas of Z slices (kx = 2^ashift per row) in a CUDA array that supports texture gather
@@ -353,7 +356,7 @@ extern "C" int sobfu_b200_solver_destroy(sobfu_b200_solver *s) {
     if (s->pn_tex) cudaDestroyTextureObject(s->pn_tex);
     if (s->pn_surf) cudaDestroySurfaceObject(s->pn_surf);
     if (s->pn_array) cudaFreeArray(s->pn_array);
-    cudaFree(s->state); cudaFree(s->maxkey); cudaFree(s->energies);
+    cudaFree(s->state); cudaFree(s->maxkey); cudaFree(s->tickets); cudaFree(s->energies);
     if (s->h_state) cudaFreeHost(s->h_state);
     for (auto &e : s->ev) if (e) cudaEventDestroy(e);
     if (s->ev_user) cudaEventDestroy(s->ev_user);
@@ -389,6 +392,7 @@ extern "C" int sobfu_b200_solver_create(sobfu_b200_solver **out, const sobfu_b20
     } while (0)
     CKD(cudaMalloc(&s->state, sizeof(LoopState)));
     CKD(cudaMalloc(&s->maxkey, mi * sizeof(unsigned long long)));
+    CKD(cudaMalloc(&s->tickets, mi * sizeof(unsigned int)));
     CKD(cudaMalloc(&s->energies, 2 * mi * sizeof(double)));
     CKD(cudaMallocHost(&s->h_state, sizeof(LoopState)));
     CKD(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -499,15 +503,6 @@ extern "C" int sobfu_b200_solver_peer_attach(sobfu_b200_solver *s, const void *a
     return 0;
 }
 
-// every rank writes its maximum of iteration `it` into slot [it][rank] of every rank's table (bit 63 marks it valid)
-struct PeerTables { unsigned long long *t[MAX_PEERS]; };
-__global__ void publish_max_kernel(const unsigned long long *maxkey_it, PeerTables tabs, size_t slot, int nranks) {
-    const int r = threadIdx.x;
-    if (r < nranks) {
-        const unsigned long long v = *maxkey_it | PEER_VALID;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(tabs.t[r] + slot), "l"(v) : "memory");
-    }
-}
 // waits until the neighbours' stores into this rank's halo planes have landed (end of a loop)
 __global__ void peer_wait_kernel(const LoopState *state, const unsigned long long *cnt, unsigned long long expect_lo,
                                  unsigned long long expect_hi, unsigned long long *err) {
@@ -577,7 +572,7 @@ static inline bool log_iter(const sobfu_b200_params &p, int iter1) {   // iter1 
     return p.verbosity == 2 || (p.verbosity == 1 && (iter1 == 1 || iter1 % 50 == 0 || iter1 == p.max_iter));
 }
 
-static ZRanges whole_slab(const sobfu_b200_solver *s) { return ZRanges{1, {0, 0}, {s->d.Z, 0}}; }
+static ZRanges whole_slab(const sobfu_b200_solver *s) { return ZRanges{1, {0, 0, 0}, {s->d.Z, 0, 0}, {0, 0, 0}}; }
 static void run_pass_a(sobfu_b200_solver *s, int it, int log) {
     if (!use_tiled(s)) launch_pass_a_generic(s->args, it, log, s->stream);
     else launch_pass_a_tma(s->args, s->tma, it, log, whole_slab(s), s->stream);
@@ -636,57 +631,59 @@ static int launch_iteration(sobfu_b200_solver *s, int it, int log, int *launches
     const int n = s->d.Z;
     static const bool no_overlap = getenv("SOBFU_B200_NO_OVERLAP") != nullptr;
     if (peer_mode(s)) {
-        // Peer mode: the same split, ONE stream, no NCCL and no events inside the loop.  Pass B on the faces stores the new psi
-        // planes into the neighbours' halo planes itself and counts its CTAs there; pass A on the faces waits for the
-        // neighbours' counts of the previous iteration; every rank publishes its maximum to every rank and pass B reads all.
-        //   A_mid [1,n-1) | A_edge (waits halo counters) | B_edge (waits maxima it-1; pushes halos) | B_mid | publish max
-        const int lo = s->rank > 0 ? -3 : 0, hi = s->rank < s->nranks - 1 ? n + 3 : n;
-        const ZRanges a_mid{1, {1, 0}, {n - 1, 0}}, a_edge{2, {lo, n - 1}, {1, hi}};
-        const ZRanges b_edge{2, {0, n - 4}, {4, n}}, b_mid{1, {4, 0}, {n - 4, 0}};
+        // Peer mode: TWO launches per iteration on one stream, no NCCL and no events inside the loop.  Work items carry a face
+        // tag.  Pass A: the middle of the slab first, then the items that read halo planes (they wait for the neighbour's
+        // counter of the previous iteration and acknowledge when done).  Pass B: the face items first -- they wait for the
+        // neighbour's acknowledgement, store the new psi planes into the neighbour's halo planes themselves and count the item
+        // there at once, so the halo travels while the middle of the slab is computed; every CTA reads the maxima all ranks
+        // published for the previous iteration, and the last CTA to finish publishes this rank's maximum to every rank.
+        const bool has_lo = s->rank > 0, has_hi = s->rank < s->nranks - 1;
+        const int lo = has_lo ? -3 : 0, hi = has_hi ? n + 3 : n;
+        const ZRanges za{3, {1, lo, n - 1}, {n - 1, 1, hi}, {0, has_lo ? 1 : 0, has_hi ? 2 : 0}};
+        const ZRanges zb{3, {0, n - 4, 4}, {4, n, n - 4}, {has_lo ? 1 : 0, has_hi ? 2 : 0, 0}};
         LoopArgs a = s->args;
         PeerCtl *mine = (PeerCtl *)(s->ctl + (size_t)s->epoch * s->ctl_bytes);
         const size_t pl = (size_t)(n + 2 * PSI_HALO) * s->XY;
         a.a_uses_max = 0;
         a.peer_n = s->nranks;
+        a.my_rank = s->rank;
         a.allmax = (const unsigned long long *)(mine + 1);
         a.peer_error = &mine->error;
         a.my_cnt = mine->halo_cnt;
         a.my_ack = mine->consumed;
-        a.expect_lo = s->rank > 0 ? s->pushed : 0ull;
-        a.expect_hi = s->rank < s->nranks - 1 ? s->pushed : 0ull;
-        if (s->rank > 0) {               // my planes [0, 4) are the lower neighbour's upper halo: its planes PSI_HALO + n + zc
+        a.expect_lo = has_lo ? s->pushed : 0ull;
+        a.expect_hi = has_hi ? s->pushed : 0ull;
+        if (has_lo) {                    // my planes [0, 4) are the lower neighbour's upper halo: its planes PSI_HALO + n + zc
             float *base = (float *)s->peer_psi[0];
             for (int c = 0; c < 3; ++c) a.peer_lo[c] = base + c * pl + (size_t)(PSI_HALO + n) * s->XY;
             PeerCtl *nb = (PeerCtl *)((unsigned char *)s->peer_ctl[s->rank - 1] + (size_t)s->epoch * s->ctl_bytes);
             a.cnt_lo = &nb->halo_cnt[1];
             a.ack_lo = &nb->consumed[1];
         }
-        if (s->rank < s->nranks - 1) {   // my planes [n-4, n) are the upper neighbour's lower halo: its planes zc - (n - 4)
+        if (has_hi) {                    // my planes [n-4, n) are the upper neighbour's lower halo: its planes zc - (n - 4)
             float *base = (float *)s->peer_psi[1];
             for (int c = 0; c < 3; ++c) a.peer_hi[c] = base + c * pl - (size_t)(n - PSI_HALO) * s->XY;
             PeerCtl *nb = (PeerCtl *)((unsigned char *)s->peer_ctl[s->rank + 1] + (size_t)s->epoch * s->ctl_bytes);
             a.cnt_hi = &nb->halo_cnt[0];
             a.ack_hi = &nb->consumed[0];
         }
-        launch_pass_a_tma(a, s->tma, it, 0, a_mid, s->stream);
         a.wait_halo = 1;
-        s->ack_grid = (unsigned long long)launch_pass_a_tma(a, s->tma, it, 0, a_edge, s->stream);
-        s->acked += s->ack_grid;
+        const LaunchInfo la = launch_pass_a_tma(a, s->tma, it, 0, za, s->stream);
+        // every face range has the same geometry on every rank (4 planes, equal slabs): the neighbour counts what I count
+        s->ack_items = (unsigned long long)(la.face_items[1] ? la.face_items[1] : la.face_items[2]);
+        s->acked += s->ack_items;
         a.wait_halo = 0;
         a.push = 1;
         a.expect_ack = s->acked;
-        s->push_grid = (unsigned long long)launch_pass_b_tma(a, s->tma, it, b_edge, s->stream);
-        s->pushed += s->push_grid;
-        a.push = 0;
-        launch_pass_b_tma(a, s->tma, it, b_mid, s->stream);
-        *launches += 4;
         if (s->args.check) {
-            PeerTables tabs;
-            for (int r = 0; r < MAX_PEERS; ++r)
-                tabs.t[r] = r < s->nranks ? (unsigned long long *)((unsigned char *)s->peer_ctl[r] + (size_t)s->epoch * s->ctl_bytes + sizeof(PeerCtl)) : nullptr;
-            publish_max_kernel<<<1, 32, 0, s->stream>>>(s->maxkey + it, tabs, (size_t)it * s->nranks + s->rank, s->nranks);
-            ++*launches;
+            a.tickets = s->tickets;
+            for (int r = 0; r < s->nranks; ++r)
+                a.pub[r] = (unsigned long long *)((unsigned char *)s->peer_ctl[r] + (size_t)s->epoch * s->ctl_bytes + sizeof(PeerCtl));
         }
+        const LaunchInfo lb = launch_pass_b_tma(a, s->tma, it, zb, s->stream);
+        s->push_items = (unsigned long long)(lb.face_items[1] ? lb.face_items[1] : lb.face_items[2]);
+        s->pushed += s->push_items;
+        *launches += 2;
         return 0;
     }
     if (s->nranks > 1 && use_tiled(s) && !log && n >= 12 && !no_overlap) {
@@ -698,8 +695,8 @@ static int launch_iteration(sobfu_b200_solver *s, int it, int log, int *launches
         // Pass A only writes scratch, so it may run before the previous iteration's global maximum is known: it honours the
         // sticky flag only (a_uses_max = 0); pass B, which changes psi, always sees the reduced maximum.
         const int lo = s->rank > 0 ? -3 : 0, hi = s->rank < s->nranks - 1 ? n + 3 : n;
-        const ZRanges a_mid{1, {1, 0}, {n - 1, 0}}, a_edge{2, {lo, n - 1}, {1, hi}};
-        const ZRanges b_edge{2, {0, n - 4}, {4, n}}, b_mid{1, {4, 0}, {n - 4, 0}};
+        const ZRanges a_mid{1, {1, 0, 0}, {n - 1, 0, 0}, {0, 0, 0}}, a_edge{2, {lo, n - 1, 0}, {1, hi, 0}, {0, 0, 0}};
+        const ZRanges b_edge{2, {0, n - 4, 0}, {4, n, 0}, {0, 0, 0}}, b_mid{1, {4, 0, 0}, {n - 4, 0, 0}, {0, 0, 0}};
         LoopArgs a = s->args;
         a.a_uses_max = 0;
         launch_pass_a_tma(a, s->tma, it, 0, a_mid, s->stream);
@@ -755,6 +752,7 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
     CK(cudaMemsetAsync(s->state, 0, sizeof(LoopState), st));
     if (mi > 0) {
         CK(cudaMemsetAsync(s->maxkey, 0, mi * sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(s->tickets, 0, mi * sizeof(unsigned int), st));
         CK(cudaMemsetAsync(s->energies, 0, 2 * mi * sizeof(double), st));
     }
     if ((rc = peer_begin(s, st))) return rc;
@@ -818,8 +816,8 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
     if (!converged && mi > 0 && norm_of(mi - 1) <= p.max_update_norm) { converged = 1; iters = mi; }
     s->last_iters = iters;
     if (peer_mode(s)) {   // launches after the converged iteration returned early; pass A of the converged iteration itself still ran
-        s->pushed = s->push_grid * (unsigned long long)iters;
-        s->acked = s->ack_grid * (unsigned long long)(s->h_state->converged && iters < mi ? iters + 1 : iters);
+        s->pushed = s->push_items * (unsigned long long)iters;
+        s->acked = s->ack_items * (unsigned long long)(s->h_state->converged && iters < mi ? iters + 1 : iters);
     }
     s->log.assign(iters, sobfu_b200_iter_log{0, 0, 0, 0});
     for (int it = 0; it < iters; ++it) {
@@ -1101,8 +1099,21 @@ extern "C" int sobfu_b200_marching_cubes(const void *vol, int X, int Y, int Z, c
                                          int *occ_nverts, int voxel_cap, int *n_voxels) {
     NEED(vol && size3 && R9 && t3 && dims_ok(X, Y, Z) && n_vertices, "marching_cubes: bad argument");
     std::string err;
-    int rc = marching_cubes_run((const float2 *)vol, Dims{X, Y, Z}, make_float3(size3[0], size3[1], size3[2]), R9, t3, (float4 *)verts,
+    int rc = marching_cubes_run((const float2 *)vol, Dims{X, Y, Z}, 0, Z, Z, make_float3(size3[0], size3[1], size3[2]), R9, t3, (float4 *)verts,
                                 (float4 *)normals, vertex_cap, n_vertices, occ_voxel, occ_cube, occ_nverts, voxel_cap, n_voxels, g_stream, err);
+    if (rc) return fail(rc, "%s", err.c_str());
+    return 0;
+}
+extern "C" int sobfu_b200_marching_cubes_slab(const void *vol_slab, int X, int Y, int Z, int z0, int nz, int nz_avail, const float *size3,
+                                              const float *R9, const float *t3, void *verts, void *normals, int vertex_cap, int *n_vertices,
+                                              int *occ_voxel, int *occ_cube, int *occ_nverts, int voxel_cap, int *n_voxels) {
+    NEED(vol_slab && size3 && R9 && t3 && dims_ok(X, Y, Z) && n_vertices, "marching_cubes_slab: bad argument");
+    NEED(z0 >= 0 && nz >= 1 && z0 + nz <= Z && nz_avail >= nz && nz_avail <= nz + 1 && z0 + nz_avail <= Z,
+         "marching_cubes_slab: the slab is planes [z0, z0 + nz) of the volume plus at most one plane of the upper neighbour");
+    std::string err;
+    int rc = marching_cubes_run((const float2 *)vol_slab, Dims{X, Y, Z}, z0, nz, nz_avail, make_float3(size3[0], size3[1], size3[2]), R9, t3,
+                                (float4 *)verts, (float4 *)normals, vertex_cap, n_vertices, occ_voxel, occ_cube, occ_nverts, voxel_cap, n_voxels,
+                                g_stream, err);
     if (rc) return fail(rc, "%s", err.c_str());
     return 0;
 }

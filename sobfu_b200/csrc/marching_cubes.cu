@@ -7,8 +7,13 @@
 // hardware schedule) and scans with thrust; here every voxel writes (occupied, #vertices) as one 64-bit word, ONE
 // cub exclusive scan yields both the voxel slot and the vertex offset, and the triangles come out ordered by voxel index:
 // the output is deterministic and identical across runs, devices and slab partitions.
+//
+// z-slab mode: a rank extracts the cells whose lower corner lies in its planes [z0, z0 + nz) from its slab
+// plus ONE plane of the upper neighbour; voxel ids and vertex coordinates use the global z, so the ranks' outputs
+// concatenated in rank order are bit-identical to the single-GPU output.
 #include <cub/device/device_scan.cuh>
 
+#include <mutex>
 #include <string>
 
 #include "mc_tables.h"
@@ -35,9 +40,10 @@ __device__ __forceinline__ int cube_index(const float2 *__restrict__ vol, int x,
     return c;
 }
 
-// pass 1: (1 << 32 | numVerts) for occupied voxels, 0 otherwise
-__global__ void classify_kernel(const float2 *__restrict__ vol, Dims d, unsigned long long *__restrict__ counts) {
-    const size_t n = (size_t)d.X * d.Y * d.Z;
+// pass 1: (1 << 32 | numVerts) for occupied voxels, 0 otherwise.  `d` = planes available at `vol` (the slab + its halo plane),
+// `nz` = planes whose cells this call owns (local z in [0, nz))
+__global__ void classify_kernel(const float2 *__restrict__ vol, Dims d, int nz, unsigned long long *__restrict__ counts) {
+    const size_t n = (size_t)d.X * d.Y * nz;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int z = (int)(i / ((size_t)d.X * d.Y)), r = (int)(i - (size_t)z * d.X * d.Y), y = r / d.X, x = r - y * d.X;
         unsigned long long v = 0ull;
@@ -60,11 +66,12 @@ __device__ __forceinline__ float3 interp(float3 p0, float3 p1, float f0, float f
 __device__ __forceinline__ float dot3(float3 a, float3 b) { return __fmaf_rn(a.x, b.x, __fmaf_rn(a.y, b.y, a.z * b.z)); }
 
 // pass 2: triangles of the occupied voxels, at the offsets of the scan
-__global__ void triangles_kernel(const float2 *__restrict__ vol, Dims d, float3 cell, Pose pose,
+__global__ void triangles_kernel(const float2 *__restrict__ vol, Dims d, int nz, int z0, float3 cell, Pose pose,
                                  const unsigned long long *__restrict__ counts, const unsigned long long *__restrict__ scan,
                                  float4 *__restrict__ verts, float4 *__restrict__ normals, int vertex_cap, int *__restrict__ occ_voxel,
                                  int *__restrict__ occ_cube, int *__restrict__ occ_nverts, int voxel_cap) {
-    const size_t n = (size_t)d.X * d.Y * d.Z;
+    const size_t n = (size_t)d.X * d.Y * nz;
+    const size_t id0 = (size_t)z0 * d.X * d.Y;        // global voxel id of local voxel 0
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const unsigned long long c = counts[i];
         if (c == 0ull) continue;
@@ -74,14 +81,14 @@ __global__ void triangles_kernel(const float2 *__restrict__ vol, Dims d, float3 
         const int z = (int)(i / ((size_t)d.X * d.Y)), r = (int)(i - (size_t)z * d.X * d.Y), y = r / d.X, x = r - y * d.X;
         float f[8];
         const int cube = cube_index(vol, x, y, z, d, f);
-        if (occ_voxel) { occ_voxel[slot] = (int)i; occ_cube[slot] = cube; occ_nverts[slot] = nv; }
+        if (occ_voxel) { occ_voxel[slot] = (int)(i + id0); occ_cube[slot] = cube; occ_nverts[slot] = nv; }
         if (!verts) continue;
         // get_node_coo, marching_cubes.cu:185-193: centre of the voxel
         float3 v[8];
         const int dx[8] = {0, 1, 1, 0, 0, 1, 1, 0}, dy[8] = {0, 0, 1, 1, 0, 0, 1, 1}, dz[8] = {0, 0, 0, 0, 1, 1, 1, 1};
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            float3 c3 = make_float3((float)(x + dx[k]), (float)(y + dy[k]), (float)(z + dz[k]));
+            float3 c3 = make_float3((float)(x + dx[k]), (float)(y + dy[k]), (float)(z0 + z + dz[k]));
             c3.x += 0.5f; c3.y += 0.5f; c3.z += 0.5f;
             c3.x *= cell.x; c3.y *= cell.y; c3.z *= cell.z;
             v[k] = c3;
@@ -135,24 +142,46 @@ bool upload_tables(std::string &err) {
 
 }  // namespace
 
-int marching_cubes_run(const float2 *vol, Dims d, float3 size, const float *R, const float *t, float4 *verts, float4 *normals,
-                       int vertex_cap, int *n_vertices, int *occ_voxel, int *occ_cube, int *occ_nverts, int voxel_cap, int *n_voxels,
-                       cudaStream_t st, std::string &err) {
-    if (!upload_tables(err)) return -2;
-    const size_t n = (size_t)d.X * d.Y * d.Z;
+// scratch (counts + scan + cub temp), kept between calls and grown on demand: a cudaMalloc/cudaFree pair per frame would
+// serialise the device twice per extraction
+struct McScratch {
+    std::mutex mu;
+    int device = -1;
     unsigned long long *buf = nullptr;
+    size_t buf_elems = 0;
     void *tmp = nullptr;
     size_t tmp_bytes = 0;
+};
+static McScratch g_mc;
+
+int marching_cubes_run(const float2 *vol, Dims dg, int z0, int nz, int nz_avail, float3 size, const float *R, const float *t,
+                       float4 *verts, float4 *normals, int vertex_cap, int *n_vertices, int *occ_voxel, int *occ_cube,
+                       int *occ_nverts, int voxel_cap, int *n_voxels, cudaStream_t st, std::string &err) {
+    if (!upload_tables(err)) return -2;
+    const Dims d{dg.X, dg.Y, nz_avail};               // what is addressable at `vol`
+    const size_t n = (size_t)d.X * d.Y * nz;
+    if (n > 0x7fffffffull) { err = "marching cubes: more than 2^31 voxels in one call"; return -1; }
+    std::lock_guard<std::mutex> lock(g_mc.mu);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int)n, st);
-    if (cudaMalloc(&buf, 2 * n * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&tmp, tmp_bytes) != cudaSuccess) {
-        err = std::string("marching cubes scratch: ") + cudaGetErrorString(cudaGetLastError());
-        cudaFree(buf);
-        return -3;
+    if (g_mc.device != dev || g_mc.buf_elems < 2 * n || g_mc.tmp_bytes < tmp_bytes) {
+        if (g_mc.device == dev) { cudaFree(g_mc.buf); cudaFree(g_mc.tmp); }      // another device's scratch is left to that device
+        g_mc.buf = nullptr; g_mc.tmp = nullptr; g_mc.buf_elems = 0; g_mc.tmp_bytes = 0; g_mc.device = dev;
+        if (cudaMalloc(&g_mc.buf, 2 * n * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&g_mc.tmp, tmp_bytes) != cudaSuccess) {
+            err = std::string("marching cubes scratch: ") + cudaGetErrorString(cudaGetLastError());
+            cudaFree(g_mc.buf);
+            g_mc.buf = nullptr; g_mc.tmp = nullptr;
+            return -3;
+        }
+        g_mc.buf_elems = 2 * n;
+        g_mc.tmp_bytes = tmp_bytes;
     }
-    unsigned long long *counts = buf, *scan = buf + n;
+    unsigned long long *counts = g_mc.buf, *scan = g_mc.buf + n;
     const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
-    classify_kernel<<<grid, 256, 0, st>>>(vol, d, counts);
-    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, scan, (int)n, st);
+    classify_kernel<<<grid, 256, 0, st>>>(vol, d, nz, counts);
+    cub::DeviceScan::ExclusiveSum(g_mc.tmp, tmp_bytes, counts, scan, (int)n, st);
     unsigned long long last[2] = {0, 0};
     cudaMemcpyAsync(&last[0], counts + n - 1, 8, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(&last[1], scan + n - 1, 8, cudaMemcpyDeviceToHost, st);
@@ -165,11 +194,11 @@ int marching_cubes_run(const float2 *vol, Dims d, float3 size, const float *R, c
         Pose pose;
         for (int i = 0; i < 9; ++i) pose.R[i] = R[i];
         for (int i = 0; i < 3; ++i) pose.t[i] = t[i];
-        // cell size as generateTriangles computes it (marching_cubes.cu:292-294): fp32 division on the host
-        const float3 cell = make_float3(size.x / d.X, size.y / d.Y, size.z / d.Z);
+        // cell size as generateTriangles computes it (marching_cubes.cu:292-294): fp32 division on the host, GLOBAL dims
+        const float3 cell = make_float3(size.x / dg.X, size.y / dg.Y, size.z / dg.Z);
         if (nvox > 0 && (verts || occ_voxel))
-            triangles_kernel<<<grid, 256, 0, st>>>(vol, d, cell, pose, counts, scan, verts, normals, vertex_cap, occ_voxel, occ_cube,
-                                                   occ_nverts, voxel_cap);
+            triangles_kernel<<<grid, 256, 0, st>>>(vol, d, nz, z0, cell, pose, counts, scan, verts, normals, vertex_cap, occ_voxel,
+                                                   occ_cube, occ_nverts, voxel_cap);
         e = cudaStreamSynchronize(st);
         if (nvox > voxel_cap) nvox = voxel_cap;
         if (n_voxels) *n_voxels = nvox;
@@ -179,8 +208,6 @@ int marching_cubes_run(const float2 *vol, Dims d, float3 size, const float *R, c
         err = std::string("marching cubes: ") + cudaGetErrorString(e);
         rc = -2;
     }
-    cudaFree(buf);
-    cudaFree(tmp);
     return rc;
 }
 

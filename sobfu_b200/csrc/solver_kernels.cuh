@@ -79,8 +79,16 @@ struct LoopArgs {
     const unsigned long long *allmax;        // own table [iteration][rank]
     unsigned long long *peer_error;          // own control block: set when a wait timed out
     int peer_n;                              // > 0: peer mode with this many ranks
-    int push;                                // pass B: this launch covers the slab faces (stores to the neighbours, bumps their counters)
-    int wait_halo;                           // pass A: this launch reads halo planes
+    // Peer mode runs an iteration as TWO launches: work items carry a face tag (ZRanges::face).  Pass A handles the middle of
+    // the slab first and the items that read halo planes last (they wait for the neighbours' counters and acknowledge when
+    // they are done); pass B handles the face items first (they wait for the acknowledgements, store into the neighbours and
+    // bump their counters as soon as the item is finished -- the halo travels while the middle of the slab is computed).
+    int push;                                // pass B: face items store to the neighbours and count there (per ITEM)
+    int wait_halo;                           // pass A: face items wait on my_cnt / acknowledge in ack_lo / ack_hi (per ITEM)
+    // publication of this rank's maximum of iteration `it` by the last CTA of pass B (ticket), into every rank's table
+    unsigned int *tickets;                   // [max_iter], zeroed per solve; null: no publication (time_loop mode / NCCL mode)
+    unsigned long long *pub[16];             // every rank's allmax table (own included)
+    int my_rank;
 };
 
 // control block of one rank in peer mode, exported through CUDA IPC; `allmax[max_iter * nranks]` follows the header
@@ -118,9 +126,18 @@ SB_DEV unsigned long long peer_wait_ge(const unsigned long long *p, unsigned lon
 }
 
 // z ranges (local planes) a launch works on: the whole slab, or the planes next to / away from the slab faces
+// face: 0 = no neighbour involved, 1 = next to the lower neighbour, 2 = next to the upper one (peer mode only).  Work items
+// are issued in the order of the ranges.
+constexpr int MAX_ZRANGES = 3;
 struct ZRanges {
     int n;
-    int lo[2], hi[2];
+    int lo[MAX_ZRANGES], hi[MAX_ZRANGES];
+    int face[MAX_ZRANGES];
+};
+// what a launch did: grid size and the number of work items per face tag (the units of the peer counters)
+struct LaunchInfo {
+    int grid;
+    int face_items[3];
 };
 
 // decision shared by every block of iteration `it` (0-based): has the loop already ended?
@@ -159,8 +176,8 @@ bool tiled_supported(const Dims d);
 struct TmaMaps;   // opaque: CUtensorMaps of the nabla_U components (pass B) and of the psi / w planes (pass A)
 TmaMaps *tma_maps_create(const LoopArgs &a);
 void tma_maps_destroy(TmaMaps *m);
-int launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, const ZRanges &zr, cudaStream_t st);   // returns the grid size
-int launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, const ZRanges &zr, cudaStream_t st);    // returns the grid size (0: generic path)
+LaunchInfo launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, const ZRanges &zr, cudaStream_t st);
+LaunchInfo launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, const ZRanges &zr, cudaStream_t st);   // grid 0: generic path
 
 // free-standing field kernels (field_ops.cu)
 void launch_init_identity(float4 *psi, Dims d, cudaStream_t st);

@@ -22,6 +22,10 @@
 // (nabla_U 12, psi 12 + 12); the reference's layouts and kernel split would need 48 + 64.  Results are bit-identical to the
 // generic kernels and to the oracle (tests/test_parity_gpu.py).
 #include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "solver_kernels.cuh"
 #include "tma_utils.cuh"
@@ -36,11 +40,11 @@ struct TmaMaps {
 
 namespace {
 
-// work items = (x tile, y tile, z chunk) over up to two z ranges of the slab
+// work items = (x tile, y tile, z chunk) over up to three z ranges of the slab, issued range by range
 struct Sched {
     int tiles_x, tiles_y, nitems;
     int nr;
-    int zlo[2], zhi[2], nz[2], zchunk[2];
+    int zlo[3], zhi[3], nz[3], zchunk[3], face[3];
 };
 
 SB_DEVI float c4(const float4 &v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
@@ -96,7 +100,7 @@ SB_DEVI float warp_sample_tex(cudaTextureObject_t tex, int ashift, int amask, fl
 // position of a CTA in its plane stream: work item -> tile origin and plane range [p, p_last]
 template <int TX, int TY, int LO, int HI>
 struct Stream {
-    int item, p, p_last, x0t, y0t, zb, ze;
+    int item, p, p_last, x0t, y0t, zb, ze, face;
     SB_DEVI void open(int it, const Sched &sc, int Z) {
         item = it;
         if (item >= sc.nitems) return;
@@ -106,11 +110,13 @@ struct Stream {
         const int tyi = rem / sc.tiles_x;
         x0t = (rem - tyi * sc.tiles_x) * TX;
         y0t = tyi * TY;
-        const bool r = tz >= sc.nz[0];          // second range? (no dynamic indexing: the schedule stays in registers)
-        tz -= r ? sc.nz[0] : 0;
-        const int chunk = r ? sc.zchunk[1] : sc.zchunk[0];
-        zb = (r ? sc.zlo[1] : sc.zlo[0]) + tz * chunk;
-        ze = min(zb + chunk, r ? sc.zhi[1] : sc.zhi[0]);
+        // which range? (no dynamic indexing: the schedule stays in registers)
+        const bool r1 = tz >= sc.nz[0], r2 = tz >= sc.nz[0] + sc.nz[1];
+        tz -= r2 ? sc.nz[0] + sc.nz[1] : (r1 ? sc.nz[0] : 0);
+        const int chunk = r2 ? sc.zchunk[2] : (r1 ? sc.zchunk[1] : sc.zchunk[0]);
+        zb = (r2 ? sc.zlo[2] : (r1 ? sc.zlo[1] : sc.zlo[0])) + tz * chunk;
+        ze = min(zb + chunk, r2 ? sc.zhi[2] : (r1 ? sc.zhi[1] : sc.zhi[0]));
+        face = r2 ? sc.face[2] : (r1 ? sc.face[1] : sc.face[0]);
         (void)Z;
         p = zb - LO;
         p_last = ze - 1 + HI;
@@ -175,10 +181,6 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
 #pragma unroll
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NW); }
         mbar_fence_init();
-        if (a.push) {   // peer mode: the neighbours have read the halo planes this launch is about to overwrite
-            if (a.peer_lo[0]) peer_wait_ge(a.my_ack + 0, a.expect_ack, a.peer_error);
-            if (a.peer_hi[0]) peer_wait_ge(a.my_ack + 1, a.expect_ack, a.peer_error);
-        }
     }
     __syncthreads();
 
@@ -237,11 +239,18 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
     unsigned best_bits = 0u, best_idx = 0u;
     const unsigned zoff = (unsigned)a.z0 * (unsigned)XY;
     float4 win[7][3];                     // nabla_U of this thread's 4 voxels at planes c-3 .. c+3
+    int ack_seen = 0;                     // faces whose acknowledgement this CTA has already waited for
     St cs;
     for (cs.open(blockIdx.x, sc, d.Z); cs.valid(sc); cs.open(cs.item + (int)gridDim.x, sc, d.Z)) {
         const int x0 = cs.x0t + 4 * lx, y = cs.y0t + ty;
         const bool active = x0 < X && y < d.Y;
         const int row = min(x0, X - 4) + X * min(y, d.Y - 1);
+        const bool face_item = a.push && cs.face != 0;
+        if (face_item && !(ack_seen & cs.face)) {   // peer mode: the neighbour has read the halo planes this item is about to overwrite
+            if (tid == 0) peer_wait_ge(a.my_ack + (cs.face - 1), a.expect_ack, a.peer_error);
+            asm volatile("bar.sync 1, %0;" ::"r"(NW * 32) : "memory");
+            ack_seen |= cs.face;
+        }
         for (int p = cs.p; p <= cs.p_last; ++p) {
             const unsigned slot = q % NSTAGE;
             const int zc = p - 3;         // centre plane whose window is complete with plane p
@@ -318,20 +327,31 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
             __syncwarp();
             if (lane == 0 && q >= 4u) mbar_arrive(empty0 + 8 * ((q - 4u) % NSTAGE));
         }
+        if (face_item) {   // the planes of this item are in the neighbour's halo: count the item there
+            __threadfence_system();                                      // this thread's stores to the neighbour are performed ...
+            asm volatile("bar.sync 1, %0;" ::"r"(NW * 32) : "memory");
+            if (tid == 0) {                                              // ... before the neighbour can see the item counted
+                if (cs.face == 1 && a.cnt_lo) atomicAdd_system(a.cnt_lo, 1ull);
+                if (cs.face == 2 && a.cnt_hi) atomicAdd_system(a.cnt_hi, 1ull);
+            }
+        }
     }
     unsigned long long best = best_bits ? (((unsigned long long)best_bits << 32) | (unsigned long long)(0xffffffffu - rank_of(best_idx, a.rm))) : 0ull;
     best = warp_max_u64(best);
     if (lane == 0) skey[warp] = best;
-    if (a.push) __threadfence_system();                          // this thread's stores to the neighbours are performed ...
     asm volatile("bar.sync 1, %0;" ::"r"(NW * 32) : "memory");   // consumers only (the producer warp has left)
     if (tid == 0) {
         unsigned long long m = 0ull;
 #pragma unroll
         for (int k = 0; k < NW; ++k) m = skey[k] > m ? skey[k] : m;
         atomicMax(&a.maxkey[it], m);
-        if (a.push) {                                            // ... before the neighbours can see this CTA counted
-            if (a.cnt_hi) atomicAdd_system(a.cnt_hi, 1ull);
-            if (a.cnt_lo) atomicAdd_system(a.cnt_lo, 1ull);
+        if (a.tickets) {   // peer mode: the last CTA of the launch publishes this rank's maximum into every rank's table
+            __threadfence();
+            if (atomicAdd(&a.tickets[it], 1u) == gridDim.x - 1u) {
+                const unsigned long long v = atomicMax(&a.maxkey[it], 0ull) | PEER_VALID;
+                for (int r = 0; r < a.peer_n; ++r)
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.pub[r] + (size_t)it * a.peer_n + a.my_rank), "l"(v) : "memory");
+            }
         }
     }
 }
@@ -399,19 +419,23 @@ __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
 #pragma unroll
         for (int s = 0; s < NSTAGE; ++s) mbar_init(full0 + 8 * s, 1);
         mbar_fence_init();
-        if (a.wait_halo) {   // peer mode: the neighbours' pass B of the previous iteration stored into this rank's halo planes
-            if (a.expect_lo) peer_wait_ge(a.my_cnt + 0, a.expect_lo, a.peer_error);
-            if (a.expect_hi) peer_wait_ge(a.my_cnt + 1, a.expect_hi, a.peer_error);
-            asm volatile("fence.proxy.async;" ::: "memory");     // the planes are read by TMA (async proxy)
-        }
     }
     __syncthreads();
 
     typedef Stream<TX, TY, 1, 1> St;
     St pr;                                    // position of the feeder (thread 0) in the CTA's plane stream
     unsigned qi = 0;
+    int halo_seen = 0;                        // faces whose halo counter thread 0 has already waited for
     auto feed = [&]() {
         if (!pr.valid(sc)) return;
+        if (a.wait_halo && pr.face != 0 && !(halo_seen & pr.face)) {
+            // peer mode: the first item of this CTA that reads the halo planes of that face -- the neighbour's pass B of the
+            // previous iteration has stored into them once the counter says so
+            const unsigned long long want = pr.face == 1 ? a.expect_lo : a.expect_hi;
+            if (want) peer_wait_ge(a.my_cnt + (pr.face - 1), want, a.peer_error);
+            asm volatile("fence.proxy.async;" ::: "memory");     // the planes are read by TMA (async proxy)
+            halo_seen |= pr.face;
+        }
         const unsigned slot = qi % NSTAGE, dst = smem + slot * STAGE_BYTES, bar = full0 + 8 * slot;
         mbar_expect_tx(bar, TX_BYTES);
         // the box starts 4 floats / 1 row before the tile (out-of-range elements arrive as zeros); the psi planes are
@@ -592,12 +616,11 @@ __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
             }
             wm = wc; wc = wp;
         }
-    }
-    if (a.wait_halo) {   // peer mode: this CTA no longer reads the halo planes -- the neighbours may overwrite them
-        __syncthreads();
-        if (tid == 0) {
-            if (a.ack_lo) atomicAdd_system(a.ack_lo, 1ull);
-            if (a.ack_hi) atomicAdd_system(a.ack_hi, 1ull);
+        // peer mode: every plane of this item has been staged (thread 0 waited for the last one itself), so the item no longer
+        // reads the halo planes -- tell the neighbour on that face that it may overwrite them
+        if (a.wait_halo && cs.face != 0 && tid == 0) {
+            if (cs.face == 1 && a.ack_lo) atomicAdd_system(a.ack_lo, 1ull);
+            if (cs.face == 2 && a.ack_hi) atomicAdd_system(a.ack_hi, 1ull);
         }
     }
 }
@@ -614,7 +637,10 @@ int sm_count() {
     return sms;
 }
 
-// number of z chunks per range: fill whole rounds of `ctas` CTAs, chunks of >= 16 planes, few halo planes per chunk
+// Number of z chunks per range.  The CTAs take items round robin (item b, b + G, ...), ranges in the given order; a chunk of
+// c planes costs c + halo_planes * halo_cost plane-steps.  Ranges of fewer than 16 planes stay one chunk; for the others the
+// chunk count that minimises the busiest CTA's load -- given the items already placed before it -- is taken (chunks of >= 16
+// planes -- 8 for ranges under 64 planes -- so that the pipeline prologue stays a small share).
 Sched make_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_planes, double halo_cost, int ctas) {
     Sched s;
     s.tiles_x = (d.X + TX - 1) / TX;
@@ -622,27 +648,64 @@ Sched make_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_plane
     const int xy = s.tiles_x * s.tiles_y;
     s.nr = zr.n;
     s.nitems = 0;
-    for (int r = 0; r < 2; ++r) { s.zlo[r] = s.zhi[r] = 0; s.nz[r] = 0; s.zchunk[r] = 1; }
-    for (int r = 0; r < zr.n; ++r) {
+    for (int r = 0; r < 3; ++r) { s.zlo[r] = s.zhi[r] = 0; s.nz[r] = 0; s.zchunk[r] = 1; s.face[r] = 0; }
+    std::vector<double> load(ctas, 0.0), trial(ctas);
+    for (int r = 0; r < zr.n && r < MAX_ZRANGES; ++r) {
         const int Z = zr.hi[r] - zr.lo[r];
-        s.zlo[r] = zr.lo[r]; s.zhi[r] = zr.hi[r];
+        s.zlo[r] = zr.lo[r]; s.zhi[r] = zr.hi[r]; s.face[r] = zr.face[r];
         if (Z <= 0) continue;
         int best_nz = 1;
-        double best_score = -1.0;
+        double best_score = 1e300;
+        const int min_chunk = Z < 64 ? 8 : 16;      // thin slabs (many ranks): parallelism matters more than the prologue share
         for (int nz = 1; nz <= 64; ++nz) {
             const int chunk = (Z + nz - 1) / nz;
-            if (chunk < 16 && nz > 1) break;
-            const int n = xy * ((Z + chunk - 1) / chunk);
-            const int rounds = (n + ctas - 1) / ctas;
-            const double balance = (double)n / ((double)rounds * ctas);
-            const double overlap = (double)chunk / (chunk + halo_planes * halo_cost);
-            if (balance * overlap > best_score) { best_score = balance * overlap; best_nz = nz; }
+            if (chunk < min_chunk && nz > 1) break;
+            const int nch = (Z + chunk - 1) / chunk;
+            trial = load;
+            int item = s.nitems;
+            for (int k = 0; k < nch; ++k) {
+                const int planes = (k + 1 < nch ? chunk : Z - chunk * (nch - 1));
+                const double cost = planes + halo_planes * halo_cost;
+                for (int t = 0; t < xy; ++t, ++item) trial[item % ctas] += cost;
+            }
+            double worst = 0.0;
+            for (int b = 0; b < ctas; ++b) worst = trial[b] > worst ? trial[b] : worst;
+            if (worst < best_score - 1e-9) { best_score = worst; best_nz = nz; }
         }
         s.zchunk[r] = (Z + best_nz - 1) / best_nz;
         s.nz[r] = (Z + s.zchunk[r] - 1) / s.zchunk[r];
+        int item = s.nitems;
+        for (int k = 0; k < s.nz[r]; ++k) {
+            const int planes = (k + 1 < s.nz[r] ? s.zchunk[r] : Z - s.zchunk[r] * (s.nz[r] - 1));
+            for (int t = 0; t < xy; ++t, ++item) load[item % ctas] += planes + halo_planes * halo_cost;
+        }
         s.nitems += xy * s.nz[r];
     }
     return s;
+}
+
+// the schedule depends on the shape and the ranges only: computed once per distinct launch geometry (the solver thread only)
+Sched cached_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_planes, double halo_cost, int ctas) {
+    struct Key { int v[16]; };
+    static std::vector<std::pair<Key, Sched>> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    Key k{};
+    k.v[0] = d.X; k.v[1] = d.Y; k.v[2] = d.Z; k.v[3] = TX; k.v[4] = TY; k.v[5] = ctas; k.v[6] = zr.n;
+    for (int r = 0; r < MAX_ZRANGES; ++r) { k.v[7 + 3 * r] = r < zr.n ? zr.lo[r] : 0; k.v[8 + 3 * r] = r < zr.n ? zr.hi[r] : 0; k.v[9 + 3 * r] = r < zr.n ? zr.face[r] : 0; }
+    for (auto &e : cache)
+        if (!memcmp(&e.first, &k, sizeof k)) return e.second;
+    const Sched sc = make_sched(d, zr, TX, TY, halo_planes, halo_cost, ctas);
+    if (cache.size() > 64) cache.clear();
+    cache.emplace_back(k, sc);
+    return sc;
+}
+
+LaunchInfo launch_info(const Sched &sc, int grid) {
+    LaunchInfo li{grid, {0, 0, 0}};
+    for (int r = 0; r < 3; ++r)
+        if (sc.face[r] >= 0 && sc.face[r] < 3) li.face_items[sc.face[r]] += sc.tiles_x * sc.tiles_y * sc.nz[r];
+    return li;
 }
 
 }  // namespace
@@ -674,28 +737,28 @@ TmaMaps *tma_maps_create(const LoopArgs &a) {
 
 void tma_maps_destroy(TmaMaps *m) { delete m; }
 
-int launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, const ZRanges &zr, cudaStream_t st) {
+LaunchInfo launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, const ZRanges &zr, cudaStream_t st) {
     const int ctas = sm_count();
-    const Sched sc = make_sched(a.d, zr, pb::TX, pb::TY, 6, 0.35, ctas);
-    if (sc.nitems == 0) return 0;
+    const Sched sc = cached_sched(a.d, zr, pb::TX, pb::TY, 6, 0.35, ctas);
+    if (sc.nitems == 0) return LaunchInfo{0, {0, 0, 0}};
     const int grid = sc.nitems < ctas ? sc.nitems : ctas;
     pb::pass_b_tma_kernel<<<grid, (pb::NW + 1) * 32, pb::SMEM_BYTES, st>>>(m->g[0], m->g[1], m->g[2], m->pb_psi[0], m->pb_psi[1], m->pb_psi[2], a, it, sc);
-    return grid;
+    return launch_info(sc, grid);
 }
 
-int launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, const ZRanges &zr, cudaStream_t st) {
+LaunchInfo launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, const ZRanges &zr, cudaStream_t st) {
     if (log) {   // logging iterations (rare): materialise the warped plane, then the generic kernel that also sums the energies
         launch_initial_warp(a, st);
         launch_pass_a_generic(a, it, 1, st);
-        return 0;
+        return LaunchInfo{0, {0, 0, 0}};
     }
     const int ctas = PA_CTAS * sm_count();
-    const Sched sc = make_sched(a.d, zr, pa::TX, pa::TY, 2, 0.5, ctas);
-    if (sc.nitems == 0) return 0;
+    const Sched sc = cached_sched(a.d, zr, pa::TX, pa::TY, 2, 0.5, ctas);
+    if (sc.nitems == 0) return LaunchInfo{0, {0, 0, 0}};
     const int grid = sc.nitems < ctas ? sc.nitems : ctas;
     if (a.pn_tex) pa::pass_a_tma_kernel<true><<<grid, pa::NTHREADS, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
     else pa::pass_a_tma_kernel<false><<<grid, pa::NTHREADS, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
-    return grid;
+    return launch_info(sc, grid);
 }
 
 }  // namespace sb

@@ -30,6 +30,36 @@ def broadcast_unique_id(dist, src=0):
     return buf[0]
 
 
+def slab_offsets(counts):
+    """exclusive prefix sum over the ranks' vertex counts: where each rank's triangles start in the concatenated mesh
+    ('MC needs a +1 z-plane halo and a cross-GPU exclusive offset, done on the host over G counts')"""
+    out, acc = [], 0
+    for c in counts:
+        out.append(acc)
+        acc += int(c)
+    return out, acc
+
+
+def upper_halo_plane(dist, slab, rank, nranks):
+    """slab [nz, Y, X, 2] -> [nz + 1, Y, X, 2] with the first plane of the upper neighbour appended (last rank: unchanged).
+    One plane travels down per rank; works with the nccl backend (device tensors) and gloo (host tensors)."""
+    import torch
+    if nranks == 1:
+        return slab
+    reqs = []
+    out = slab
+    if rank < nranks - 1:
+        out = torch.empty((slab.shape[0] + 1,) + tuple(slab.shape[1:]), dtype=slab.dtype, device=slab.device)
+        out[:-1].copy_(slab)
+        reqs.append(dist.irecv(out[-1], src=rank + 1))
+    if rank > 0:
+        first = slab[0].contiguous()
+        reqs.append(dist.isend(first, dst=rank - 1))
+    for r in reqs:
+        r.wait()
+    return out
+
+
 class SlabSolver(Solver):
     """sobfu::cuda::Solver on a z-slab.  estimate_psi takes slab-local volumes/fields except phi_n (whole volume)."""
 
@@ -90,6 +120,9 @@ class SlabFusion:
         self.slab_params.volume_size = (params.volume_size[0], params.volume_size[1], float(params.voxel_sizes()[2]) * self.nz)
         self.frame_counter_ = 0
         self.poses_ = [Affine3f()]
+        from .api import MarchingCubes
+        self.mc = MarchingCubes()
+        self.mc.setPose(params.volume_pose)
         self._T, self._D = TsdfVolume, DeformationField
         self.phi_global = self.phi_global_psi_inv = self.phi_n = self.phi_n_psi = None
         self.psi = self.psi_inv = self.solver = None
@@ -127,3 +160,52 @@ class SlabFusion:
         self.phi_global.integrate(self.phi_n_psi)
         self.frame_counter_ += 1
         return True
+
+    # ---- meshes (SobFusion::get_phi_*_mesh, sob_fusion.cpp:147-183): marching cubes per slab ----
+    def slab_mesh(self, vol, vertex_cap=None):
+        """this rank's part of the zero level set of a slab volume: (vertices [n,4], normals [n,4], offset, total) where
+        `offset` is the position of the rank's first vertex in the mesh of the whole volume and `total` its vertex count.
+        The parts concatenated in rank order are bit-identical to marching cubes on the whole volume on one GPU."""
+        import torch
+        p = self.params
+        slab = upper_halo_plane(self.dist, vol.data(), self.rank, self.nranks)
+        verts, normals = self.mc.run_slab(slab, p.volume_dims, p.volume_size, self.z0, self.nz, vertex_cap)
+        counts = [None] * self.nranks
+        self.dist.all_gather_object(counts, int(verts.shape[0]))
+        offs, total = slab_offsets(counts)
+        return verts, normals, offs[self.rank], total
+
+    def gather_mesh(self, vol, dst=0, vertex_cap=None):
+        """the whole mesh on rank `dst` (vertices, normals), None elsewhere -- for export"""
+        import torch
+        verts, normals, off, total = self.slab_mesh(vol, vertex_cap)
+        counts = [None] * self.nranks
+        self.dist.all_gather_object(counts, int(verts.shape[0]))
+        if self.rank == dst:
+            V = torch.empty((total, 4), dtype=torch.float32, device=verts.device)
+            Nn = torch.empty((total, 4), dtype=torch.float32, device=verts.device)
+            offs, _ = slab_offsets(counts)
+            reqs = []
+            for r in range(self.nranks):
+                if r == dst:
+                    V[offs[r]:offs[r] + counts[r]].copy_(verts)
+                    Nn[offs[r]:offs[r] + counts[r]].copy_(normals)
+                elif counts[r] > 0:
+                    reqs.append(self.dist.irecv(V[offs[r]:offs[r] + counts[r]], src=r))
+                    reqs.append(self.dist.irecv(Nn[offs[r]:offs[r] + counts[r]], src=r))
+            for q in reqs:
+                q.wait()
+            return V, Nn
+        if verts.shape[0] > 0:
+            self.dist.send(verts.contiguous(), dst=dst)
+            self.dist.send(normals.contiguous(), dst=dst)
+        return None
+
+    def get_phi_global_mesh(self):
+        return self.slab_mesh(self.phi_global)
+
+    def get_phi_global_psi_inv_mesh(self):
+        return self.slab_mesh(self.phi_global_psi_inv)
+
+    def get_phi_n_psi_mesh(self):
+        return self.slab_mesh(self.phi_n_psi)

@@ -109,3 +109,34 @@ def test_gpu_marching_cubes_matches_the_reference_cuda(built):
     hits = sum(t in ours for t in theirs)
     print("reference triangles %d, ours %d, reference triangles found in ours bit-exactly: %d" % (len(theirs), len(ours), hits))
     assert hits >= 0.98 * len(theirs)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_gpu_slab_marching_cubes_concatenates_to_the_whole_volume(built, nranks):
+    """marching cubes per z-slab (+1 plane of the upper neighbour); the parts in rank order == one-GPU output"""
+    import torch
+    import sobfu_b200 as sf
+    from sobfu_b200.parallel import slab_offsets, slab_range
+    dims = (40, 36, 32)
+    vol, vs = sphere_volume(dims)
+    vol[5:9, 5:9, 5:9, 1] = 0
+    size = tuple(float(vs[i]) * dims[i] for i in range(3))
+    p = sf.Params(volume_dims=dims, volume_size=size, tsdf_trunc_dist=1.0, eta=1.0, tsdf_max_weight=1.0)
+    v = sf.TsdfVolume(p)
+    v.data().copy_(torch.from_numpy(vol))
+    mc = sf.MarchingCubes()
+    mc.setPose(sf.Affine3f().translate((-0.1, 0.05, 0.3)))
+    verts, normals, occ = mc.run(v, return_occupied=True)
+    parts = []
+    for r in range(nranks):
+        z0, nz = slab_range(dims[2], r, nranks)
+        avail = nz + (1 if r < nranks - 1 else 0)
+        slab = v.data()[z0:z0 + avail].contiguous()
+        parts.append(mc.run_slab(slab, dims, size, z0, nz, return_occupied=True))
+    offs, total = slab_offsets([q[0].shape[0] for q in parts])
+    assert total == verts.shape[0] and offs[0] == 0
+    assert torch.equal(torch.cat([q[0] for q in parts]), verts)
+    assert torch.equal(torch.cat([q[1] for q in parts]), normals)
+    assert torch.equal(torch.cat([q[2] for q in parts], dim=1), occ)        # global voxel ids, cube indices, vertex counts
+    assert all(q[0].shape[0] > 0 for q in parts)

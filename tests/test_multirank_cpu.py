@@ -60,6 +60,22 @@ WORKER = textwrap.dedent('''
     err = float(np.abs(own - ref["psi"][z0:z0 + nz]).max())
     assert err < 1e-5, err
     print("rank", rank, "slab", (z0, nz), "max |psi_slab - psi_oracle| =", err)
+    # (3) marching cubes per slab: one plane of the upper neighbour travels down, vertex offsets = exclusive sum over the ranks
+    from sobfu_b200.parallel import upper_halo_plane, slab_offsets
+    slab = upper_halo_plane(dist, torch.from_numpy(np.ascontiguousarray(pg[z0:z0 + nz])), rank, world).numpy()
+    assert slab.shape[0] == nz + (1 if rank < world - 1 else 0)
+    if rank < world - 1:
+        assert np.array_equal(slab[-1], pg[z0 + nz])
+    vox, cube, nvt = orc.mc_occupied(np.ascontiguousarray(slab))
+    keep = vox < nz * X * Y                       # cells whose lower corner this rank owns
+    vox, cube, nvt = vox[keep] + z0 * X * Y, cube[keep], nvt[keep]
+    parts = [None] * world
+    dist.all_gather_object(parts, (vox, cube, nvt))
+    fv, fc, fn = orc.mc_occupied(pg)
+    assert np.array_equal(np.concatenate([q[0] for q in parts]), fv) and np.array_equal(np.concatenate([q[1] for q in parts]), fc)
+    offs, total = slab_offsets([int(q[2].sum()) for q in parts])
+    assert total == int(fn.sum()) and offs[0] == 0 and offs[rank] == int(fn[fv < z0 * X * Y].sum())
+    print("rank", rank, "slab mesh offset", offs[rank], "of", total)
     dist.destroy_process_group()
 ''')
 
@@ -73,6 +89,7 @@ def test_two_rank_slab_scheme_on_gloo(built, tmp_path):
                         "--master-port", "29533", str(script)], capture_output=True, text=True, env=env, timeout=560)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("max |psi_slab - psi_oracle|") == 2
+    assert r.stdout.count("slab mesh offset") == 2
 
 
 def test_slab_range_rejects_bad_partitions(built):
