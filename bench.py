@@ -227,7 +227,7 @@ def run_ours(args, rank, world, torch, dist):
     }
     if rank == 0:
         if world > 1:
-            peer = bool(getattr(fusion.solver, "peer", False)) and not os.environ.get("SOBFU_B200_NO_PEER")
+            peer = bool(getattr(fusion.solver, "peer", False))
             out["config"]["multi_gpu"] = ("z-slab of %d planes per GPU; nabla_U on the 3 halo planes is recomputed locally, so an iteration needs "
                                           "one psi halo exchange (4 planes) + one scalar MAX; " % (dim // world)) + (
                 "peer mode: pass B on the slab faces stores the planes straight into the neighbours' halo planes over NVLink (CUDA IPC) and "

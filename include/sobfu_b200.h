@@ -176,7 +176,9 @@ int sobfu_b200_solver_attach_comm(sobfu_b200_solver *s, const void *id128_host, 
  * pass A does the middle of the slab first and the halo-reading work items last, pass B the face items first, so the halo
  * planes travel while the middle of the slab is computed.
  *   every rank: peer_export(block);  launcher: all-gather the blocks (rank-major);  every rank: peer_attach(all blocks).
- * Optional: without it (or with SOBFU_B200_NO_PEER set, or when attach fails) the solver keeps exchanging over NCCL.
+ * Optional: without it (or with SOBFU_B200_NO_PEER set, or when attach fails) the solver keeps exchanging over NCCL -- which
+ * is what the Python launcher does unless SOBFU_B200_PEER is set: on B200 the NCCL exchange overlapped on a second stream
+ * measured faster at 2 and 4 GPUs (256^3: 4528 vs 4351, 7496 vs 6755 iterations/s).
  * Results are bit-identical in both modes.  Replaces nothing in the reference (single GPU, solver.cu:85-205). */
 #define SOBFU_B200_PEER_HANDLE_BYTES 128
 int sobfu_b200_solver_peer_export(sobfu_b200_solver *s, void *handle_block_host);

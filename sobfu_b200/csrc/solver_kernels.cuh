@@ -113,7 +113,8 @@ SB_DEV unsigned long long global_timer_ns() {
 }
 // spins until *p >= want (counters) -- bounded: after 4 s the error word of the control block is set and the caller goes on
 // (the host reports SOBFU_B200_ECOMM), so a lost peer cannot hang the GPU
-SB_DEV unsigned long long peer_wait_ge(const unsigned long long *p, unsigned long long want, unsigned long long *err) {
+// (not inlined: the spin loop stays out of the kernels' steady-state loops, whose code size matters)
+static __device__ __noinline__ unsigned long long peer_wait_ge(const unsigned long long *p, unsigned long long want, unsigned long long *err) {
     unsigned long long v = ld_acquire_sys(p);
     if (v >= want) return v;
     if (err && *reinterpret_cast<volatile unsigned long long *>(err)) return v;   // an earlier wait already gave up: drain quickly

@@ -144,13 +144,16 @@ constexpr int PSI_STAGE_BYTES = 3 * PSI_COMP_BYTES;
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + NPSI * PSI_STAGE_BYTES + 128;
 constexpr unsigned TX_BYTES = 3u * SX * SY * 4u;
 
+// PEER: the peer-mode instantiation (face-tagged items, stores into the neighbours, counters, publication); the plain one
+// carries none of that code
+template <bool PEER>
 __global__ void __launch_bounds__((NW + 1) * 32, 1)
     pass_b_tma_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapy,
                       const __grid_constant__ CUtensorMap mapz, const __grid_constant__ CUtensorMap mpx,
                       const __grid_constant__ CUtensorMap mpy, const __grid_constant__ CUtensorMap mpz, LoopArgs a, int it,
                       Sched sc) {
     bool fin;
-    if (a.peer_n > 0) {      // peer mode: one thread waits for the maxima every rank published, the block follows
+    if (PEER && a.peer_n > 0) {      // peer mode: one thread waits for the maxima every rank published, the block follows
         __shared__ int s_fin;
         if (threadIdx.x == 0) s_fin = loop_finished_peer(a, it) ? 1 : 0;
         __syncthreads();
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
         const int x0 = cs.x0t + 4 * lx, y = cs.y0t + ty;
         const bool active = x0 < X && y < d.Y;
         const int row = min(x0, X - 4) + X * min(y, d.Y - 1);
-        const bool face_item = a.push && cs.face != 0;
+        const bool face_item = PEER && a.push && cs.face != 0;
         if (face_item && !(ack_seen & cs.face)) {   // peer mode: the neighbour has read the halo planes this item is about to overwrite
             if (tid == 0) peer_wait_ge(a.my_ack + (cs.face - 1), a.expect_ack, a.peer_error);
             asm volatile("bar.sync 1, %0;" ::"r"(NW * 32) : "memory");
@@ -305,12 +308,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
                     for (int c = 0; c < 3; ++c)
                         *reinterpret_cast<float4 *>(P[c] + o) = make_float4(np[c][0], np[c][1], np[c][2], np[c][3]);
                     // peer mode: the planes next to a slab face also go straight into the neighbour's halo planes over NVLink
-                    if (a.peer_hi[0] && zc >= d.Z - PSI_HALO) {
+                    if (PEER && a.peer_hi[0] && zc >= d.Z - PSI_HALO) {
 #pragma unroll
                         for (int c = 0; c < 3; ++c)
                             *reinterpret_cast<float4 *>(a.peer_hi[c] + o) = make_float4(np[c][0], np[c][1], np[c][2], np[c][3]);
                     }
-                    if (a.peer_lo[0] && zc < PSI_HALO) {
+                    if (PEER && a.peer_lo[0] && zc < PSI_HALO) {
 #pragma unroll
                         for (int c = 0; c < 3; ++c)
                             *reinterpret_cast<float4 *>(a.peer_lo[c] + o) = make_float4(np[c][0], np[c][1], np[c][2], np[c][3]);
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
 #pragma unroll
         for (int k = 0; k < NW; ++k) m = skey[k] > m ? skey[k] : m;
         atomicMax(&a.maxkey[it], m);
-        if (a.tickets) {   // peer mode: the last CTA of the launch publishes this rank's maximum into every rank's table
+        if (PEER && a.tickets) {   // peer mode: the last CTA of the launch publishes this rank's maximum into every rank's table
             __threadfence();
             if (atomicAdd(&a.tickets[it], 1u) == gridDim.x - 1u) {
                 const unsigned long long v = atomicMax(&a.maxkey[it], 0ull) | PEER_VALID;
@@ -395,7 +398,7 @@ SB_DEVI void sts1(unsigned saddr, float v) { asm volatile("st.shared.f32 [%0], %
 //   central differences of w at zc, nabla_U -> global (+ replicated halo)
 // Tried and measured slower (profiles/r1_tuning_log.md): a producer warp (caps the CTA at 96 registers), all gathers of a
 // step in flight before the first use / across the stencil (more instructions + spills, same stall time), bigger CTAs.
-template <bool TEX>
+template <bool TEX, bool PEER>
 __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
     pass_a_tma_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__ CUtensorMap m1,
                       const __grid_constant__ CUtensorMap m2, LoopArgs a, int it, Sched sc) {
@@ -428,7 +431,7 @@ __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
     int halo_seen = 0;                        // faces whose halo counter thread 0 has already waited for
     auto feed = [&]() {
         if (!pr.valid(sc)) return;
-        if (a.wait_halo && pr.face != 0 && !(halo_seen & pr.face)) {
+        if (PEER && a.wait_halo && pr.face != 0 && !(halo_seen & pr.face)) {
             // peer mode: the first item of this CTA that reads the halo planes of that face -- the neighbour's pass B of the
             // previous iteration has stored into them once the counter says so
             const unsigned long long want = pr.face == 1 ? a.expect_lo : a.expect_hi;
@@ -618,7 +621,7 @@ __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
         }
         // peer mode: every plane of this item has been staged (thread 0 waited for the last one itself), so the item no longer
         // reads the halo planes -- tell the neighbour on that face that it may overwrite them
-        if (a.wait_halo && cs.face != 0 && tid == 0) {
+        if (PEER && a.wait_halo && cs.face != 0 && tid == 0) {
             if (cs.face == 1 && a.ack_lo) atomicAdd_system(a.ack_lo, 1ull);
             if (cs.face == 2 && a.ack_hi) atomicAdd_system(a.ack_hi, 1ull);
         }
@@ -723,9 +726,12 @@ TmaMaps *tma_maps_create(const LoopArgs &a) {
     for (int c = 0; c < 3; ++c) ok = ok && encode_map_3d(&m->g[c], g[c], a.gl.PX, a.gl.PY, a.gl.PZ, pb::SX, pb::SY);
     for (int c = 0; c < 3; ++c) ok = ok && encode_map_3d(&m->in[c], in[c], a.d.X, a.d.Y, a.d.Z + 2 * PSI_HALO, pa::SX, pa::SY);
     for (int c = 0; c < 3; ++c) ok = ok && encode_map_3d(&m->pb_psi[c], in[c], a.d.X, a.d.Y, a.d.Z + 2 * PSI_HALO, pb::TX, pb::TY);
-    ok = ok && cudaFuncSetAttribute(pb::pass_b_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pb::SMEM_BYTES) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(pb::pass_b_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb::SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(pb::pass_b_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb::SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
     if (!ok) {
         fprintf(stderr, "sobfu_b200: TMA tensor maps unavailable; using the generic kernels\n");
         cudaGetLastError();
@@ -742,7 +748,8 @@ LaunchInfo launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, const 
     const Sched sc = cached_sched(a.d, zr, pb::TX, pb::TY, 6, 0.35, ctas);
     if (sc.nitems == 0) return LaunchInfo{0, {0, 0, 0}};
     const int grid = sc.nitems < ctas ? sc.nitems : ctas;
-    pb::pass_b_tma_kernel<<<grid, (pb::NW + 1) * 32, pb::SMEM_BYTES, st>>>(m->g[0], m->g[1], m->g[2], m->pb_psi[0], m->pb_psi[1], m->pb_psi[2], a, it, sc);
+    if (a.peer_n > 0) pb::pass_b_tma_kernel<true><<<grid, (pb::NW + 1) * 32, pb::SMEM_BYTES, st>>>(m->g[0], m->g[1], m->g[2], m->pb_psi[0], m->pb_psi[1], m->pb_psi[2], a, it, sc);
+    else pb::pass_b_tma_kernel<false><<<grid, (pb::NW + 1) * 32, pb::SMEM_BYTES, st>>>(m->g[0], m->g[1], m->g[2], m->pb_psi[0], m->pb_psi[1], m->pb_psi[2], a, it, sc);
     return launch_info(sc, grid);
 }
 
@@ -756,8 +763,11 @@ LaunchInfo launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int lo
     const Sched sc = cached_sched(a.d, zr, pa::TX, pa::TY, 2, 0.5, ctas);
     if (sc.nitems == 0) return LaunchInfo{0, {0, 0, 0}};
     const int grid = sc.nitems < ctas ? sc.nitems : ctas;
-    if (a.pn_tex) pa::pass_a_tma_kernel<true><<<grid, pa::NTHREADS, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
-    else pa::pass_a_tma_kernel<false><<<grid, pa::NTHREADS, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
+    const bool peer = a.peer_n > 0 && a.wait_halo;
+    if (a.pn_tex && peer) pa::pass_a_tma_kernel<true, true><<<grid, pa::NTHREADS, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
+    else if (a.pn_tex) pa::pass_a_tma_kernel<true, false><<<grid, pa::NTHREADS, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
+    else if (peer) pa::pass_a_tma_kernel<false, true><<<grid, pa::NTHREADS, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
+    else pa::pass_a_tma_kernel<false, false><<<grid, pa::NTHREADS, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
     return launch_info(sc, grid);
 }
 

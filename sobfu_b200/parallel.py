@@ -78,7 +78,9 @@ class SlabSolver(Solver):
         the blocks are all-gathered, every rank maps its neighbours.  Returns False (NCCL exchange stays) when the ranks are
         not all on one node / cannot map each other; the decision is collective so that all ranks run the same protocol."""
         import os
-        if os.environ.get("SOBFU_B200_NO_PEER"):
+        # Opt-in: measured on B200 (profiles/r1_tuning_log.md) the NCCL exchange overlapped on a second stream is faster at
+        # 2 and 4 GPUs (256^3: 4528 vs 4351 and 7496 vs 6755 it/s), so it stays the default.
+        if not os.environ.get("SOBFU_B200_PEER") or os.environ.get("SOBFU_B200_NO_PEER"):
             return False
         blk = (C.c_ubyte * 128)()
         ok = lib().sobfu_b200_solver_peer_export(self._h, blk) == 0

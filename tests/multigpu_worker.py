@@ -45,8 +45,33 @@ def main():
             assert abs(a[2] - b[2]) <= 2e-5 * abs(b[2]) + 1e-6 and abs(a[3] - b[3]) <= 2e-5 * abs(b[3]) + 1e-6
         if rank == 0:
             print("slab == single GPU, bit for bit:", dims, "iters", full["info"].iters, "ranks", world, "peer mode:", slab["peer"], flush=True)
+    frames_and_meshes(rank, world)
     dist.barrier()
     dist.destroy_process_group()
+
+
+def frames_and_meshes(rank, world):
+    """SlabFusion (depth frame -> slab TSDF -> slab solve -> slab fusion -> marching cubes per slab) against SobFusion on one GPU"""
+    from sobfu_b200.parallel import SlabFusion
+    import bench
+    p = bench.make_params(sf, 64, 6)
+    p.max_update_norm = -1.0
+    one, slab = sf.SobFusion(p), SlabFusion(p, dist)
+    for f in range(3):
+        d = torch.from_numpy(bench.synth_depth(3 * f).view(np.int16)).cuda().view(torch.uint16)
+        one(d)
+        slab(d)
+    z0, nz = slab.z0, slab.nz
+    for name in ("phi_global", "phi_n_psi", "phi_global_psi_inv"):
+        assert_bits(getattr(slab, name).data().cpu().numpy(), getattr(one, name).data().cpu().numpy()[z0:z0 + nz], "SlabFusion %s rank %d" % (name, rank))
+    V, Nn = one.mc.run(one.phi_global)
+    v, n, off, total = slab.get_phi_global_mesh()
+    assert total == V.shape[0] and total > 1000, (total, V.shape)
+    assert torch.equal(v, V[off:off + v.shape[0]]) and torch.equal(n, Nn[off:off + n.shape[0]])
+    whole = slab.gather_mesh(slab.phi_global, dst=0)
+    if rank == 0:
+        assert torch.equal(whole[0], V) and torch.equal(whole[1], Nn)
+        print("slab meshes == single GPU, bit for bit:", total, "vertices over", world, "ranks", flush=True)
 
 
 def sf_identity(dims):
