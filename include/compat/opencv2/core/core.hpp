@@ -85,32 +85,91 @@ Ptr<T> makePtr(A &&... a) { return Ptr<T>(new T(std::forward<A>(a)...)); }
 
 enum { DECOMP_LU = 0, DECOMP_SVD = 1 };
 
-/* dense n-d float matrix, enough for field download / print helpers (at<T>(k,j,i), ptr<T>()) */
+/* element types as OpenCV encodes them: depth + ((channels - 1) << 3) */
+#ifndef CV_8U
+#define CV_8U 0
+#define CV_8S 1
+#define CV_16U 2
+#define CV_16S 3
+#define CV_32S 4
+#define CV_32F 5
+#define CV_64F 6
+#define CV_MAKETYPE(depth, cn) ((depth) + (((cn) - 1) << 3))
+#define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
+#define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
+#define CV_16UC1 CV_MAKETYPE(CV_16U, 1)
+#endif
+
+struct Size {
+    int width, height;
+    Size() : width(0), height(0) {}
+    Size(int w, int h) : width(w), height(h) {}
+    bool operator==(const Size &o) const { return width == o.width && height == o.height; }
+};
+struct MatStep {
+    size_t v;
+    MatStep(size_t s = 0) : v(s) {}
+    operator size_t() const { return v; }
+};
+
+/* dense matrix with OpenCV's public members (rows, cols, data, step): n-d float fields for the download / print helpers
+ * (at<T>(k,j,i), ptr<T>()) and 8/16-bit images for the application (imread, copyTo with a mask) */
 class Mat {
 public:
-    Mat() : type_(CV_32FC1) {}
+    int rows, cols, dims;
+    unsigned char *data;
+    MatStep step;                                   /* bytes per row (2-d) */
+    Mat() : rows(0), cols(0), dims(0), data(nullptr), type_(CV_32FC1) {}
     Mat(int ndims, const int *sizes, int type) : type_(type) { sz_.assign(sizes, sizes + ndims); alloc(); }
-    Mat(int rows, int cols, int type) : type_(type) { sz_ = {rows, cols}; alloc(); }
+    Mat(int r, int c, int type) : type_(type) { sz_ = {r, c}; alloc(); }
+    Mat(Size s, int type) : type_(type) { sz_ = {s.height, s.width}; alloc(); }
     static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
+    static Mat zeros(Size s, int type) { return Mat(s, type); }
     static Mat eye(int r, int c, int type) { Mat m(r, c, type); for (int i = 0; i < (r < c ? r : c); ++i) m.at<float>(i, i) = 1.f; return m; }
+    int type() const { return type_; }
+    int depth() const { return type_ & 7; }
     int channels() const { return (type_ >> 3) + 1; }
-    size_t elemSize() const { return 4u * channels(); }
-    template <typename T> T *ptr() { return reinterpret_cast<T *>(buf_->data()); }
-    template <typename T> const T *ptr() const { return reinterpret_cast<const T *>(buf_->data()); }
-    template <typename T> T &at(int i0) { return ptr<T>()[i0]; }
-    template <typename T> T &at(int i0, int i1) { return ptr<T>()[(size_t)i0 * sz_[1] + i1]; }
-    template <typename T> T &at(int i0, int i1, int i2) { return ptr<T>()[((size_t)i0 * sz_[1] + i1) * sz_[2] + i2]; }
-    int rows() const { return sz_.empty() ? 0 : sz_[0]; }
-    int cols() const { return sz_.size() < 2 ? 0 : sz_[1]; }
+    size_t elemSize1() const { static const size_t b[8] = {1, 1, 2, 2, 4, 4, 8, 2}; return b[depth()]; }
+    size_t elemSize() const { return elemSize1() * channels(); }
+    Size size() const { return Size(cols, rows); }
+    bool empty() const { return data == nullptr || total() == 0; }
+    template <typename T> T *ptr(int y = 0) { return reinterpret_cast<T *>(data + (size_t)y * step.v); }
+    template <typename T> const T *ptr(int y = 0) const { return reinterpret_cast<const T *>(data + (size_t)y * step.v); }
+    template <typename T> T &at(int i0) { return reinterpret_cast<T *>(data)[i0]; }
+    template <typename T> T &at(int i0, int i1) { return reinterpret_cast<T *>(data)[(size_t)i0 * sz_[1] + i1]; }
+    template <typename T> T &at(int i0, int i1, int i2) { return reinterpret_cast<T *>(data)[((size_t)i0 * sz_[1] + i1) * sz_[2] + i2]; }
     size_t total() const { size_t t = 1; for (int s : sz_) t *= s; return sz_.empty() ? 0 : t; }
+    /* dst(x) = src(x) where mask(x) != 0 (8-bit single-channel mask of the same size); dst is (re)allocated when its size or
+     * type differs, as cv::Mat::copyTo does -- then the unmasked elements are zero */
+    void copyTo(Mat &dst, const Mat &mask) const {
+        if (dst.rows != rows || dst.cols != cols || dst.type_ != type_ || !dst.data) dst = Mat(rows, cols, type_);
+        const size_t es = elemSize();
+        for (int y = 0; y < rows; ++y) {
+            const unsigned char *m = mask.data + (size_t)y * mask.step.v;
+            for (int x = 0; x < cols; ++x)
+                if (m[(size_t)x * mask.elemSize()]) std::memcpy(dst.data + (size_t)y * dst.step.v + x * es, data + (size_t)y * step.v + x * es, es);
+        }
+    }
+    void copyTo(Mat &dst) const {
+        dst = Mat(dims, sz_.data(), type_);
+        if (data) std::memcpy(dst.data, data, total() * elemSize());
+    }
+    Mat clone() const { Mat m; copyTo(m); return m; }
     std::vector<int> sz_;
 private:
-    void alloc() { buf_ = std::make_shared<std::vector<unsigned char>>(total() * elemSize(), 0); }
+    void alloc() {
+        buf_ = std::make_shared<std::vector<unsigned char>>(total() * elemSize(), 0);
+        data = buf_->empty() ? nullptr : buf_->data();
+        dims = (int)sz_.size();
+        rows = dims == 2 ? sz_[0] : (dims == 1 ? sz_[0] : -1);
+        cols = dims == 2 ? sz_[1] : (dims == 1 ? 1 : -1);
+        step = MatStep(dims >= 1 ? (size_t)sz_.back() * elemSize() : 0);
+    }
     int type_;
     std::shared_ptr<std::vector<unsigned char>> buf_;
 };
-inline Mat operator*(float s, const Mat &m) { Mat r = m; Mat o(m.rows(), m.cols(), CV_32FC1); for (size_t i = 0; i < m.total(); ++i) o.ptr<float>()[i] = s * m.ptr<float>()[i]; return o; }
-inline Mat operator-(const Mat &a, const Mat &b) { Mat o(a.rows(), a.cols(), CV_32FC1); for (size_t i = 0; i < a.total(); ++i) o.ptr<float>()[i] = a.ptr<float>()[i] - b.ptr<float>()[i]; return o; }
+inline Mat operator*(float s, const Mat &m) { Mat o(m.rows, m.cols, CV_32FC1); for (size_t i = 0; i < m.total(); ++i) o.ptr<float>()[i] = s * m.ptr<float>()[i]; return o; }
+inline Mat operator-(const Mat &a, const Mat &b) { Mat o(a.rows, a.cols, CV_32FC1); for (size_t i = 0; i < a.total(); ++i) o.ptr<float>()[i] = a.ptr<float>()[i] - b.ptr<float>()[i]; return o; }
 inline std::ostream &operator<<(std::ostream &os, const Mat &m) { for (size_t i = 0; i < m.total(); ++i) os << m.ptr<float>()[i] << (i + 1 < m.total() ? ", " : ""); return os; }
 /* dense solve is only referenced from dead code in the reference (solver.cpp:107-158) */
 inline bool solve(const Mat &, const Mat &, Mat &, int) { std::fprintf(stderr, "cv::solve: not provided by the compat shim\n"); return false; }

@@ -22,10 +22,18 @@
 #include <pcl/point_cloud.h>
 #include <pcl/point_types.h>
 
+// headers the reference's own headers pull in (directly or through OpenCV / PCL / Boost) and its sources rely on
+#include <boost/filesystem.hpp>
+
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
+#include <iomanip>
 #include <iostream>
 #include <memory>
+#include <sstream>
+#include <string>
 #include <vector>
 
 #ifndef KF_EXPORTS
@@ -165,7 +173,73 @@ struct Surface {
     Norms normals;
 };
 inline void waitAllDefaultStream() { cudaSafeCall(cudaDeviceSynchronize()); }
+
+// device management of include/kfusion/kinfu.hpp:25-30 (src/kfusion/core.cpp:8-212), as the application's main() uses it
+inline int getCudaEnabledDeviceCount() {
+    int count = 0;
+    const cudaError_t e = cudaGetDeviceCount(&count);
+    if (e == cudaErrorInsufficientDriver) return -1;
+    if (e == cudaErrorNoDevice) return 0;
+    cudaSafeCall(e);
+    return count;
+}
+inline void setDevice(int device) { cudaSafeCall(cudaSetDevice(device)); }
+inline std::string getDeviceName(int device) {
+    cudaDeviceProp prop;
+    cudaSafeCall(cudaGetDeviceProperties(&prop, device));
+    return prop.name;
+}
+inline bool checkIfPreFermiGPU(int device) {
+    if (device < 0) cudaSafeCall(cudaGetDevice(&device));
+    cudaDeviceProp prop;
+    cudaSafeCall(cudaGetDeviceProperties(&prop, device));
+    return prop.major < 2;
+}
+// one line per device, the reference's format (core.cpp:189-212); FP32 lanes per SM: 128 on every architecture this library runs on
+inline void printShortCudaDeviceInfo(int device) {
+    const int count = getCudaEnabledDeviceCount();
+    const bool valid = device >= 0 && device < count;
+    int driver = 0, runtime = 0;
+    cudaSafeCall(cudaDriverGetVersion(&driver));
+    cudaSafeCall(cudaRuntimeGetVersion(&runtime));
+    for (int dev = valid ? device : 0; dev < (valid ? device + 1 : count); ++dev) {
+        cudaDeviceProp prop;
+        cudaSafeCall(cudaGetDeviceProperties(&prop, dev));
+        std::printf("Device %d:  \"%s\"  %.0fMb, sm_%d%d%s, %d cores, Driver/Runtime ver.%d.%d/%d.%d\n", dev, prop.name,
+                    (float)prop.totalGlobalMem / 1048576.0f, prop.major, prop.minor, prop.major < 2 ? " (pre-Fermi)" : "",
+                    128 * prop.multiProcessorCount, driver / 1000, driver % 100, runtime / 1000, runtime % 100);
+    }
+    std::fflush(stdout);
+}
+inline void printCudaDeviceInfo(int device) { printShortCudaDeviceInfo(device); }
 }  // namespace cuda
+
+// timers of include/kfusion/types.hpp:100-122 (src/kfusion/core.cpp:214-236)
+struct ScopeTime {
+    const char *name;
+    double start;
+    ScopeTime(const char *name_) : name(name_), start((double)cv::getTickCount()) {}
+    ~ScopeTime() { std::cout << "Time(" << name << ") = " << ((double)cv::getTickCount() - start) * 1000.0 / cv::getTickFrequency() << "ms" << std::endl; }
+};
+struct SampledScopeTime {
+    enum { EACH = 34 };
+    SampledScopeTime(double &time_ms) : time_ms_(time_ms), start((double)cv::getTickCount()) {}
+    ~SampledScopeTime() {
+        static int i_ = 0;
+        time_ms_ += ((double)cv::getTickCount() - start) * 1000.0 / cv::getTickFrequency();
+        if (i_ % EACH == 0 && i_) {
+            std::cout << "avg. frame time = " << time_ms_ / EACH << "ms (" << 1000.f * EACH / time_ms_ << "fps)" << std::endl;
+            time_ms_ = 0.0;
+        }
+        ++i_;
+    }
+
+private:
+    SampledScopeTime(const SampledScopeTime &);
+    SampledScopeTime &operator=(const SampledScopeTime &);
+    double &time_ms_;
+    double start;
+};
 
 namespace device {
 typedef int3 Vec3i;
