@@ -125,6 +125,13 @@ int sobfu_b200_max_update_norm(const void *updates4, int N, float *value, float 
 int sobfu_b200_tsdf_clear(void *vol, int X, int Y, int Z);                          /* tsdf_volume.cu:23-46 */
 int sobfu_b200_tsdf_init_sphere(void *vol, int X, int Y, int Z, const float *voxel_size3, float trunc_dist,
                                 float eta, const float *centre3, float radius);     /* tsdf_volume.cu:249-275 */
+/* signed distance fields of primitives centred in the volume, weight 1 (TsdfVolume::initBox / initEllipsoid / initPlane /
+ * initTorus, tsdf_volume.cpp:108-146 -> tsdf_volume.cu:181-247, 277-334): half extents b, semi-axes r, plane height z (metres
+ * from the volume origin, not centred), torus (major radius, tube radius) */
+int sobfu_b200_tsdf_init_box(void *vol, int X, int Y, int Z, const float *voxel_size3, float trunc_dist, const float *b3);
+int sobfu_b200_tsdf_init_ellipsoid(void *vol, int X, int Y, int Z, const float *voxel_size3, float trunc_dist, const float *r3);
+int sobfu_b200_tsdf_init_plane(void *vol, int X, int Y, int Z, const float *voxel_size3, float trunc_dist, float z);
+int sobfu_b200_tsdf_init_torus(void *vol, int X, int Y, int Z, const float *voxel_size3, float trunc_dist, const float *t2);
 int sobfu_b200_tsdf_fuse(void *phi_global, const void *phi_n_psi, int X, int Y, int Z, float max_weight); /* :103-130 */
 /* vol2cam: R (row-major 3x3) and t; dists: float image with row pitch in bytes (tsdf_volume.cu:62-101,141-162) */
 int sobfu_b200_tsdf_integrate(const void *dists, size_t pitch_bytes, int cols, int rows, void *vol, int X, int Y,

@@ -353,6 +353,25 @@ public:
         const float c[3] = {centre.x, centre.y, centre.z};
         SOBFU_SHIM_CALL(sobfu_b200_tsdf_init_sphere(data_.ptr<float2>(), dims_[0], dims_[1], dims_[2], vs.val, trunc_dist_, eta_, c, radius));
     }
+    virtual void initBox(const float3 &b) {
+        const Vec3f vs = getVoxelSize();
+        const float v[3] = {b.x, b.y, b.z};
+        SOBFU_SHIM_CALL(sobfu_b200_tsdf_init_box(data_.ptr<float2>(), dims_[0], dims_[1], dims_[2], vs.val, trunc_dist_, v));
+    }
+    virtual void initEllipsoid(const float3 &r) {
+        const Vec3f vs = getVoxelSize();
+        const float v[3] = {r.x, r.y, r.z};
+        SOBFU_SHIM_CALL(sobfu_b200_tsdf_init_ellipsoid(data_.ptr<float2>(), dims_[0], dims_[1], dims_[2], vs.val, trunc_dist_, v));
+    }
+    virtual void initPlane(const float &z) {
+        const Vec3f vs = getVoxelSize();
+        SOBFU_SHIM_CALL(sobfu_b200_tsdf_init_plane(data_.ptr<float2>(), dims_[0], dims_[1], dims_[2], vs.val, trunc_dist_, z));
+    }
+    virtual void initTorus(const float2 &t) {
+        const Vec3f vs = getVoxelSize();
+        const float v[2] = {t.x, t.y};
+        SOBFU_SHIM_CALL(sobfu_b200_tsdf_init_torus(data_.ptr<float2>(), dims_[0], dims_[1], dims_[2], vs.val, trunc_dist_, v));
+    }
     void print_sdf_values() {
         std::vector<float2> h((size_t)dims_[0] * dims_[1] * dims_[2]);
         data_.download(h.data());

@@ -167,6 +167,19 @@ def tsdf_init_sphere(dims, voxel, trunc, eta, centre, radius):
     return vol
 
 
+SHAPES = {"box": 0, "ellipsoid": 1, "plane": 2, "torus": 3}
+
+
+def tsdf_init_shape(dims, voxel, trunc, shape, prm):
+    """TsdfVolume::initBox / initEllipsoid / initPlane / initTorus (tsdf_volume.cu:181-247, 277-334)"""
+    X, Y, Z = dims
+    vol = np.zeros((Z, Y, X, 2), dtype=np.float32)
+    q = list(prm) + [0.0, 0.0, 0.0]
+    lib().orc_tsdf_init_shape(_p(vol), X, Y, Z, C.c_float(voxel[0]), C.c_float(voxel[1]), C.c_float(voxel[2]), C.c_float(trunc),
+                              SHAPES[shape], C.c_float(q[0]), C.c_float(q[1]), C.c_float(q[2]))
+    return vol
+
+
 def tsdf_fuse(pg, pn, max_weight):
     lib().orc_tsdf_fuse(_p(pg), _p(pn), int(pg.size // 2), C.c_float(max_weight))
     return pg
@@ -262,6 +275,11 @@ class Reference:
     def psi_clear(self, which=0): self.L.ref_psi_clear(self.h, which)
     def tsdf_clear(self, which): self.L.ref_tsdf_clear(self.h, which)
     def init_sphere(self, which, c, r): self.L.ref_init_sphere(self.h, which, c[0], c[1], c[2], r)
+
+    def init_shape(self, which, shape, prm):
+        q = list(prm) + [0.0, 0.0, 0.0]
+        self.L.ref_init_shape.argtypes = [_P, _I, _I, _F, _F, _F]
+        self.L.ref_init_shape(self.h, which, SHAPES[shape], q[0], q[1], q[2])
     def estimate_psi(self): return float(self.L.ref_estimate_psi(self.h))
     def apply(self, which_psi, src, dst): self.L.ref_apply(self.h, which_psi, src, dst)
     def get_inverse(self): self.L.ref_get_inverse(self.h)

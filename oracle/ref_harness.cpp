@@ -107,6 +107,15 @@ void ref_init_sphere(void *h, int which, float cx, float cy, float cz, float rad
     ((Ref *)h)->vol[which]->initSphere(make_float3(cx, cy, cz), radius);
 }
 
+/* TsdfVolume::initBox / initEllipsoid / initPlane / initTorus (tsdf_volume.cpp:108-146) */
+void ref_init_shape(void *h, int which, int shape, float a, float b, float c) {
+    kfusion::cuda::TsdfVolume &v = *((Ref *)h)->vol[which];
+    if (shape == 0) v.initBox(make_float3(a, b, c));
+    else if (shape == 1) v.initEllipsoid(make_float3(a, b, c));
+    else if (shape == 2) v.initPlane(a);
+    else v.initTorus(make_float2(a, b));
+}
+
 /* sobfu::cuda::Solver::estimate_psi (solver.cpp:69); returns device milliseconds of the call */
 float ref_estimate_psi(void *h) {
     Ref *r = (Ref *)h;

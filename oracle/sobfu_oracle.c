@@ -567,6 +567,45 @@ void orc_tsdf_init_sphere(orc_f2 *vol, int X, int Y, int Z, float vx, float vy, 
     }
 }
 
+/* tsdf_volume.cu:181-247, 277-334: box / ellipsoid / plane / torus, centred in the volume (the plane is not), weight 1.
+ * shape 0..3; prm = half extents | semi-axes | (z) | (major radius, tube radius).  norm(float3) = sqrt(fma(x,x,fma(y,y,z*z)))
+ * (temp_utils.hpp:33-35,86), norm(float2) = sqrt_rn(x*x + y*y) without contraction (utils.hpp:212-214). */
+static inline float orc_norm3(float x, float y, float z) { return sqrtf(fmaf(x, x, fmaf(y, y, z * z))); }
+static inline float orc_norm2(float x, float y) { return sqrtf(x * x + y * y); }
+void orc_tsdf_init_shape(orc_f2 *vol, int X, int Y, int Z, float vx, float vy, float vz, float trunc, int shape, float a, float b,
+                         float c) {
+#pragma omp parallel
+    {
+        const unsigned csr__ = orc_ftz_on();
+#pragma omp for
+        for (int y = 0; y < Y; ++y)
+            for (int x = 0; x < X; ++x) {
+                float cx = 0.f, cy = 0.f, cz = 0.f;
+                if (shape != 2) { cx = (float)X / 2.f * vx; cy = (float)Y / 2.f * vy; cz = (float)Z / 2.f * vz; }
+                const float px = fmaf((float)x, vx, vx * 0.5f) - cx, py = fmaf((float)y, vy, vy * 0.5f) - cy;
+                float pz = vz * 0.5f - cz;
+                for (int z = 0; z < Z; ++z, pz += vz) {
+                    float sdf;
+                    if (shape == 0) {
+                        const float dx = fabsf(px) - a, dy = fabsf(py) - b, dz = fabsf(pz) - c;
+                        sdf = fminf(fmaxf(dx, fmaxf(dy, dz)), 0.f) + orc_norm3(fmaxf(dx, 0.f), fmaxf(dy, 0.f), fmaxf(dz, 0.f));
+                    } else if (shape == 1) {
+                        const float k0 = orc_norm3(px / a, py / b, pz / c);
+                        const float k1 = orc_norm3(px / (a * a), py / (b * b), pz / (c * c));
+                        sdf = k0 * (k0 - 1.f) / k1;
+                    } else if (shape == 2) {
+                        sdf = pz - a;
+                    } else {
+                        const float qx = orc_norm2(px, pz) - a;
+                        sdf = orc_norm2(qx, py) - b;
+                    }
+                    vol[IDX(x, y, z)] = pack_tsdf(sdf, trunc, 1.f);
+                }
+            }
+        _mm_setcsr(csr__);
+    }
+}
+
 /* tsdf_volume.cu:103-130 */
 void orc_tsdf_fuse(orc_f2 *pg, const orc_f2 *pn, int N, float max_weight) {
 #pragma omp parallel

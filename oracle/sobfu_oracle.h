@@ -92,6 +92,8 @@ void  orc_solver_iteration(const orc_f2 *phi_global, const orc_f2 *phi_n, orc_f2
 /* tsdf_volume.cu:23-46 */
 void  orc_tsdf_clear(orc_f2 *vol, int N);
 /* tsdf_volume.cu:249-275  (approx: powf/sqrtf/__fdividef) */
+void  orc_tsdf_init_shape(orc_f2 *vol, int X, int Y, int Z, float vx, float vy, float vz, float trunc, int shape, float a, float b,
+                          float c);   /* 0 box, 1 ellipsoid, 2 plane, 3 torus: tsdf_volume.cu:181-247, 277-334 */
 void  orc_tsdf_init_sphere(orc_f2 *vol, int X, int Y, int Z, float vx, float vy, float vz, float trunc, float eta,
                            float cx, float cy, float cz, float radius);
 /* tsdf_volume.cu:103-130 (approx: __fdividef) */

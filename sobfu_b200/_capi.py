@@ -56,6 +56,10 @@ SIGNATURES = {
     "sobfu_b200_max_update_norm": [_P, _I, _FP, _FP, C.POINTER(C.c_longlong)],
     "sobfu_b200_tsdf_clear": [_P, _I, _I, _I],
     "sobfu_b200_tsdf_init_sphere": [_P, _I, _I, _I, _FP, _F, _F, _FP, _F],
+    "sobfu_b200_tsdf_init_box": [_P, _I, _I, _I, _FP, _F, _FP],
+    "sobfu_b200_tsdf_init_ellipsoid": [_P, _I, _I, _I, _FP, _F, _FP],
+    "sobfu_b200_tsdf_init_plane": [_P, _I, _I, _I, _FP, _F, _F],
+    "sobfu_b200_tsdf_init_torus": [_P, _I, _I, _I, _FP, _F, _FP],
     "sobfu_b200_tsdf_fuse": [_P, _P, _I, _I, _I, _F],
     "sobfu_b200_tsdf_integrate": [_P, _Z, _I, _I, _P, _I, _I, _I, _FP, _F, _F, _FP, _FP, _F, _F, _F, _F],
     "sobfu_b200_depth_bilateral": [_P, _Z, _P, _Z, _I, _I, _I, _F, _F],

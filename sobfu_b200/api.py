@@ -126,6 +126,15 @@ class TsdfVolume:
         check(lib().sobfu_b200_tsdf_init_sphere(_ptr(self.data_), X, Y, Z, fvec(self.getVoxelSize()), self.trunc_dist_,
                                                 self.eta_, fvec(centre), f32(radius)))
 
+    def _init_shape(self, fn, prm):
+        X, Y, Z = self.dims_
+        check(fn(_ptr(self.data_), X, Y, Z, fvec(self.getVoxelSize()), self.trunc_dist_, prm))
+
+    def initBox(self, b): self._init_shape(lib().sobfu_b200_tsdf_init_box, fvec(b))                    # tsdf_volume.cpp:108-114
+    def initEllipsoid(self, r): self._init_shape(lib().sobfu_b200_tsdf_init_ellipsoid, fvec(r))        # :116-122
+    def initPlane(self, z): self._init_shape(lib().sobfu_b200_tsdf_init_plane, f32(z))                 # :124-130
+    def initTorus(self, t): self._init_shape(lib().sobfu_b200_tsdf_init_torus, fvec(t))                # :140-146
+
     def integrate(self, other, camera_pose=None, intr=None):
         """integrate(TsdfVolume) = running-average fusion (tsdf_volume.cpp:84-93);
         integrate(dists, camera_pose, intr) = projective integration of a ray-length image (tsdf_volume.cpp:95-108)."""

@@ -37,6 +37,7 @@ void launch_max_norm(const float4 *u, size_t n, RankMap rm, unsigned long long *
 // tsdf_ops.cu
 void launch_tsdf_clear(float2 *vol, size_t n, cudaStream_t st);
 void launch_tsdf_init_sphere(float2 *vol, Dims d, float3 vs, float trunc, float eta, float3 c, float r, cudaStream_t st);
+void launch_tsdf_init_shape(float2 *vol, Dims d, float3 vs, float trunc, int shape, float3 prm, cudaStream_t st);
 void launch_tsdf_fuse(float2 *pg, const float2 *pn, size_t n, float max_weight, cudaStream_t st);
 void launch_tsdf_integrate(const float *dists, size_t pitch, int cols, int rows, float2 *vol, Dims d, float3 vs, float trunc,
                            float eta, const float *R, const float *t, float fx, float fy, float cx, float cy, cudaStream_t st);
@@ -1061,6 +1062,26 @@ extern "C" int sobfu_b200_tsdf_init_sphere(void *vol, int X, int Y, int Z, const
     launch_tsdf_init_sphere((float2 *)vol, Dims{X, Y, Z}, make_float3(vs[0], vs[1], vs[2]), trunc, eta, make_float3(c[0], c[1], c[2]),
                             radius, g_stream);
     SYNC_RET();
+}
+static int init_shape(void *vol, int X, int Y, int Z, const float *vs, float trunc, int shape, float a, float b, float c, const char *what) {
+    if (!(vol && vs && dims_ok(X, Y, Z))) return fail(SOBFU_B200_EINVAL, "%s: bad argument", what);
+    launch_tsdf_init_shape((float2 *)vol, Dims{X, Y, Z}, make_float3(vs[0], vs[1], vs[2]), trunc, shape, make_float3(a, b, c), g_stream);
+    SYNC_RET();
+}
+extern "C" int sobfu_b200_tsdf_init_box(void *vol, int X, int Y, int Z, const float *vs, float trunc, const float *b) {
+    NEED(b, "tsdf_init_box: bad argument");
+    return init_shape(vol, X, Y, Z, vs, trunc, 0, b[0], b[1], b[2], "tsdf_init_box");
+}
+extern "C" int sobfu_b200_tsdf_init_ellipsoid(void *vol, int X, int Y, int Z, const float *vs, float trunc, const float *r) {
+    NEED(r, "tsdf_init_ellipsoid: bad argument");
+    return init_shape(vol, X, Y, Z, vs, trunc, 1, r[0], r[1], r[2], "tsdf_init_ellipsoid");
+}
+extern "C" int sobfu_b200_tsdf_init_plane(void *vol, int X, int Y, int Z, const float *vs, float trunc, float z) {
+    return init_shape(vol, X, Y, Z, vs, trunc, 2, z, 0.f, 0.f, "tsdf_init_plane");
+}
+extern "C" int sobfu_b200_tsdf_init_torus(void *vol, int X, int Y, int Z, const float *vs, float trunc, const float *t) {
+    NEED(t, "tsdf_init_torus: bad argument");
+    return init_shape(vol, X, Y, Z, vs, trunc, 3, t[0], t[1], 0.f, "tsdf_init_torus");
 }
 extern "C" int sobfu_b200_tsdf_fuse(void *pg, const void *pn, int X, int Y, int Z, float max_weight) {
     NEED(pg && pn && dims_ok(X, Y, Z), "tsdf_fuse: bad argument");

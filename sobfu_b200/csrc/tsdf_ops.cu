@@ -47,6 +47,44 @@ __global__ void init_sphere_kernel(float2 *__restrict__ vol, Dims d, float3 vs, 
     }
 }
 
+// init_{box,ellipsoid,plane,torus}_kernel, tsdf_volume.cu:181-247, 277-334: signed distance fields of primitives centred in the
+// volume (the plane is not centred), weight 1 everywhere.  Same running sum along z as the reference (vc += zstep), replayed
+// per z chunk; expressions are written as in the reference so that the compiler contracts the same multiply-adds.
+enum { SHAPE_BOX = 0, SHAPE_ELLIPSOID = 1, SHAPE_PLANE = 2, SHAPE_TORUS = 3 };
+SB_DEV float norm3(float x, float y, float z) { return sqrtf(__fmaf_rn(x, x, __fmaf_rn(y, y, z * z))); }      // temp_utils.hpp:33-35,86
+SB_DEV float norm2(float x, float y) { return __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))); }      // utils.hpp:212-214
+template <int SHAPE>
+__global__ void init_shape_kernel(float2 *__restrict__ vol, Dims d, float3 vs, float trunc, float3 prm) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int z0 = blockIdx.z * ZCHUNK;
+    if (x >= d.X || y >= d.Y) return;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (SHAPE != SHAPE_PLANE) { cx = d.X / 2.f * vs.x; cy = d.Y / 2.f * vs.y; cz = d.Z / 2.f * vs.z; }
+    const float vx = (x * vs.x + vs.x / 2.f) - cx, vy = (y * vs.y + vs.y / 2.f) - cy;
+    float vz = (vs.z / 2.f) - cz;
+    for (int i = 0; i < z0; ++i) vz += vs.z;
+    const int z1 = min(z0 + ZCHUNK, d.Z);
+    float2 *p = vol + x + (size_t)d.X * (y + (size_t)d.Y * z0);
+    for (int i = z0; i < z1; ++i, vz += vs.z, p += (size_t)d.X * d.Y) {
+        float sdf;
+        if (SHAPE == SHAPE_BOX) {
+            const float dx = fabs(vx) - prm.x, dy = fabs(vy) - prm.y, dz = fabs(vz) - prm.z;
+            sdf = fmin(fmax(dx, fmax(dy, dz)), 0.f) + norm3(fmax(dx, 0.f), fmax(dy, 0.f), fmax(dz, 0.f));
+        } else if (SHAPE == SHAPE_ELLIPSOID) {
+            const float k0 = norm3(vx / prm.x, vy / prm.y, vz / prm.z);
+            const float k1 = norm3(vx / (prm.x * prm.x), vy / (prm.y * prm.y), vz / (prm.z * prm.z));
+            sdf = k0 * (k0 - 1.f) / k1;
+        } else if (SHAPE == SHAPE_PLANE) {
+            sdf = vz - prm.x;
+        } else {
+            const float qx = norm2(vx, vz) - prm.x, qy = vy;
+            sdf = norm2(qx, qy) - prm.y;
+        }
+        *p = pack_tsdf(sdf, trunc, 1.f);
+    }
+}
+
 // TsdfIntegrator::operator()(phi_global, phi_n_psi), tsdf_volume.cu:103-130
 __global__ void tsdf_fuse_kernel(float2 *__restrict__ pg, const float2 *__restrict__ pn, size_t n, float max_weight) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -146,6 +184,15 @@ void launch_tsdf_clear(float2 *vol, size_t n, cudaStream_t st) {
 void launch_tsdf_init_sphere(float2 *vol, Dims d, float3 vs, float trunc, float eta, float3 c, float r, cudaStream_t st) {
     dim3 block(32, 8), grid((d.X + 31) / 32, (d.Y + 7) / 8, (d.Z + ZCHUNK - 1) / ZCHUNK);
     init_sphere_kernel<<<grid, block, 0, st>>>(vol, d, vs, trunc, eta, c, r);
+}
+void launch_tsdf_init_shape(float2 *vol, Dims d, float3 vs, float trunc, int shape, float3 prm, cudaStream_t st) {
+    dim3 block(32, 8), grid((d.X + 31) / 32, (d.Y + 7) / 8, (d.Z + ZCHUNK - 1) / ZCHUNK);
+    switch (shape) {
+        case SHAPE_BOX: init_shape_kernel<SHAPE_BOX><<<grid, block, 0, st>>>(vol, d, vs, trunc, prm); break;
+        case SHAPE_ELLIPSOID: init_shape_kernel<SHAPE_ELLIPSOID><<<grid, block, 0, st>>>(vol, d, vs, trunc, prm); break;
+        case SHAPE_PLANE: init_shape_kernel<SHAPE_PLANE><<<grid, block, 0, st>>>(vol, d, vs, trunc, prm); break;
+        default: init_shape_kernel<SHAPE_TORUS><<<grid, block, 0, st>>>(vol, d, vs, trunc, prm); break;
+    }
 }
 void launch_tsdf_fuse(float2 *pg, const float2 *pn, size_t n, float max_weight, cudaStream_t st) {
     tsdf_fuse_kernel<<<sgrid(n), 256, 0, st>>>(pg, pn, n, max_weight);

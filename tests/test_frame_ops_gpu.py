@@ -125,6 +125,31 @@ def test_frame_kernels_bit_exact_against_the_reference_cuda(env):
     ref.close()
 
 
+SHAPE_CASES = [("box", (0.21, 0.15, 0.1)), ("ellipsoid", (0.25, 0.18, 0.12)), ("plane", (0.31,)), ("torus", (0.2, 0.07))]
+
+
+@pytest.mark.parametrize("shape,prm", SHAPE_CASES)
+def test_primitive_initialisers(env, shape, prm):
+    """TsdfVolume::initBox / initEllipsoid / initPlane / initTorus (tsdf_volume.cu:181-247, 277-334): within float tolerance of
+    the oracle (approximate sqrt / division on the GPU, as in the reference) and bit-exact against the reference's CUDA"""
+    sf, orc, torch = env
+    p = make_params(sf, dims=(48, 40, 36))
+    vol = sf.TsdfVolume(p)
+    call = {"box": vol.initBox, "ellipsoid": vol.initEllipsoid, "plane": vol.initPlane, "torus": vol.initTorus}[shape]
+    call(prm if shape != "plane" else prm[0])
+    got = vol.data().cpu().numpy()
+    want = orc.tsdf_init_shape(p.volume_dims, p.voxel_sizes(), f32(p.tsdf_trunc_dist), shape, prm)
+    assert np.array_equal(got[..., 1], want[..., 1]) and (got[..., 1] == 1).all()
+    assert np.abs(got[..., 0] - want[..., 0]).max() < 2e-5
+    assert got[..., 0].min() < 0 < got[..., 0].max()                      # the surface is inside the volume
+    if os.path.exists(orc.REF):
+        ref = orc.Reference(p.volume_dims, p.volume_size, p.tsdf_trunc_dist, p.eta, p.tsdf_max_weight, 0, p.max_iter, 7, p.max_update_norm, p.lambda_,
+                            p.alpha, p.w_reg, pose_t=tuple(p.volume_pose.t), intr=(CAM["fx"], CAM["fy"], CAM["cx"], CAM["cy"]))
+        ref.init_shape(ref.GLOBAL, shape, prm)
+        assert_bits(got, ref.download_tsdf(ref.GLOBAL), "init " + shape)
+        ref.close()
+
+
 def test_frame_sequence_through_sobfusion_matches_the_reference(env):
     """SobFusion::operator() (sob_fusion.cpp:71-145) on 5 synthetic frames: init, rigid fusion, then 3 solver frames with a
     warm-started psi -- every volume and field equal to the reference's own CUDA, bit for bit"""

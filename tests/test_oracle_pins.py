@@ -146,3 +146,26 @@ def test_max_update_norm_is_round_down_sqrt():
     for x in (2.0, 3.0, 1e-12, 0.3, 12345.678):
         r = orc.lib().orc_sqrt_rd(f32(x))
         assert np.float64(r) ** 2 <= np.float64(f32(x)) < np.float64(np.nextafter(f32(r), f32(np.inf))) ** 2
+
+
+def test_primitive_signed_distance_fields():
+    """oracle restatement of tsdf_volume.cu:181-247, 277-334 against the closed forms they implement (double precision)"""
+    dims, size, trunc = (24, 20, 28), (0.48, 0.40, 0.56), 0.05
+    vs = tuple(f32(size[i]) / f32(dims[i]) for i in range(3))
+    z, y, x = np.meshgrid(*[(np.arange(dims[k], dtype=np.float64) + 0.5) * float(vs[k]) for k in (2, 1, 0)], indexing="ij")
+    cx, cy, cz = [dims[k] / 2.0 * float(vs[k]) for k in range(3)]
+    X, Y, Z = x - cx, y - cy, z - cz
+    clamp = lambda sdf: np.clip(sdf / trunc, -1.0, 1.0)  # noqa: E731
+    b = (0.1, 0.08, 0.12)
+    d = np.stack([np.abs(X) - b[0], np.abs(Y) - b[1], np.abs(Z) - b[2]])
+    box = np.minimum(d.max(0), 0) + np.linalg.norm(np.maximum(d, 0), axis=0)
+    r = (0.15, 0.1, 0.2)
+    k0 = np.sqrt((X / r[0]) ** 2 + (Y / r[1]) ** 2 + (Z / r[2]) ** 2)
+    k1 = np.sqrt((X / r[0] ** 2) ** 2 + (Y / r[1] ** 2) ** 2 + (Z / r[2] ** 2) ** 2)
+    ell = k0 * (k0 - 1) / k1
+    t = (0.12, 0.04)
+    tor = np.sqrt((np.sqrt(X * X + Z * Z) - t[0]) ** 2 + Y * Y) - t[1]
+    for shape, prm, sdf in (("box", b, box), ("ellipsoid", r, ell), ("plane", (0.2,), z - 0.2), ("torus", t, tor)):
+        vol = orc.tsdf_init_shape(dims, vs, f32(trunc), shape, prm)
+        assert (vol[..., 1] == 1).all(), shape
+        assert np.abs(vol[..., 0] - clamp(sdf)).max() < 2e-5, shape
