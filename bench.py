@@ -42,10 +42,11 @@ ALGO_BYTES_PASS_B = 48      # R nabla_U 16 + R psi 16 + W psi 16   (Sobolev filt
 ALGO_BYTES_ITER = 112
 
 
-def synth_depth(frame, radius=0.15, z0=0.5):
+def synth_depth(frame, radius=0.15, z0=0.5, intr=None):
     """analytically ray-cast sphere: centre (0.002*frame, 0, z0) m, ushort millimetres, background 0"""
     u, v = np.meshgrid(np.arange(COLS, dtype=np.float64), np.arange(ROWS, dtype=np.float64))
-    dx, dy = (u - BOXING["cx"]) / BOXING["fx"], (v - BOXING["cy"]) / BOXING["fy"]
+    k = intr or BOXING
+    dx, dy = (u - k["cx"]) / k["fx"], (v - k["cy"]) / k["fy"]
     c = np.array([0.002 * frame, 0.0, z0])
     a = dx * dx + dy * dy + 1.0
     b = -2.0 * (dx * c[0] + dy * c[1] + c[2])
@@ -239,6 +240,78 @@ def run_ours(args, rank, world, torch, dist):
         print(json.dumps(out), flush=True)
 
 
+# params/params_snoopy.ini of the reference (BASELINE.json configs[4]: 256^3, 50-frame sequence, marching cubes every frame);
+# the truncation band is given in voxels and kept at snoopy's 10 / 5
+SNOOPY = dict(vol_size=0.9, trunc_vox=10.0, eta_vox=5.0, max_weight=128.0, fx=517.0, fy=517.0, cx=320.0, cy=240.0, trunc_depth=3.0,
+              pose_tz=0.05, sigma_depth=0.01, sigma_spatial=4.5, ksz=7, start_frame=4, max_update_norm=1e-3, s=7, lam=0.1, alpha=0.1, w_reg=0.2)
+
+
+def run_pipeline(args, rank, world, torch, dist):
+    """BASELINE.json configs[4]: the whole per-frame pipeline (depth preparation, TSDF integration, solver, fusion, marching cubes on
+    phi_global every frame) over a synthetic sequence of a radially pulsating, translating sphere.  One step
+    = one frame from pinned host memory; value = frames/s over the frames after START_FRAME (the ones that run the solver)."""
+    import sobfu_b200 as sf
+    from sobfu_b200.parallel import SlabFusion
+    b, dim = SNOOPY, args.dim
+    p = sf.Params(cols=COLS, rows=ROWS, volume_dims=(dim, dim, dim), volume_size=(b["vol_size"],) * 3, intr=sf.Intr(b["fx"], b["fy"], b["cx"], b["cy"]),
+                  icp_truncate_depth_dist=b["trunc_depth"], bilateral_sigma_depth=b["sigma_depth"], bilateral_sigma_spatial=b["sigma_spatial"],
+                  bilateral_kernel_size=b["ksz"], tsdf_max_weight=b["max_weight"], gradient_delta_factor=0.5, start_frame=b["start_frame"], verbosity=0,
+                  s=b["s"], max_iter=args.iters, max_update_norm=b["max_update_norm"], lambda_=b["lam"], alpha=b["alpha"], w_reg=b["w_reg"])
+    vs = p.voxel_sizes()
+    p.tsdf_trunc_dist, p.eta = float(np.float32(b["trunc_vox"]) * vs[0]), float(np.float32(b["eta_vox"]) * vs[0])
+    p.volume_pose = sf.Affine3f().translate((-b["vol_size"] / 2, -b["vol_size"] / 2, b["pose_tz"]))
+    fusion = sf.SobFusion(p) if world == 1 else SlabFusion(p, dist)
+    nframes = args.frames
+    frames = [torch.from_numpy(synth_depth(f, radius=0.15 + 0.01 * np.sin(2 * np.pi * f / 25.0), intr=b).view(np.int16)).pin_memory() for f in range(nframes)]
+    dev_depth = torch.empty((ROWS, COLS), dtype=torch.int16, device="cuda")
+    nverts, iters_run = [], []
+
+    def frame_step(f):
+        dev_depth.copy_(frames[f], non_blocking=True)
+        fusion(dev_depth.view(torch.uint16))
+        mesh = fusion.get_phi_global_mesh()                     # marching cubes on the canonical model, every frame
+        nverts.append(int(mesh[3]) if world > 1 else int(mesh[0].shape[0]))
+        if fusion.solver is not None and fusion.solver.info is not None and f >= b["start_frame"]:
+            iters_run.append(int(fusion.solver.info.iters))
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    warm = b["start_frame"] + max(1, args.warmup - 2)          # rigid frames + the first solver frames (allocations, tensor maps)
+    for f in range(warm):
+        frame_step(f)
+    clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sync_all()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for f in range(warm, nframes):
+        frame_step(f)
+    e1.record()
+    sync_all()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    timed = nframes - warm
+    if rank == 0:
+        it = iters_run[-timed:]
+        print(json.dumps({
+            "metric": "pipeline_frames_per_s", "value": timed / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": timed, "warmup": warm,
+            "ms_per_step": ms / timed, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%d^3 volume, params_snoopy.ini (dims->%d, MAX_ITER->%d), %d-frame synthetic sequence (pulsating, translating sphere), "
+                                   "marching cubes on phi_global every frame; 1 step = 1 frame from pinned host memory" % (dim, dim, args.iters, nframes),
+                       "parallelism": "1 GPU" if world == 1 else "z-slab x%d (solver, fusion and marching cubes per slab)" % world},
+            "solver_iterations_per_frame": {"mean": float(np.mean(it)) if it else 0.0, "min": int(min(it)) if it else 0, "max": int(max(it)) if it else 0},
+            "mesh_vertices_last_frame": nverts[-1], "clocks": clk,
+            "e2e": {"value": timed / (ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": COLS * ROWS * 2, "d2h_bytes_per_step": 4 + 16 + 8},
+        }), flush=True)
+
+
 def run_reference(args, rank, world):
     """the unmodified reference CUDA through its own host API, same frames / same parameters (rank 0 only)"""
     if rank != 0:
@@ -315,6 +388,9 @@ def main():
     ap.add_argument("--dim", type=int, default=256)
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="solver", choices=["solver", "pipeline"],
+                    help="solver: BASELINE.json configs[2] (default, the headline metric); pipeline: configs[4], the per-frame pipeline incl. marching cubes")
+    ap.add_argument("--frames", type=int, default=50, help="pipeline workload: length of the synthetic sequence")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -328,7 +404,10 @@ def main():
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     if world > 1:
         dist.init_process_group("nccl")
-    run_ours(args, rank, world, torch, dist)
+    if args.workload == "pipeline":
+        run_pipeline(args, rank, world, torch, dist)
+    else:
+        run_ours(args, rank, world, torch, dist)
     if world > 1:
         dist.destroy_process_group()
 

@@ -244,3 +244,37 @@ def test_tiled_equals_generic_at_128(env):
     for k in ("psi", "phi_n_psi", "psi_inv", "phi_global_psi_inv"):
         assert_bits(a[k], b[k], "128^3 tiled vs generic: " + k)
     assert a["log"] == b["log"]
+
+
+def test_full_size_properties_at_256(env):
+    """BASELINE.json's headline size (256^3, configs[2]) -- the oracle would need minutes here, so size-independent properties:
+      * two independent kernel families (tiled TMA pipelines vs one-thread-per-voxel) agree bit for bit on every output
+      * determinism: the same solve twice gives the same bits
+      * fixed point: phi_n == phi_global and psi == identity => every update is exactly zero, psi stays the identity bit for
+        bit, the maximum update norm is 0 and the loop stops after its first iteration (solver.cu:183)"""
+    sf, orc, torch = env
+    dims = (256, 256, 256)
+    pg, pn, vs, trunc, eta = sphere_pair(dims, r=0.08, shift=0.002)
+    psi0 = wavy_psi(dims, amp=0.45)
+    a = run_solver(sf, torch, dims, pg, pn, psi0, vs, trunc, eta, 6, -1.0, 0.05, 0.4, variant=2)
+    keep = {k: a[k] for k in ("psi", "phi_n_psi", "psi_inv", "phi_global_psi_inv")}
+    log_a, norm_a = a["log"], a["info"].max_norm
+    del a
+    torch.cuda.empty_cache()
+    b = run_solver(sf, torch, dims, pg, pn, psi0, vs, trunc, eta, 6, -1.0, 0.05, 0.4, variant=1)
+    for k in keep:
+        assert_bits(keep[k], b[k], "256^3 tiled vs generic: " + k)
+    assert [r[:2] for r in log_a] == [r[:2] for r in b["log"]] and norm_a == b["info"].max_norm and norm_a > 0
+    del b
+    torch.cuda.empty_cache()
+    c = run_solver(sf, torch, dims, pg, pn, psi0, vs, trunc, eta, 6, -1.0, 0.05, 0.4, variant=2)
+    for k in keep:
+        assert_bits(keep[k], c[k], "256^3 determinism: " + k)
+    del c, keep
+    torch.cuda.empty_cache()
+    ident = orc.init_identity(*dims)
+    d = run_solver(sf, torch, dims, pg, pg, ident, vs, trunc, eta, 50, 0.0, 0.05, 0.4)
+    assert d["info"].iters == 1 and d["info"].converged == 1 and d["info"].max_norm == 0.0
+    assert_bits(d["psi"], ident, "fixed point: psi")
+    assert_bits(d["psi_inv"], ident, "fixed point: psi_inv")
+    assert_bits(d["phi_n_psi"][..., 0], pg[..., 0], "fixed point: phi_n o psi")
