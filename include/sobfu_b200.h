@@ -99,7 +99,15 @@ int sobfu_b200_solver_set_variant(sobfu_b200_solver *s, int variant);
  * without convergence checks; returns device ms of pass A, pass B and the whole loop */
 int sobfu_b200_solver_time_loop(sobfu_b200_solver *s, int iters, float *ms_pass_a, float *ms_pass_b, float *ms_loop);
 
-int sobfu_b200_sobolev_taps(int s, float lambda, float *taps); /* solver.cpp:160-262 */
+int sobfu_b200_sobolev_taps(int s, float lambda, float *taps); /* solver.cpp:160-262: the reference's tables, unit sum */
+/* the filter for ANY lambda > 0 and odd s in [3, 11]: (Id - lambda * Laplacian) S = delta on an s^3 grid
+ * (the system the reference's unused get_3d_sobolev_filter builds, solver.cpp:107-158), separated into its dominant rank-1
+ * factor and normalised to unit sum.  Reproduces the reference's tables to their printed digits where those are consistent. */
+int sobfu_b200_sobolev_taps_computed(int s, float lambda, float *taps);
+/* solver_create with options: SOBFU_B200_CREATE_COMPUTE_FILTER = use sobolev_taps_computed for a lambda that is not tabulated
+ * (s must still be 7: the kernels are 7-tap like the reference's, solver.cu:211) instead of refusing it */
+#define SOBFU_B200_CREATE_COMPUTE_FILTER 1u
+int sobfu_b200_solver_create_ex(sobfu_b200_solver **out, const sobfu_b200_params *p, unsigned flags);
 
 /* ---- deformation field: sobfu::cuda::DeformationField (include/sobfu/vector_fields.hpp:52-66) ---- */
 int sobfu_b200_init_identity(void *psi, int X, int Y, int Z);                       /* vector_fields.cu:56-79 */

@@ -59,6 +59,35 @@ def sobolev_taps(s, lam):
     return t[:s].copy()
 
 
+def sobolev_taps_computed(s, lam):
+    """Restatement of what the reference's unused get_3d_sobolev_filter builds (solver.cpp:107-158): (Id - lambda * L) S = delta on an
+    s^3 grid with the 7-point Laplacian truncated at the faces, solved densely; then the separation the tables of
+    decompose_sobolev_filter (solver.cpp:160-251) come from -- first left singular vector of the s x s^2 unfolding -- and the
+    unit-sum normalisation in fp32, left to right (solver.cpp:253-261).  numpy.linalg in double: independent of the product's
+    conjugate-gradient / power-iteration implementation."""
+    n = s ** 3
+    A = np.zeros((n, n))
+    for i in range(n):
+        z = i // (s * s)
+        y = (i - z * s * s) // s
+        x = i - s * (y + s * z)
+        A[i, i] = 1.0 + 6.0 * float(np.float32(lam))
+        for dx, dy, dz in ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)):
+            xx, yy, zz = x + dx, y + dy, z + dz
+            if 0 <= xx < s and 0 <= yy < s and 0 <= zz < s:
+                A[i, xx + s * (yy + s * zz)] = -float(np.float32(lam))
+    v = np.zeros(n)
+    v[n // 2] = 1.0
+    S = np.linalg.solve(A, v).reshape(s, s * s)
+    u = np.linalg.svd(S)[0][:, 0]
+    u = u * np.sign(u[s // 2])
+    raw = u.astype(np.float32)
+    total = np.float32(0)
+    for t in raw:
+        total = np.float32(total + t)
+    return raw, (raw / total).astype(np.float32)
+
+
 def init_identity(X, Y, Z):
     psi = np.empty((Z, Y, X, 4), dtype=np.float32)
     lib().orc_init_identity(_p(psi), X, Y, Z)
@@ -133,8 +162,9 @@ def estimate_inverse(psi, psi_inv, iters=48):
     return psi_inv
 
 
-def estimate_psi(phi_global, phi_n, psi, max_iter, max_update_norm, s, lam, alpha, w_reg, log_energies=0):
-    """returns dict(phi_n_psi, phi_global_psi_inv, psi (updated copy), psi_inv, result, log)"""
+def estimate_psi(phi_global, phi_n, psi, max_iter, max_update_norm, s, lam, alpha, w_reg, log_energies=0, taps=None):
+    """returns dict(phi_n_psi, phi_global_psi_inv, psi (updated copy), psi_inv, result, log); taps: seven explicit filter taps
+    (then s / lam are ignored)"""
     X, Y, Z = dims_of(phi_global)
     psi = psi.copy()
     phi_n_psi = np.zeros_like(phi_n)
@@ -142,9 +172,16 @@ def estimate_psi(phi_global, phi_n, psi, max_iter, max_update_norm, s, lam, alph
     psi_inv = np.zeros_like(psi)
     res = SolveResult()
     log = np.zeros((max(max_iter, 1), 4), dtype=np.float32)
-    rc = lib().orc_estimate_psi(_p(phi_global), _p(pgpi), _p(phi_n), _p(phi_n_psi), _p(psi), _p(psi_inv), X, Y, Z, int(max_iter),
-                                C.c_float(max_update_norm), int(s), C.c_float(lam), C.c_float(alpha), C.c_float(w_reg),
-                                int(log_energies), C.byref(res), _p(log))
+    if taps is not None:
+        t7 = np.ascontiguousarray(taps, dtype=np.float32)
+        assert t7.shape == (7,)
+        rc = lib().orc_estimate_psi_taps(_p(phi_global), _p(pgpi), _p(phi_n), _p(phi_n_psi), _p(psi), _p(psi_inv), X, Y, Z, int(max_iter),
+                                         C.c_float(max_update_norm), _p(t7), C.c_float(alpha), C.c_float(w_reg), int(log_energies),
+                                         C.byref(res), _p(log))
+    else:
+        rc = lib().orc_estimate_psi(_p(phi_global), _p(pgpi), _p(phi_n), _p(phi_n_psi), _p(psi), _p(psi_inv), X, Y, Z, int(max_iter),
+                                    C.c_float(max_update_norm), int(s), C.c_float(lam), C.c_float(alpha), C.c_float(w_reg),
+                                    int(log_energies), C.byref(res), _p(log))
     if rc != 0:
         raise ValueError("orc_estimate_psi failed: %d" % rc)
     return dict(phi_n_psi=phi_n_psi, phi_global_psi_inv=pgpi, psi=psi, psi_inv=psi_inv, iters=res.iters, max_norm=res.max_norm,

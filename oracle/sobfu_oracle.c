@@ -503,6 +503,15 @@ int orc_estimate_psi(const orc_f2 *phi_global, orc_f2 *phi_global_psi_inv, const
                      orc_solve_result *res, orc_iter_log *log) {
     float taps[16];
     if (s != 7 || orc_sobolev_taps(s, lambda, taps) != 0) return -1; /* KERNEL_RADIUS is 3: solver.cu:211 */
+    return orc_estimate_psi_taps(phi_global, phi_global_psi_inv, phi_n, phi_n_psi, psi, psi_inv, X, Y, Z, max_iter, max_update_norm,
+                                 taps, alpha, w_reg, log_energies, res, log);
+}
+
+/* the same loop with the seven filter taps given explicitly (filters outside the reference's tables) */
+int orc_estimate_psi_taps(const orc_f2 *phi_global, orc_f2 *phi_global_psi_inv, const orc_f2 *phi_n,
+                          orc_f2 *phi_n_psi, orc_f4 *psi, orc_f4 *psi_inv, int X, int Y, int Z, int max_iter,
+                          float max_update_norm, const float *taps, float alpha, float w_reg, int log_energies,
+                          orc_solve_result *res, orc_iter_log *log) {
     size_t N = (size_t)X * Y * Z;
     orc_f4 *scratch = (orc_f4 *)malloc(sizeof(orc_f4) * 5 * N);
     float *J = log_energies ? (float *)malloc(sizeof(float) * 16 * N) : NULL;

@@ -77,6 +77,10 @@ void  orc_estimate_inverse(const orc_f4 *psi, orc_f4 *psi_inv, int X, int Y, int
 
 /* solver.cu:85-205 : the whole estimate_psi pipeline. scratch is allocated internally.
  * log (may be NULL) must hold max_iter records. */
+int   orc_estimate_psi_taps(const orc_f2 *phi_global, orc_f2 *phi_global_psi_inv, const orc_f2 *phi_n,
+                            orc_f2 *phi_n_psi, orc_f4 *psi, orc_f4 *psi_inv, int X, int Y, int Z, int max_iter,
+                            float max_update_norm, const float *taps7, float alpha, float w_reg, int log_energies,
+                            orc_solve_result *res, orc_iter_log *log);
 int   orc_estimate_psi(const orc_f2 *phi_global, orc_f2 *phi_global_psi_inv, const orc_f2 *phi_n,
                        orc_f2 *phi_n_psi, orc_f4 *psi, orc_f4 *psi_inv, int X, int Y, int Z,
                        int max_iter, float max_update_norm, int s, float lambda, float alpha, float w_reg,

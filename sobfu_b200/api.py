@@ -77,6 +77,7 @@ class Params:
     lambda_: float = 0.1
     alpha: float = 0.0
     w_reg: float = 0.0
+    compute_filter: bool = False      # extension: compute the Sobolev filter for a lambda the reference does not tabulate
 
     def voxel_sizes(self):
         """params.hpp:34-37 -- fp32 division, as in the reference"""
@@ -207,7 +208,9 @@ class Solver:
         p.alpha, p.w_reg = float(params.alpha), float(params.w_reg)
         self._h = C.c_void_p()
         _dev()
-        check(lib().sobfu_b200_solver_create(C.byref(self._h), C.byref(p)))
+        # compute_filter (not a field of the reference's Params): a lambda outside the reference's tables gets the computed filter
+        flags = 1 if getattr(params, "compute_filter", False) else 0
+        check(lib().sobfu_b200_solver_create_ex(C.byref(self._h), C.byref(p), flags))
         self.info = None
 
     def __del__(self):

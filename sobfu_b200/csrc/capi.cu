@@ -80,6 +80,8 @@ extern "C" const char *sobfu_b200_last_error(void) { return g_err.c_str(); }
 extern "C" const char *sobfu_b200_version(void) { return "sobfu_b200 0.1 (sm_100a)"; }
 extern "C" int sobfu_b200_set_stream(void *s) { g_stream = (cudaStream_t)s; return 0; }
 
+static thread_local bool g_compute_filter = false;
+
 // decompose_sobolev_filter, src/sobfu/solver.cpp:160-262: tabulated taps, then fp32 normalisation to unit sum
 extern "C" int sobfu_b200_sobolev_taps(int s, float lambda, float *h) {
     struct Row { int s; float lambda; int n; float v[11]; };
@@ -102,6 +104,75 @@ extern "C" int sobfu_b200_sobolev_taps(int s, float lambda, float *h) {
         }
     // the reference leaves h_S_i uninitialised here (solver.cpp:160-251); we refuse instead
     return fail(SOBFU_B200_EINVAL, "no Sobolev filter tabulated for s=%d lambda=%g (solver.cpp:160-251)", s, (double)lambda);
+}
+
+// What the reference's dead get_3d_sobolev_filter (solver.cpp:107-158) set out to do, completed: solve (Id - lambda * L) S = delta
+// on an s^3 grid (L = 7-point Laplacian truncated at the grid faces, exactly the matrix built there), then separate S into its
+// dominant rank-1 factor -- the first left singular vector of the s x s^2 unfolding, unit L2 norm, positive -- and normalise to
+// unit sum as decompose_sobolev_filter does.  This procedure reproduces the reference's tables to their 5 printed digits for
+// (3, .1), (7, .1), (7, .2), (9, .05), (9, .1), (11, .1); the (7, .05) table differs in one tap (0.00015 for 0.00155, a typo
+// that parity keeps) and the (7, .4) table holds a different filter.  Conjugate gradients (the matrix is SPD) + power
+// iteration, in double.
+extern "C" int sobfu_b200_sobolev_taps_computed(int s, float lambda, float *h) {
+    if (!h || s < 3 || s > 11 || (s & 1) == 0 || !(lambda > 0.f) || !(lambda < 1e3f))
+        return fail(SOBFU_B200_EINVAL, "sobolev_taps_computed: s must be odd in [3, 11] and lambda in (0, 1000)");
+    const int n = s * s * s;
+    const double lam = (double)lambda;
+    auto apply = [&](const std::vector<double> &x, std::vector<double> &y) {       // y = (Id - lambda L) x
+        for (int z = 0; z < s; ++z)
+            for (int yy = 0; yy < s; ++yy)
+                for (int xx = 0; xx < s; ++xx) {
+                    const int i = xx + s * (yy + s * z);
+                    double nb = 0.0;
+                    if (xx + 1 < s) nb += x[i + 1];
+                    if (xx - 1 >= 0) nb += x[i - 1];
+                    if (yy + 1 < s) nb += x[i + s];
+                    if (yy - 1 >= 0) nb += x[i - s];
+                    if (z + 1 < s) nb += x[i + s * s];
+                    if (z - 1 >= 0) nb += x[i - s * s];
+                    y[i] = (1.0 + 6.0 * lam) * x[i] - lam * nb;
+                }
+    };
+    std::vector<double> S(n, 0.0), r(n, 0.0), pdir(n), Ap(n);
+    r[n / 2] = 1.0;                               // one-hot right-hand side (solver.cpp:148-149), start from S = 0
+    pdir = r;
+    double rr = 1.0;
+    for (int it = 0; it < 4 * n && rr > 1e-30; ++it) {
+        apply(pdir, Ap);
+        double pAp = 0.0;
+        for (int i = 0; i < n; ++i) pAp += pdir[i] * Ap[i];
+        const double a = rr / pAp;
+        double rr_new = 0.0;
+        for (int i = 0; i < n; ++i) { S[i] += a * pdir[i]; r[i] -= a * Ap[i]; rr_new += r[i] * r[i]; }
+        const double b = rr_new / rr;
+        for (int i = 0; i < n; ++i) pdir[i] = r[i] + b * pdir[i];
+        rr = rr_new;
+    }
+    // M = U U^T for the unfolding U[a][b], a = first index, b = the other two (S is symmetric in its three indices)
+    std::vector<double> M(s * s, 0.0), u(s, 0.0), v(s);
+    for (int a = 0; a < s; ++a)
+        for (int b = 0; b < s; ++b) {
+            double acc = 0.0;
+            for (int k = 0; k < s * s; ++k) acc += S[a + s * k] * S[b + s * k];
+            M[a * s + b] = acc;
+        }
+    u[s / 2] = 1.0;
+    for (int it = 0; it < 500; ++it) {
+        double nrm = 0.0;
+        for (int a = 0; a < s; ++a) {
+            double acc = 0.0;
+            for (int b = 0; b < s; ++b) acc += M[a * s + b] * u[b];
+            v[a] = acc;
+            nrm += acc * acc;
+        }
+        nrm = std::sqrt(nrm);
+        for (int a = 0; a < s; ++a) u[a] = v[a] / nrm;
+    }
+    const double sign = u[s / 2] < 0.0 ? -1.0 : 1.0;
+    float sum = 0.f;
+    for (int i = 0; i < s; ++i) { h[i] = (float)(sign * u[i]); sum += h[i]; }     // solver.cpp:253-261: fp32, left to right
+    for (int i = 0; i < s; ++i) h[i] /= sum;
+    return 0;
 }
 
 // __fsqrt_rd on the host: largest float r with r*r <= x (the product of two floats is exact in double)
@@ -378,6 +449,9 @@ extern "C" int sobfu_b200_solver_create(sobfu_b200_solver **out, const sobfu_b20
     sobfu_b200_solver *s = new sobfu_b200_solver();
     s->p = *p;
     int rc = sobfu_b200_sobolev_taps(p->s, p->lambda, s->taps);
+    // opt-in (SOBFU_B200_COMPUTE_FILTER=1 or sobfu_b200_solver_create_ex): a lambda the reference does not tabulate gets the
+    // filter its tables were derived by, instead of being refused
+    if (rc && p->s == 7 && (g_compute_filter || getenv("SOBFU_B200_COMPUTE_FILTER"))) rc = sobfu_b200_sobolev_taps_computed(p->s, p->lambda, s->taps);
     if (rc) { delete s; return rc; }
     s->dg = Dims{p->dims[0], p->dims[1], p->dims[2]};
     s->Ng = (size_t)s->dg.X * s->dg.Y * s->dg.Z;
@@ -406,6 +480,13 @@ extern "C" int sobfu_b200_solver_create(sobfu_b200_solver **out, const sobfu_b20
     if (rc) { sobfu_b200_solver_destroy(s); return rc; }
     *out = s;
     return 0;
+}
+
+extern "C" int sobfu_b200_solver_create_ex(sobfu_b200_solver **out, const sobfu_b200_params *p, unsigned flags) {
+    g_compute_filter = (flags & SOBFU_B200_CREATE_COMPUTE_FILTER) != 0;
+    const int rc = sobfu_b200_solver_create(out, p);
+    g_compute_filter = false;
+    return rc;
 }
 
 extern "C" size_t sobfu_b200_solver_workspace_bytes(sobfu_b200_solver *s) { return s ? s->ws_bytes : 0; }
