@@ -68,3 +68,31 @@ def test_taps_match_the_reference_table(built):
     t = (ctypes.c_float * 16)()
     assert lib().sobfu_b200_sobolev_taps(7, ctypes.c_float(0.3), t) != 0
     assert b"solver.cpp" in lib().sobfu_b200_last_error()
+
+
+def test_header_is_plain_c_and_links_from_c(built, tmp_path):
+    """the drop-in boundary is a C ABI: include/sobfu_b200.h compiles as C99 (-pedantic), a C program links against the library
+    and calls host-only entries (version, filter taps, slab partition) without a GPU"""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <sobfu_b200.h>
+#include <stdio.h>
+int main(void) {
+    float taps[11];
+    int z0 = -1, nz = -1;
+    if (!sobfu_b200_version()) return 1;
+    if (sobfu_b200_sobolev_taps(7, 0.1f, taps) != 0) return 2;
+    if (sobfu_b200_sobolev_taps(7, 0.3f, taps) == 0 || !sobfu_b200_last_error()[0]) return 3;   /* not tabulated: refused, with a message */
+    if (sobfu_b200_sobolev_taps_computed(7, 0.3f, taps) != 0) return 4;
+    if (sobfu_b200_slab_range(256, 3, 8, &z0, &nz) != 0 || z0 != 96 || nz != 32) return 5;
+    printf("%s %.6f\n", sobfu_b200_version(), taps[3]);
+    return 0;
+}
+''')
+    lib = os.path.dirname(built)
+    exe = str(tmp_path / "abi")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"), str(src), "-o", exe,
+                           "-L" + lib, "-lsobfu_b200", "-Wl,-rpath," + lib, "-Wl,-rpath,/usr/local/cuda/lib64"])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
