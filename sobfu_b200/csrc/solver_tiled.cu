@@ -643,7 +643,7 @@ int sm_count() {
 // Number of z chunks per range.  The CTAs take items round robin (item b, b + G, ...), ranges in the given order; a chunk of
 // c planes costs c + halo_planes * halo_cost plane-steps.  Ranges of fewer than 16 planes stay one chunk; for the others the
 // chunk count that minimises the busiest CTA's load -- given the items already placed before it -- is taken (chunks of >= 16
-// planes -- 8 for ranges under 64 planes -- so that the pipeline prologue stays a small share).
+// planes -- 8 for ranges under 64 planes or when 16-plane chunks cannot fill the CTAs -- so that the pipeline prologue stays a small share).
 Sched make_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_planes, double halo_cost, int ctas) {
     Sched s;
     s.tiles_x = (d.X + TX - 1) / TX;
@@ -659,7 +659,9 @@ Sched make_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_plane
         if (Z <= 0) continue;
         int best_nz = 1;
         double best_score = 1e300;
-        const int min_chunk = Z < 64 ? 8 : 16;      // thin slabs (many ranks): parallelism matters more than the prologue share
+        // chunks of >= 16 planes keep the pipeline prologue a small share; thin slabs (many ranks) and small volumes (16-plane
+        // chunks would leave CTAs without work, e.g. 128^3) may go down to 8: there parallelism matters more
+        const int min_chunk = (Z < 64 || xy * ((Z + 15) / 16) < ctas) ? 8 : 16;
         for (int nz = 1; nz <= 64; ++nz) {
             const int chunk = (Z + nz - 1) / nz;
             if (chunk < min_chunk && nz > 1) break;
@@ -668,7 +670,7 @@ Sched make_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_plane
             int item = s.nitems;
             for (int k = 0; k < nch; ++k) {
                 const int planes = (k + 1 < nch ? chunk : Z - chunk * (nch - 1));
-                const double cost = planes + halo_planes * halo_cost;
+                const double cost = planes + halo_planes * halo_cost + 1.0;      // + 1: fixed cost of opening an item
                 for (int t = 0; t < xy; ++t, ++item) trial[item % ctas] += cost;
             }
             double worst = 0.0;
@@ -680,7 +682,7 @@ Sched make_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_plane
         int item = s.nitems;
         for (int k = 0; k < s.nz[r]; ++k) {
             const int planes = (k + 1 < s.nz[r] ? s.zchunk[r] : Z - s.zchunk[r] * (s.nz[r] - 1));
-            for (int t = 0; t < xy; ++t, ++item) load[item % ctas] += planes + halo_planes * halo_cost;
+            for (int t = 0; t < xy; ++t, ++item) load[item % ctas] += planes + halo_planes * halo_cost + 1.0;
         }
         s.nitems += xy * s.nz[r];
     }
