@@ -198,6 +198,9 @@ int sobfu_b200_solver_attach_comm(sobfu_b200_solver *s, const void *id128_host, 
 #define SOBFU_B200_PEER_HANDLE_BYTES 128
 int sobfu_b200_solver_peer_export(sobfu_b200_solver *s, void *handle_block_host);
 int sobfu_b200_solver_peer_attach(sobfu_b200_solver *s, const void *all_handle_blocks_host);   /* NULL: detach */
+/* measurement aid (slab mode over NCCL, after an estimate_psi; collective): mean milliseconds per iteration of
+ * out5[0] A_mid, [1] wait for the psi halos + A_edge, [2] wait for the global maximum + B_edge, [3] B_mid, [4] the whole iteration */
+int sobfu_b200_solver_time_phases(sobfu_b200_solver *s, int iters, float *out5);
 
 #ifdef __cplusplus
 }

@@ -33,6 +33,7 @@ _FP, _IP = C.POINTER(C.c_float), C.POINTER(C.c_int)
 SIGNATURES = {
     "sobfu_b200_set_stream": [_P],
     "sobfu_b200_solver_create": [C.POINTER(_P), C.POINTER(Params)],
+    "sobfu_b200_solver_time_phases": [_P, _I, _FP],
     "sobfu_b200_solver_create_ex": [C.POINTER(_P), C.POINTER(Params), C.c_uint],
     "sobfu_b200_sobolev_taps_computed": [_I, _F, _FP],
     "sobfu_b200_solver_destroy": [_P],

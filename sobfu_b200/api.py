@@ -261,6 +261,12 @@ class Solver:
         check(lib().sobfu_b200_solver_time_loop(self._h, int(iters), C.byref(a), C.byref(b), C.byref(l)))
         return a.value, b.value, l.value
 
+    def time_phases(self, iters=50):
+        """slab mode over NCCL: (A_mid, wait + A_edge, wait + B_edge, B_mid, iteration) mean ms -- see include/sobfu_b200.h"""
+        out = (C.c_float * 5)()
+        check(lib().sobfu_b200_solver_time_phases(self._h, int(iters), out))
+        return tuple(out)
+
     def workspace_bytes(self):
         return int(lib().sobfu_b200_solver_workspace_bytes(self._h))
 

@@ -267,6 +267,8 @@ struct sobfu_b200_solver {
     unsigned long long push_items = 0;            // face items (per face) of one launch
     unsigned long long acked = 0, ack_items = 0;  // the same for pass A (items that read halo planes)
     unsigned int *tickets = nullptr;              // [max_iter]: CTAs of pass B that have finished (the last one publishes the maximum)
+    std::vector<cudaEvent_t> phase_ev;   // time_phases(): 5 timing events per iteration on the compute stream (empty otherwise)
+    size_t phase_pos = 0;
     bool psi_exchange_pending = false;   // ev_p has been recorded and not yet waited for by the compute stream
     bool max_pending = false;            // ev_m (global maximum of the previous iteration) likewise
     int variant = 0;
@@ -781,17 +783,29 @@ static int launch_iteration(sobfu_b200_solver *s, int it, int log, int *launches
         const ZRanges b_edge{2, {0, n - 4, 0}, {4, n, 0}, {0, 0, 0}}, b_mid{1, {4, 0, 0}, {n - 4, 0, 0}, {0, 0, 0}};
         LoopArgs a = s->args;
         a.a_uses_max = 0;
+        // measurement aid (sobfu_b200_solver_time_phases): timing events between the launches of the compute stream
+        auto mark = [&]() { if (s->phase_pos < s->phase_ev.size()) cudaEventRecord(s->phase_ev[s->phase_pos++], s->stream); };
+        // SOBFU_B200_SLAB_SCHED=3 (experiment, off by default): pass B as ONE launch -- the psi exchange then starts after the
+        // whole pass and hides behind A_mid of the next iteration only; saves the small B_edge launch (10 plane-steps of pipeline
+        // for 4 planes of output on 88 of 148 CTAs at 256^2) and one kernel boundary
+        static const bool whole_b = getenv("SOBFU_B200_SLAB_SCHED") && atoi(getenv("SOBFU_B200_SLAB_SCHED")) == 3;
+        mark();
         launch_pass_a_tma(a, s->tma, it, 0, a_mid, s->stream);
+        mark();
         if ((rc = join_psi_exchange(s))) return rc;
         launch_pass_a_tma(a, s->tma, it, 0, a_edge, s->stream);
+        mark();
         if ((rc = join_max(s))) return rc;
-        launch_pass_b_tma(a, s->tma, it, b_edge, s->stream);
+        if (whole_b) launch_pass_b_tma(a, s->tma, it, whole_slab(s), s->stream);
+        else launch_pass_b_tma(a, s->tma, it, b_edge, s->stream);
+        mark();
         CK(cudaEventRecord(s->ev_b, s->stream));
         CK(cudaStreamWaitEvent(s->comm_stream, s->ev_b, 0));
         if ((rc = exchange_psi(s, s->comm_stream))) return rc;
         CK(cudaEventRecord(s->ev_p, s->comm_stream));
         s->psi_exchange_pending = true;
-        launch_pass_b_tma(a, s->tma, it, b_mid, s->stream);
+        if (!whole_b) launch_pass_b_tma(a, s->tma, it, b_mid, s->stream);
+        mark();
         if (s->args.check) {
             ncclComm_t cm = s->comm_max ? s->comm_max : s->comm;
             cudaStream_t ms = s->comm_max ? s->max_stream : s->comm_stream;   // without a second communicator: behind the exchange
@@ -801,7 +815,7 @@ static int launch_iteration(sobfu_b200_solver *s, int it, int log, int *launches
             CK(cudaEventRecord(s->ev_m, ms));
             s->max_pending = true;
         }
-        *launches += 4;
+        *launches += whole_b ? 3 : 4;
         return 0;
     }
     // serial form: pass A on the owned planes, nabla_U halo exchange, pass B, psi halo exchange, global max
@@ -1025,6 +1039,48 @@ extern "C" int sobfu_b200_solver_time_loop(sobfu_b200_solver *s, int iters, floa
     if (ms_a) *ms_a = ta / iters;
     if (ms_b) *ms_b = tb / iters;
     if (ms_loop) *ms_loop = tl / iters;
+    return 0;
+}
+
+// Measurement aid for the z-slab (NCCL) schedule: `iters` iterations with timing events between the launches of the compute
+// stream.  out[0..3] = mean milliseconds of A_mid | wait psi halos + A_edge | wait global max + B_edge (or the whole pass B with
+// SOBFU_B200_SLAB_SCHED=3) | B_mid; out[4] = mean milliseconds of a whole iteration.  Collective: every rank calls it.
+extern "C" int sobfu_b200_solver_time_phases(sobfu_b200_solver *s, int iters, float *out5) {
+    if (!s || !out5 || iters <= 0 || iters > 1000) return fail(SOBFU_B200_EINVAL, "time_phases: bad argument");
+    if (!s->have_state) return fail(SOBFU_B200_EINVAL, "time_phases needs the state left by a previous estimate_psi");
+    if (s->nranks < 2 || peer_mode(s)) return fail(SOBFU_B200_EINVAL, "time_phases measures the NCCL slab schedule (needs attach_comm, no peer mode)");
+    cudaStream_t st = s->stream;
+    int launches = 0, rc = 0;
+    s->phase_ev.assign((size_t)5 * iters, nullptr);
+    for (auto &e : s->phase_ev) CK(cudaEventCreate(&e));
+    s->phase_pos = 0;
+    s->args.check = 1;                       // keep the MAX all-reduce in the schedule; maxkey[0] is scratch here
+    const float thr = s->args.thr;
+    s->args.thr = -1.f;                      // never converge
+    CK(cudaMemsetAsync(s->state, 0, sizeof(LoopState), st));
+    for (int i = 0; i < iters && !rc; ++i) rc = launch_iteration(s, 0, 0, &launches);
+    if (!rc) rc = join_psi_exchange(s);
+    if (!rc) rc = join_max(s);
+    s->args.thr = thr;
+    cudaError_t e = cudaStreamSynchronize(st);
+    const size_t got = s->phase_pos;
+    double acc[5] = {0, 0, 0, 0, 0};
+    int n = 0;
+    if (!rc && e == cudaSuccess && got == (size_t)5 * iters) {
+        for (int i = 0; i < iters; ++i) {
+            float ms = 0.f;
+            for (int k = 0; k < 4; ++k) { cudaEventElapsedTime(&ms, s->phase_ev[5 * i + k], s->phase_ev[5 * i + k + 1]); acc[k] += ms; }
+            if (i + 1 < iters) { cudaEventElapsedTime(&ms, s->phase_ev[5 * i], s->phase_ev[5 * (i + 1)]); acc[4] += ms; ++n; }
+        }
+        for (int k = 0; k < 4; ++k) out5[k] = (float)(acc[k] / iters);
+        out5[4] = n ? (float)(acc[4] / n) : 0.f;
+    }
+    for (auto &ev : s->phase_ev) if (ev) cudaEventDestroy(ev);
+    s->phase_ev.clear();
+    s->phase_pos = 0;
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(SOBFU_B200_ECUDA, "time_phases: %s", cudaGetErrorString(e));
+    if (got != (size_t)5 * iters) return fail(SOBFU_B200_EINVAL, "time_phases: the overlapped slab schedule was not used (volume too small / generic kernels)");
     return 0;
 }
 

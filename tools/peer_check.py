@@ -73,6 +73,12 @@ def main():
                 best = min(best, float(t.item()))
         assert info.iters == iters
         out[mode] = {"peer_attached": bool(getattr(solver, "peer", False)), "loop_ms_per_iter": best / iters, "iters_per_s": iters / (best * 1e-3), "launches": info.launches}
+        if mode == "nccl":      # where the time of an iteration goes on this rank: A_mid | wait + A_edge | wait + B_edge | B_mid | iteration
+            ph = torch.tensor(solver.time_phases(50), device="cuda")
+            dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+            out[mode]["phases_ms_max_over_ranks"] = [round(float(x), 5) for x in ph.tolist()]
+            ta, tb, tl = solver.time_loop(50)
+            out[mode]["whole_slab_kernels_ms"] = {"pass_a": ta, "pass_b": tb}
         del solver
     if rank == 0:
         print(json.dumps({"n_gpus": world, "dim": dim, "iters": iters, **out}), flush=True)
