@@ -1,6 +1,6 @@
 """torchrun worker (N >= 2 GPUs): (1) slab solve in peer mode == single-GPU solve, bit for bit, on a small volume (exercises
 ranks with TWO neighbours when N >= 3); (2) it/s of a 256^3 estimate_psi (200 iterations) in peer mode and over NCCL in the
-same process.  Usage: python -m torch.distributed.run --nproc-per-node N ... tools/peer_check.py [dim] [iters]"""
+same process.  Usage: python -m torch.distributed.run --nproc-per-node N ... tests/peer_check_worker.py [dim] [iters]"""
 import json
 import os
 import sys
