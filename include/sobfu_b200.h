@@ -201,6 +201,10 @@ int sobfu_b200_solver_peer_attach(sobfu_b200_solver *s, const void *all_handle_b
 /* measurement aid (slab mode over NCCL, after an estimate_psi; collective): mean milliseconds per iteration of
  * out5[0] A_mid, [1] wait for the psi halos + A_edge, [2] wait for the global maximum + B_edge, [3] B_mid, [4] the whole iteration */
 int sobfu_b200_solver_time_phases(sobfu_b200_solver *s, int iters, float *out5);
+/* host-only: the work decomposition of a launch of pass A (pass 0) or pass B (pass 1) over up to three z ranges of a slab of
+ * X x Y x Zlocal voxels, planned for `sms` SMs: items[i] = {cta, x0, y0, zb, ze, face} in issue order.  For the schedule tests. */
+int sobfu_b200_debug_schedule(int pass, int X, int Y, int Zlocal, int nranges, const int *lo, const int *hi, const int *face, int sms,
+                              int *items6, int cap, int *n_items, int *grid);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,7 @@ SIGNATURES = {
     "sobfu_b200_set_stream": [_P],
     "sobfu_b200_solver_create": [C.POINTER(_P), C.POINTER(Params)],
     "sobfu_b200_solver_time_phases": [_P, _I, _FP],
+    "sobfu_b200_debug_schedule": [_I, _I, _I, _I, _I, _IP, _IP, _IP, _I, _IP, _I, _IP, _IP],
     "sobfu_b200_solver_create_ex": [C.POINTER(_P), C.POINTER(Params), C.c_uint],
     "sobfu_b200_sobolev_taps_computed": [_I, _F, _FP],
     "sobfu_b200_solver_destroy": [_P],

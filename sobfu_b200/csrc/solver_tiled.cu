@@ -97,6 +97,25 @@ SB_DEVI float warp_sample_tex(cudaTextureObject_t tex, int ashift, int amask, fl
     return tex_finish(s);
 }
 
+// work item -> tile origin, plane range [zb, ze) and face tag.  Host and device: the same function drives the kernels and the
+// schedule checks of the CPU tests (sobfu_b200_debug_schedule).
+__host__ __device__ __forceinline__ void locate_item(const Sched &sc, int item, int TX, int TY, int &x0t, int &y0t, int &zb, int &ze, int &face) {
+    const int xy = sc.tiles_x * sc.tiles_y;
+    int tz = item / xy;
+    const int rem = item - tz * xy;
+    const int tyi = rem / sc.tiles_x;
+    x0t = (rem - tyi * sc.tiles_x) * TX;
+    y0t = tyi * TY;
+    // which range? (no dynamic indexing: the schedule stays in registers)
+    const bool r1 = tz >= sc.nz[0], r2 = tz >= sc.nz[0] + sc.nz[1];
+    tz -= r2 ? sc.nz[0] + sc.nz[1] : (r1 ? sc.nz[0] : 0);
+    const int chunk = r2 ? sc.zchunk[2] : (r1 ? sc.zchunk[1] : sc.zchunk[0]);
+    zb = (r2 ? sc.zlo[2] : (r1 ? sc.zlo[1] : sc.zlo[0])) + tz * chunk;
+    const int zend = r2 ? sc.zhi[2] : (r1 ? sc.zhi[1] : sc.zhi[0]);
+    ze = zb + chunk < zend ? zb + chunk : zend;
+    face = r2 ? sc.face[2] : (r1 ? sc.face[1] : sc.face[0]);
+}
+
 // position of a CTA in its plane stream: work item -> tile origin and plane range [p, p_last]
 template <int TX, int TY, int LO, int HI>
 struct Stream {
@@ -104,19 +123,7 @@ struct Stream {
     SB_DEVI void open(int it, const Sched &sc, int Z) {
         item = it;
         if (item >= sc.nitems) return;
-        const int xy = sc.tiles_x * sc.tiles_y;
-        int tz = item / xy;
-        const int rem = item - tz * xy;
-        const int tyi = rem / sc.tiles_x;
-        x0t = (rem - tyi * sc.tiles_x) * TX;
-        y0t = tyi * TY;
-        // which range? (no dynamic indexing: the schedule stays in registers)
-        const bool r1 = tz >= sc.nz[0], r2 = tz >= sc.nz[0] + sc.nz[1];
-        tz -= r2 ? sc.nz[0] + sc.nz[1] : (r1 ? sc.nz[0] : 0);
-        const int chunk = r2 ? sc.zchunk[2] : (r1 ? sc.zchunk[1] : sc.zchunk[0]);
-        zb = (r2 ? sc.zlo[2] : (r1 ? sc.zlo[1] : sc.zlo[0])) + tz * chunk;
-        ze = min(zb + chunk, r2 ? sc.zhi[2] : (r1 ? sc.zhi[1] : sc.zhi[0]));
-        face = r2 ? sc.face[2] : (r1 ? sc.face[1] : sc.face[0]);
+        locate_item(sc, item, TX, TY, x0t, y0t, zb, ze, face);
         (void)Z;
         p = zb - LO;
         p_last = ze - 1 + HI;
@@ -774,3 +781,29 @@ LaunchInfo launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int lo
 }
 
 }  // namespace sb
+
+// Host-only view of the work decomposition of a launch (no GPU needed): the items in issue order with the CTA that takes them
+// under the static round-robin assignment.  pass 0 = A, 1 = B; `sms` = number of SMs to plan for (148 on B200).
+// items: [cap][6] = {cta, x0, y0, zb, ze, face}.  Used by tests/test_schedule_cpu.py to check that every plane of every range is
+// covered exactly once for the shapes the multi-GPU runs use.
+extern "C" int sobfu_b200_debug_schedule(int pass, int X, int Y, int Zlocal, int nranges, const int *lo, const int *hi, const int *face, int sms,
+                                         int *items, int cap, int *n_items, int *grid) {
+    using namespace sb;
+    if (!lo || !hi || !face || !n_items || !grid || nranges < 1 || nranges > MAX_ZRANGES || sms < 1 || (pass != 0 && pass != 1)) return -1;
+    ZRanges zr;
+    zr.n = nranges;
+    for (int r = 0; r < MAX_ZRANGES; ++r) { zr.lo[r] = r < nranges ? lo[r] : 0; zr.hi[r] = r < nranges ? hi[r] : 0; zr.face[r] = r < nranges ? face[r] : 0; }
+    const int TX = pass ? pb::TX : pa::TX, TY = pass ? pb::TY : pa::TY;
+    const int ctas = pass ? sms : PA_CTAS * sms;
+    const Sched sc = pass ? make_sched(Dims{X, Y, Zlocal}, zr, TX, TY, 6, 0.35, ctas) : make_sched(Dims{X, Y, Zlocal}, zr, TX, TY, 2, 0.5, ctas);
+    *n_items = sc.nitems;
+    *grid = sc.nitems < ctas ? sc.nitems : ctas;
+    for (int i = 0; i < sc.nitems && i < cap; ++i) {
+        int x0, y0, zb, ze, f;
+        locate_item(sc, i, TX, TY, x0, y0, zb, ze, f);
+        int *o = items + 6 * i;
+        o[0] = *grid ? i % *grid : 0; o[1] = x0; o[2] = y0; o[3] = zb; o[4] = ze; o[5] = f;
+    }
+    return 0;
+}
+
