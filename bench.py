@@ -150,6 +150,8 @@ def run_ours(args, rank, world, torch, dist):
     for _ in range(args.warmup):
         frame_step(f); f += 1
     solver = fusion.solver
+    if args.variant:
+        solver.set_variant(args.variant)
     N = dim ** 3
 
     # ---- value: solver only, volumes resident ------------------------------------------------------------------
@@ -391,6 +393,7 @@ def main():
     ap.add_argument("--workload", default="solver", choices=["solver", "pipeline"],
                     help="solver: BASELINE.json configs[2] (default, the headline metric); pipeline: configs[4], the per-frame pipeline incl. marching cubes")
     ap.add_argument("--frames", type=int, default=50, help="pipeline workload: length of the synthetic sequence")
+    ap.add_argument("--variant", type=int, default=0, help="kernel variant of the solver (0 default; 1 generic; 2 tiled; 3 experimental)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))

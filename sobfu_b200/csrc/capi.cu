@@ -498,8 +498,8 @@ extern "C" int sobfu_b200_solver_get_taps(sobfu_b200_solver *s, float *t) {
     return 0;
 }
 extern "C" int sobfu_b200_solver_set_variant(sobfu_b200_solver *s, int v) {
-    if (!s || v < 0 || v > 2) return fail(SOBFU_B200_EINVAL, "variant must be 0, 1 or 2");
-    if (v == 2 && !(tiled_supported(s->d) && s->tma)) return fail(SOBFU_B200_EINVAL, "tiled/TMA kernels do not support dims %dx%dx%d", s->d.X, s->d.Y, s->d.Z);
+    if (!s || v < 0 || v > 3) return fail(SOBFU_B200_EINVAL, "variant must be 0 (default), 1 (generic), 2 (tiled) or 3 (tiled, warp-specialised pass A: experimental)");
+    if (v >= 2 && !(tiled_supported(s->d) && s->tma)) return fail(SOBFU_B200_EINVAL, "tiled/TMA kernels do not support dims %dx%dx%d", s->d.X, s->d.Y, s->d.Z);
     s->variant = v;
     return 0;
 }
@@ -658,6 +658,7 @@ static inline bool log_iter(const sobfu_b200_params &p, int iter1) {   // iter1 
 
 static ZRanges whole_slab(const sobfu_b200_solver *s) { return ZRanges{1, {0, 0, 0}, {s->d.Z, 0, 0}, {0, 0, 0}}; }
 static void run_pass_a(sobfu_b200_solver *s, int it, int log) {
+    set_pass_a_variant(s->variant == 3 ? 3 : 0);
     if (!use_tiled(s)) launch_pass_a_generic(s->args, it, log, s->stream);
     else launch_pass_a_tma(s->args, s->tma, it, log, whole_slab(s), s->stream);
 }
@@ -712,6 +713,7 @@ static int peer_check_error(sobfu_b200_solver *s) {   // stream already synchron
 // one gradient-descent iteration
 static int launch_iteration(sobfu_b200_solver *s, int it, int log, int *launches) {
     int rc = 0;
+    set_pass_a_variant(s->variant == 3 ? 3 : 0);
     const int n = s->d.Z;
     static const bool no_overlap = getenv("SOBFU_B200_NO_OVERLAP") != nullptr;
     if (peer_mode(s)) {

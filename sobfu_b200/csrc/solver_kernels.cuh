@@ -178,6 +178,7 @@ struct TmaMaps;   // opaque: CUtensorMaps of the nabla_U components (pass B) and
 TmaMaps *tma_maps_create(const LoopArgs &a);
 void tma_maps_destroy(TmaMaps *m);
 LaunchInfo launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, const ZRanges &zr, cudaStream_t st);
+void set_pass_a_variant(int v);   // 0: default kernel, 3: warp-specialised sampling (experimental); per host thread
 LaunchInfo launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, const ZRanges &zr, cudaStream_t st);   // grid 0: generic path
 
 // free-standing field kernels (field_ops.cu)

@@ -636,6 +636,274 @@ __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
 }
 }  // namespace pa
 
+// =============================================================================================================
+// pass A, warp-specialised (EXPERIMENTAL: variant 3, not the default)
+// =============================================================================================================
+// Same arithmetic and the same outputs as pa::pass_a_tma_kernel, different division of labour inside the CTA.  The warp of the
+// live TSDF (two gather4 texture round trips per sample) is 30 % of pass A's instructions and all of its long-scoreboard stalls;
+// here it is done by dedicated SAMPLER warps that run a plane or two ahead and need few registers (setmaxnreg.dec), while one
+// STENCIL warpgroup (setmaxnreg.inc) turns finished planes of w into the Laplacian / gradient / nabla_U.  More warps per SM hide
+// the texture latency, and the FP32 work of the stencil overlaps it.
+//   psi ring   : NSTAGE stages filled by TMA (lane 0 of the first sampler warp feeds AHEAD planes ahead of its own position);
+//                full[stage] (tx count) / empty[stage] (NSAMP sampler warps + NWS stencil warps arrive)
+//   w ring     : NWB planes of warped TSDF (tile + cross halo); wfull[b] (NSAMP arrivals) / wempty[b] (NWS arrivals)
+//   stream pos : every role walks the same continuous plane stream (items of a CTA back to back); position q uses psi stage
+//                q % NSTAGE and w buffer q % NWB; the stencil at position q reads psi and w of positions q-2, q-1, q and then
+//                releases position q-2
+#ifndef PAW_NSAMP
+#define PAW_NSAMP 8          // sampler warps (multiple of 4: setmaxnreg works on warpgroups)
+#define PAW_CTAS 2           // CTAs per SM
+#define PAW_REG_STENCIL 144   // 128 x 144 + 256 x 48 = 30720 = 384 threads x 80 registers at launch
+#define PAW_REG_SAMPLER 48
+#endif
+namespace paw {
+constexpr int LX = 8, RW = 32 / LX, NWS = 4, NSAMP = PAW_NSAMP;
+constexpr int NTHREADS = (NWS + NSAMP) * 32;
+constexpr int TX = 4 * LX, TY = NWS * RW;          // 32 x 16 outputs per plane, as pa
+constexpr int SX = TX + 8, SY = TY + 2;
+constexpr int NSTAGE = 6, AHEAD = 2, NWB = 5, PF_AHEAD = 4;
+constexpr int ARR_BYTES = ((SX * SY * 4 + 127) / 128) * 128;
+constexpr int STAGE_BYTES = 3 * ARR_BYTES;
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + NWB * ARR_BYTES + 128;
+constexpr unsigned TX_BYTES = 3u * SX * SY * 4u;
+constexpr int NHALO = 2 * TX + 2 * TY;
+constexpr int NSAMPLES = TX * TY + NHALO;
+static_assert(NSAMP % 4 == 0 && AHEAD <= NSTAGE - 3 && NWB >= 4, "ring depths");
+static_assert(TX == pa::TX && TY == pa::TY, "same tile as pass A: the schedule and the tensor maps are shared");
+
+template <bool TEX>
+__global__ void __launch_bounds__(NTHREADS, PAW_CTAS)
+    pass_a_ws_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__ CUtensorMap m1,
+                     const __grid_constant__ CUtensorMap m2, LoopArgs a, int it, Sched sc) {
+    if (a.a_uses_max ? loop_finished(a, it) : (a.check && a.state->converged)) {
+        if (a.check && blockIdx.x == 0 && threadIdx.x == 0 && !a.state->converged) {
+            a.state->iters = it;
+            a.state->converged = 1;
+        }
+        return;
+    }
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned smem = (smem_u32(smem_raw) + 127u) & ~127u;
+    const unsigned wbuf0 = smem + NSTAGE * STAGE_BYTES;
+    __shared__ unsigned long long bars[2 * NSTAGE + 2 * NWB];
+    const unsigned full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[NSTAGE]);
+    const unsigned wfull0 = smem_u32(&bars[2 * NSTAGE]), wempty0 = smem_u32(&bars[2 * NSTAGE + NWB]);
+
+    const Dims d = a.d, dg = a.dg;
+    const int X = d.X, XY = d.X * d.Y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NWS + NSAMP); }
+#pragma unroll
+        for (int b = 0; b < NWB; ++b) { mbar_init(wfull0 + 8 * b, NSAMP); mbar_init(wempty0 + 8 * b, NWS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    typedef Stream<TX, TY, 1, 1> St;
+
+    if (warp >= NWS) {
+        // ------------------------------------------------------------------------------------------------ samplers
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PAW_REG_SAMPLER));
+        const int sid = tid - NWS * 32;
+        const bool feeder = (sid == 0);
+        St pr{};                              // feeder only: position of the TMA loads in the plane stream
+        unsigned qi = 0;
+        auto feed = [&]() {
+            const unsigned slot = qi % NSTAGE, n = qi / NSTAGE;
+            if (n > 0) mbar_wait(empty0 + 8 * slot, (n - 1) & 1u);      // samplers and stencil are done with the plane that was here
+            const unsigned dst = smem + slot * STAGE_BYTES, bar = full0 + 8 * slot;
+            mbar_expect_tx(bar, TX_BYTES);
+            tma_load_3d(dst, &m0, bar, pr.x0t - 4, pr.y0t - 1, pr.p + PSI_HALO);
+            tma_load_3d(dst + ARR_BYTES, &m1, bar, pr.x0t - 4, pr.y0t - 1, pr.p + PSI_HALO);
+            tma_load_3d(dst + 2 * ARR_BYTES, &m2, bar, pr.x0t - 4, pr.y0t - 1, pr.p + PSI_HALO);
+            if (pr.p + PF_AHEAD <= pr.p_last) {
+                tma_prefetch_3d(&m0, pr.x0t - 4, pr.y0t - 1, pr.p + PF_AHEAD + PSI_HALO);
+                tma_prefetch_3d(&m1, pr.x0t - 4, pr.y0t - 1, pr.p + PF_AHEAD + PSI_HALO);
+                tma_prefetch_3d(&m2, pr.x0t - 4, pr.y0t - 1, pr.p + PF_AHEAD + PSI_HALO);
+            }
+            ++qi;
+            pr.next(sc, d.Z);
+        };
+        if (feeder) pr.open(blockIdx.x, sc, d.Z);
+        const float *__restrict__ pn = a.pn;
+        unsigned q = 0;
+        St ss;
+        for (ss.open(blockIdx.x, sc, d.Z); ss.valid(sc); ss.open(ss.item + (int)gridDim.x, sc, d.Z)) {
+            for (int p = ss.p; p <= ss.p_last; ++p) {
+                if (feeder) {
+                    while (qi <= q + AHEAD && pr.valid(sc)) feed();
+                }
+                const unsigned slot = q % NSTAGE, wb = q % NWB;
+                mbar_wait(full0 + 8 * slot, (q / NSTAGE) & 1u);
+                if (q >= (unsigned)NWB) mbar_wait(wempty0 + 8 * wb, ((q / NWB) - 1u) & 1u);   // the stencil has left the plane that was here
+                const unsigned stP = smem + slot * STAGE_BYTES, wcur = wbuf0 + wb * ARR_BYTES;
+                const bool plane_on = (a.z0 + p >= 0 && a.z0 + p < dg.Z);      // planes outside the volume are never used
+                if (plane_on) {
+                    // sample i -> cell of the staged box: the tile first (x fastest), then the cross halo (rows y0-1 and y0+TY,
+                    // columns x0-1 and x0+TX), as in pa::pass_a_tma_kernel.  off < 0: the cell lies outside the volume.
+                    auto cell = [&](int i) -> int {
+                        int bx, by;
+                        if (i < TX * TY) { bx = 4 + (i % TX); by = 1 + i / TX; }
+                        else {
+                            const int h = i - TX * TY;
+                            if (h < TX) { bx = 4 + h; by = 0; }
+                            else if (h < 2 * TX) { bx = 4 + h - TX; by = TY + 1; }
+                            else if (h < 2 * TX + TY) { bx = 3; by = 1 + h - 2 * TX; }
+                            else { bx = 4 + TX; by = 1 + h - 2 * TX - TY; }
+                        }
+                        const int gx = ss.x0t - 4 + bx, gy = ss.y0t - 1 + by;
+                        return (gx < 0 || gx >= X || gy < 0 || gy >= d.Y) ? -1 : (by * SX + bx) * 4;
+                    };
+                    // two samples per round: the gathers of both are in flight before the first result is touched
+                    for (int i = sid; i < NSAMPLES; i += 2 * NSAMP * 32) {
+                        const int o0 = cell(i), o1 = (i + NSAMP * 32 < NSAMPLES) ? cell(i + NSAMP * 32) : -1;
+                        if (TEX) {
+                            TexSample s0, s1;
+                            if (o0 >= 0) tex_issue(s0, a.pn_tex, a.ashift, a.amask, lds1(stP + o0), lds1(stP + o0 + ARR_BYTES), lds1(stP + o0 + 2 * ARR_BYTES), dg);
+                            if (o1 >= 0) tex_issue(s1, a.pn_tex, a.ashift, a.amask, lds1(stP + o1), lds1(stP + o1 + ARR_BYTES), lds1(stP + o1 + 2 * ARR_BYTES), dg);
+                            if (o0 >= 0) pa::sts1(wcur + o0, tex_finish(s0));
+                            if (o1 >= 0) pa::sts1(wcur + o1, tex_finish(s1));
+                        } else {
+                            if (o0 >= 0) pa::sts1(wcur + o0, warp_sample(pn, lds1(stP + o0), lds1(stP + o0 + ARR_BYTES), lds1(stP + o0 + 2 * ARR_BYTES), dg, X, XY));
+                            if (o1 >= 0) pa::sts1(wcur + o1, warp_sample(pn, lds1(stP + o1), lds1(stP + o1 + ARR_BYTES), lds1(stP + o1 + 2 * ARR_BYTES), dg, X, XY));
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(wfull0 + 8 * wb);        // this warp's share of w(p) is written (release)
+                    mbar_arrive(empty0 + 8 * slot);      // ... and it no longer reads psi(p)
+                }
+                ++q;
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------------------------------------- stencil
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PAW_REG_STENCIL));
+    const int lx = lane % LX, ty = warp * RW + lane / LX;
+    const unsigned own_off = (unsigned)(((ty + 1) * SX + 4 * lx + 4) * 4);
+    float *__restrict__ G[3] = {a.gx, a.gy, a.gz};
+    const GLayout gl = a.gl;
+    unsigned q = 0;
+    St cs;
+    for (cs.open(blockIdx.x, sc, d.Z); cs.valid(sc); cs.open(cs.item + (int)gridDim.x, sc, d.Z)) {
+        const int x0 = cs.x0t + 4 * lx, y = cs.y0t + ty;
+        const bool active = x0 < X && y < d.Y;
+        const int row = min(x0, X - 4) + X * min(y, d.Y - 1);
+        const bool y_lo = (y == 0), y_hi = (y == d.Y - 1), by = y_lo || y_hi;
+        const bool x_lo = (x0 == 0), x_hi = (x0 + 4 == X);
+        for (int p = cs.p; p <= cs.p_last; ++p) {
+            const unsigned slot = q % NSTAGE, wb = q % NWB;
+            const int zc = p - 1;
+            const bool centre_on = zc >= cs.zb;
+            float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (centre_on) g4 = *reinterpret_cast<const float4 *>(a.pg + row + XY * zc);
+            mbar_wait(full0 + 8 * slot, (q / NSTAGE) & 1u);
+            mbar_wait(wfull0 + 8 * wb, (q / NWB) & 1u);
+            ++q;                                  // q-1: plane p, q-2: plane p-1 (centre), q-3: plane p-2
+            if (centre_on) {
+                const unsigned stP = smem + slot * STAGE_BYTES + own_off;
+                const unsigned sC = smem + ((q + NSTAGE - 2u) % NSTAGE) * STAGE_BYTES + own_off;
+                const unsigned sM = smem + ((q + NSTAGE - 3u) % NSTAGE) * STAGE_BYTES + own_off;
+                const unsigned wP = wbuf0 + wb * ARR_BYTES + own_off;
+                const unsigned wC = wbuf0 + ((q + NWB - 2u) % NWB) * ARR_BYTES + own_off;
+                const unsigned wM = wbuf0 + ((q + NWB - 3u) % NWB) * ARR_BYTES + own_off;
+                const bool z_lo = (a.z0 + zc == 0), z_hi = (a.z0 + zc == dg.Z - 1), bz = z_lo || z_hi;   // global faces only
+                const bool edge = by || bz;
+                // ---- w_reg * laplacian(psi) at the centre plane (vector_fields.cu:291-337) ----
+                float Lw[3][4];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const unsigned p0 = sC + c * ARR_BYTES;
+                    const float4 C = lds4(p0);
+                    float4 Ym = lds4(p0 - SX * 4), Yp = lds4(p0 + SX * 4), Zp = lds4(stP + c * ARR_BYTES), Zm = lds4(sM + c * ARR_BYTES);
+                    const float xl = lds1(p0 - 4), xr = lds1(p0 + 16);
+                    const float xm[4] = {x_lo ? C.x : xl, C.x, C.y, x_hi ? C.w : C.z}, xp[4] = {x_lo ? C.x : C.y, C.z, C.w, x_hi ? C.w : xr};
+                    if (edge) {
+                        if (by) Yp = Ym = C;
+                        if (bz) Zp = Zm = C;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float v = mul(c4(C, j), -6.f);
+                        v = add(v, xp[j]);
+                        v = add(v, xm[j]);
+                        v = add(v, c4(Yp, j));
+                        v = add(v, c4(Ym, j));
+                        v = add(v, c4(Zp, j));
+                        v = add(v, c4(Zm, j));
+                        Lw[c][j] = mul(mul(v, -1.f), a.w_reg);
+                    }
+                }
+                // ---- central differences of the warped TSDF (vector_fields.cu:157-208) and nabla_U (solver.cu:15-33) ----
+                float nx[4], ny[4], nz[4], df[4];
+                {
+                    const float4 C = lds4(wC), Ym = lds4(wC - SX * 4), Yp = lds4(wC + SX * 4), wp = lds4(wP), wm = lds4(wM);
+                    const float xl = lds1(wC - 4), xr = lds1(wC + 16);
+                    const float xm[4] = {x_lo ? C.y : xl, C.x, C.y, C.z}, xp[4] = {C.y, C.z, C.w, x_hi ? C.z : xr};
+                    float4 Y1 = Yp, Y2 = Ym, Z1 = wp, Z2 = wm;
+                    if (edge) {
+                        if (y_hi) Y1 = Ym;
+                        if (y_lo) Y2 = Yp;
+                        if (z_hi) Z1 = wm;
+                        if (z_lo) Z2 = wp;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        nx[j] = mul(sub(xp[j], xm[j]), 0.5f);
+                        ny[j] = mul(sub(c4(Y1, j), c4(Y2, j)), 0.5f);
+                        nz[j] = mul(sub(c4(Z1, j), c4(Z2, j)), 0.5f);
+                        df[j] = sub(c4(C, j), c4(g4, j));
+                    }
+                }
+                const size_t o = gl.at(min(x0, X - 4), min(y, d.Y - 1), zc);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float u[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float n = (c == 0) ? nx[j] : (c == 1 ? ny[j] : nz[j]);
+                        u[j] = add(mul(n, df[j]), Lw[c][j]);
+                    }
+                    if (active) {
+                        float *__restrict__ g = G[c];
+                        const float4 uv = make_float4(u[0], u[1], u[2], u[3]);
+                        *reinterpret_cast<float4 *>(g + o) = uv;
+                        if (x0 == 0) *reinterpret_cast<float4 *>(g + o - 4) = make_float4(u[0], u[0], u[0], u[0]);
+                        if (x0 + 4 == X) *reinterpret_cast<float4 *>(g + o + 4) = make_float4(u[3], u[3], u[3], u[3]);
+                        if (y_lo) {
+#pragma unroll
+                            for (int k = 1; k <= 3; ++k) *reinterpret_cast<float4 *>(g + o - (size_t)k * gl.PX) = uv;
+                        }
+                        if (y_hi) {
+#pragma unroll
+                            for (int k = 1; k <= 3; ++k) *reinterpret_cast<float4 *>(g + o + (size_t)k * gl.PX) = uv;
+                        }
+                        if (z_lo) {
+#pragma unroll
+                            for (int k = 1; k <= 3; ++k) *reinterpret_cast<float4 *>(g + o - (size_t)k * gl.plane) = uv;
+                        }
+                        if (z_hi) {
+#pragma unroll
+                            for (int k = 1; k <= 3; ++k) *reinterpret_cast<float4 *>(g + o + (size_t)k * gl.plane) = uv;
+                        }
+                    }
+                }
+            }
+            // plane p-2 (position q-3) is no longer needed by this warp
+            __syncwarp();
+            if (lane == 0 && q >= 3u) {
+                mbar_arrive(empty0 + 8 * ((q - 3u) % NSTAGE));
+                mbar_arrive(wempty0 + 8 * ((q - 3u) % NWB));
+            }
+        }
+    }
+}
+}  // namespace paw
+
 int sm_count() {
     static int sms = 0;
     if (!sms) {
@@ -741,6 +1009,10 @@ TmaMaps *tma_maps_create(const LoopArgs &a) {
     ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
+    // experimental variant: a failure here only disables that variant
+    if (cudaFuncSetAttribute(paw::pass_a_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, paw::SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(paw::pass_a_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, paw::SMEM_BYTES) != cudaSuccess)
+        cudaGetLastError();
     if (!ok) {
         fprintf(stderr, "sobfu_b200: TMA tensor maps unavailable; using the generic kernels\n");
         cudaGetLastError();
@@ -762,17 +1034,31 @@ LaunchInfo launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, const 
     return launch_info(sc, grid);
 }
 
+// experimental kernels are selected per solver (sobfu_b200_solver_set_variant) through this per-thread switch, set by the host
+// loop before it launches; 0 = the default kernels
+static thread_local int g_pass_a_variant = 0;
+void set_pass_a_variant(int v) { g_pass_a_variant = v; }
+
 LaunchInfo launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, const ZRanges &zr, cudaStream_t st) {
     if (log) {   // logging iterations (rare): materialise the warped plane, then the generic kernel that also sums the energies
         launch_initial_warp(a, st);
         launch_pass_a_generic(a, it, 1, st);
         return LaunchInfo{0, {0, 0, 0}};
     }
+    const bool peer = a.peer_n > 0 && a.wait_halo;
+    if (g_pass_a_variant == 3 && !peer) {      // warp-specialised sampling (experimental)
+        const int wctas = PAW_CTAS * sm_count();
+        const Sched wsc = cached_sched(a.d, zr, paw::TX, paw::TY, 2, 0.5, wctas);
+        if (wsc.nitems == 0) return LaunchInfo{0, {0, 0, 0}};
+        const int wgrid = wsc.nitems < wctas ? wsc.nitems : wctas;
+        if (a.pn_tex) paw::pass_a_ws_kernel<true><<<wgrid, paw::NTHREADS, paw::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, wsc);
+        else paw::pass_a_ws_kernel<false><<<wgrid, paw::NTHREADS, paw::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, wsc);
+        return launch_info(wsc, wgrid);
+    }
     const int ctas = PA_CTAS * sm_count();
     const Sched sc = cached_sched(a.d, zr, pa::TX, pa::TY, 2, 0.5, ctas);
     if (sc.nitems == 0) return LaunchInfo{0, {0, 0, 0}};
     const int grid = sc.nitems < ctas ? sc.nitems : ctas;
-    const bool peer = a.peer_n > 0 && a.wait_halo;
     if (a.pn_tex && peer) pa::pass_a_tma_kernel<true, true><<<grid, pa::NTHREADS, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
     else if (a.pn_tex) pa::pass_a_tma_kernel<true, false><<<grid, pa::NTHREADS, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
     else if (peer) pa::pass_a_tma_kernel<false, true><<<grid, pa::NTHREADS, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);

@@ -1,6 +1,7 @@
 """GPU parity tests proper: the CUDA path, called through the C ABI (via the reference-shaped host classes), against the
 CPU oracle on identical seeded inputs.  Bit-exact on the solver core (tolerance stated where approximate units are used)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -278,3 +279,16 @@ def test_full_size_properties_at_256(env):
     assert_bits(d["psi"], ident, "fixed point: psi")
     assert_bits(d["psi_inv"], ident, "fixed point: psi_inv")
     assert_bits(d["phi_n_psi"][..., 0], pg[..., 0], "fixed point: phi_n o psi")
+
+
+@pytest.mark.skipif(not os.environ.get("SOBFU_B200_TEST_EXPERIMENTAL"), reason="experimental kernels are opt-in (SOBFU_B200_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("dims,iters", [((64, 64, 64), 9), ((96, 40, 36), 6), ((128, 24, 16), 5), ((32, 8, 8), 4)])
+def test_experimental_warp_specialised_pass_a(env, dims, iters):
+    """variant 3 (sampler warpgroups + stencil warpgroup, setmaxnreg) must give the bits of the default kernels; not part of the
+    default suite until it has been validated on hardware (run with a timeout: a pipeline bug here is a hang, not a wrong number)"""
+    sf, orc, torch = env
+    pg, pn, vs, trunc, eta = sphere_pair(dims, r=0.07)
+    psi0 = wavy_psi(dims, amp=0.5)
+    want = orc.estimate_psi(pg, pn, psi0, iters, -1.0, 7, 0.2, 0.02, 0.3)
+    got = run_solver(sf, torch, dims, pg, pn, psi0, vs, trunc, eta, iters, -1.0, 0.02, 0.3, variant=3, lam=0.2)
+    compare_solver(got, want, "variant 3 %s" % (dims,))
