@@ -1009,10 +1009,6 @@ TmaMaps *tma_maps_create(const LoopArgs &a) {
     ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
-    // experimental variant: a failure here only disables that variant
-    if (cudaFuncSetAttribute(paw::pass_a_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, paw::SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(paw::pass_a_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, paw::SMEM_BYTES) != cudaSuccess)
-        cudaGetLastError();
     if (!ok) {
         fprintf(stderr, "sobfu_b200: TMA tensor maps unavailable; using the generic kernels\n");
         cudaGetLastError();
@@ -1046,7 +1042,13 @@ LaunchInfo launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int lo
         return LaunchInfo{0, {0, 0, 0}};
     }
     const bool peer = a.peer_n > 0 && a.wait_halo;
-    if (g_pass_a_variant == 3 && !peer) {      // warp-specialised sampling (experimental)
+    if (g_pass_a_variant == 3 && !peer) {      // warp-specialised sampling (experimental); the default path never touches this kernel
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(paw::pass_a_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, paw::SMEM_BYTES);
+            cudaFuncSetAttribute(paw::pass_a_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, paw::SMEM_BYTES);
+            attr_set = true;
+        }
         const int wctas = PAW_CTAS * sm_count();
         const Sched wsc = cached_sched(a.d, zr, paw::TX, paw::TY, 2, 0.5, wctas);
         if (wsc.nitems == 0) return LaunchInfo{0, {0, 0, 0}};
