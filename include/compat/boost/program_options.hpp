@@ -10,6 +10,7 @@
  * the include path.
  */
 #pragma once
+#include <cctype>
 #include <istream>
 #include <map>
 #include <memory>

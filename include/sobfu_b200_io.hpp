@@ -182,16 +182,18 @@ inline uint32_t adler32(const uint8_t *d, size_t n) {
     return (b << 16) | a;
 }
 inline uint32_t crc32(const uint8_t *d, size_t n, uint32_t crc = 0) {
-    static uint32_t table[256];
-    static bool init = false;
-    if (!init) {
-        for (uint32_t i = 0; i < 256; ++i) {
-            uint32_t c = i;
-            for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xedb88320u ^ (c >> 1) : c >> 1;
-            table[i] = c;
+    struct Table {
+        uint32_t v[256];
+        Table() {
+            for (uint32_t i = 0; i < 256; ++i) {
+                uint32_t c = i;
+                for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xedb88320u ^ (c >> 1) : c >> 1;
+                v[i] = c;
+            }
         }
-        init = true;
-    }
+    };
+    static const Table tab;                 // initialised once, thread-safe (C++11 magic static)
+    const uint32_t *table = tab.v;
     crc = ~crc;
     for (size_t i = 0; i < n; ++i) crc = table[(crc ^ d[i]) & 0xffu] ^ (crc >> 8);
     return ~crc;

@@ -120,9 +120,14 @@ __global__ void triangles_kernel(const float2 *__restrict__ vol, Dims d, int nz,
     }
 }
 
+// the tables live in __constant__ memory, i.e. per device: uploaded once per device the library is used on
 bool upload_tables(std::string &err) {
-    static bool done = false;
-    if (done) return true;
+    static std::mutex mu;
+    static bool done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && done[dev]) return true;
     unsigned char nv[256];
     signed char tri[256 * 16];
     for (int c = 0; c < 256; ++c) {
@@ -136,7 +141,7 @@ bool upload_tables(std::string &err) {
         err = std::string("marching cubes tables: ") + cudaGetErrorString(cudaGetLastError());
         return false;
     }
-    done = true;
+    if (dev >= 0 && dev < 64) done[dev] = true;
     return true;
 }
 
