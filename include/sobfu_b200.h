@@ -206,6 +206,15 @@ int sobfu_b200_solver_time_phases(sobfu_b200_solver *s, int iters, float *out5);
 int sobfu_b200_debug_schedule(int pass, int X, int Y, int Zlocal, int nranges, const int *lo, const int *hi, const int *face, int sms,
                               int *items6, int cap, int *n_items, int *grid);
 
+/* ---- file formats of the application layer (host only; src/apps/demo.cpp:237-246, 301-309) ----
+ * 16-bit depth PNG (cv::imread(path, CV_LOAD_IMAGE_ANYDEPTH)), 8-bit mask PNG (cv::imread(path, CV_8U)), legacy-VTK mesh
+ * (pcl::io::saveVTKFile).  out == NULL: only the image size is returned.  Errors: sobfu_b200_io_last_error(). */
+int sobfu_b200_read_depth_png(const char *path, unsigned short *out, int capacity_pixels, int *cols, int *rows);
+int sobfu_b200_read_mask_png(const char *path, unsigned char *out, int capacity_pixels, int *cols, int *rows);
+int sobfu_b200_write_depth_png(const char *path, const unsigned short *depth, int cols, int rows);
+int sobfu_b200_write_vtk_mesh(const char *path, const float *vertices, long long n_vertices, int stride_floats);
+const char *sobfu_b200_io_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,10 @@ SIGNATURES = {
     "sobfu_b200_set_stream": [_P],
     "sobfu_b200_solver_create": [C.POINTER(_P), C.POINTER(Params)],
     "sobfu_b200_solver_time_phases": [_P, _I, _FP],
+    "sobfu_b200_read_depth_png": [C.c_char_p, _P, _I, _IP, _IP],
+    "sobfu_b200_read_mask_png": [C.c_char_p, _P, _I, _IP, _IP],
+    "sobfu_b200_write_depth_png": [C.c_char_p, _P, _I, _I],
+    "sobfu_b200_write_vtk_mesh": [C.c_char_p, _P, C.c_longlong, _I],
     "sobfu_b200_debug_schedule": [_I, _I, _I, _I, _I, _IP, _IP, _IP, _I, _IP, _I, _IP, _IP],
     "sobfu_b200_solver_create_ex": [C.POINTER(_P), C.POINTER(Params), C.c_uint],
     "sobfu_b200_sobolev_taps_computed": [_I, _F, _FP],
@@ -77,7 +81,7 @@ SIGNATURES = {
     "sobfu_b200_solver_peer_attach": [_P, _P],
     "sobfu_b200_slab_range": [_I, _I, _I, _IP, _IP],
 }
-OTHER_SYMBOLS = ["sobfu_b200_last_error", "sobfu_b200_version", "sobfu_b200_solver_workspace_bytes"]
+OTHER_SYMBOLS = ["sobfu_b200_last_error", "sobfu_b200_version", "sobfu_b200_solver_workspace_bytes", "sobfu_b200_io_last_error"]
 
 _lib = None
 
@@ -98,6 +102,7 @@ def lib():
         f.restype = C.c_int
     L.sobfu_b200_last_error.restype = C.c_char_p
     L.sobfu_b200_version.restype = C.c_char_p
+    L.sobfu_b200_io_last_error.restype = C.c_char_p
     L.sobfu_b200_solver_workspace_bytes.restype = C.c_size_t
     L.sobfu_b200_solver_workspace_bytes.argtypes = [_P]
     _lib = L

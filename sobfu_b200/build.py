@@ -12,13 +12,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libsobfu_b200.so")
-SOURCES = ["capi.cu", "solver_generic.cu", "solver_tiled.cu", "field_ops.cu", "tsdf_ops.cu", "marching_cubes.cu"]
+SOURCES = ["capi.cu", "solver_generic.cu", "solver_tiled.cu", "field_ops.cu", "tsdf_ops.cu", "marching_cubes.cu", "io_capi.cu"]
 # --ftz/--prec-* are the reference's numerics flags (CMakeLists.txt:42-44): parity depends on them
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--ftz=true", "--prec-div=false", "--prec-sqrt=false", "-Xcompiler", "-fPIC",
     "-I" + os.path.join(HERE, "..", "include"), "-I" + CSRC,
 ]
+# per-source additions: the host-only I/O entries use the dependency-free OpenCV stand-in (cv::imread over sobfu_b200_io.hpp)
+EXTRA_FLAGS = {"io_capi.cu": ["-I" + os.path.join(HERE, "..", "include", "compat")]}
 
 
 def _nvcc():
@@ -30,7 +32,8 @@ def _nvcc():
 
 def _digest():
     h = hashlib.sha256()
-    names = sorted(os.listdir(CSRC)) + ["../../include/sobfu_b200.h"]
+    names = sorted(os.listdir(CSRC)) + ["../../include/sobfu_b200.h", "../../include/sobfu_b200_io.hpp", "../../include/compat/opencv2/highgui/highgui.hpp",
+                                        "../../include/compat/opencv2/core/core.hpp"]
     for n in names:
         p = os.path.join(CSRC, n)
         if os.path.isfile(p):
@@ -52,7 +55,7 @@ def build_library(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + EXTRA_FLAGS.get(src, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
