@@ -467,6 +467,32 @@ struct Differentiator {
     void calculate_deformation_jacobian(Jacobian &J) { SOBFU_SHIM_CALL(sobfu_b200_jacobian(psi.data, J.data, psi.dims.x, psi.dims.y, psi.dims.z, 1)); }
     DeformationField psi;
 };
+// device-level free functions and helper structs of include/sobfu/solver.hpp:16-47,100-121 and vector_fields.hpp:258-277: the
+// plumbing between the reference's Solver and its kernels.  The stages are available one by one (the whole loop is
+// sobfu::cuda::Solver::estimate_psi); the three per-axis convolution launchers are provided as one call that does what the
+// reference's rows + columns + depth sequence does (solver.cu:152-159).
+inline void calculate_potential_gradient(kfusion::device::TsdfVolume &phi_n_psi, kfusion::device::TsdfVolume &phi_global, TsdfGradient &nabla_phi_n_o_psi,
+                                         Laplacian &L, PotentialGradient &nabla_U, float w_reg) {
+    SOBFU_SHIM_CALL(sobfu_b200_potential_gradient(phi_n_psi.data, phi_global.data, nabla_phi_n_o_psi.data, L.data, nabla_U.data, w_reg,
+                                                  nabla_U.dims.x, nabla_U.dims.y, nabla_U.dims.z));
+}
+inline void update_psi(DeformationField &psi, PotentialGradient &nabla_U_S, float4 *updates, float alpha) {
+    SOBFU_SHIM_CALL(sobfu_b200_update_psi(psi.data, nabla_U_S.data, updates, alpha, psi.dims.x, psi.dims.y, psi.dims.z));
+}
+// nabla_U_S = S *x nabla_U + S *y nabla_U + S *z nabla_U with the seven HOST taps h_S_i (convolution_rows / _columns / _depth)
+inline void convolve_sobolev(PotentialGradient &nabla_U_S, PotentialGradient &nabla_U, const float *h_S_i) {
+    SOBFU_SHIM_CALL(sobfu_b200_sobolev_filter(nabla_U_S.data, nabla_U.data, h_S_i, nabla_U.dims.x, nabla_U.dims.y, nabla_U.dims.z));
+}
+struct SpatialGradients {
+    SpatialGradients(TsdfGradient *nabla_phi_n_, TsdfGradient *nabla_phi_n_o_psi_, Jacobian *J_, Jacobian *J_inv_, Laplacian *L_, Laplacian *L_o_psi_inv_,
+                     PotentialGradient *nabla_U_, PotentialGradient *nabla_U_S_)
+        : nabla_phi_n(nabla_phi_n_), nabla_phi_n_o_psi(nabla_phi_n_o_psi_), J(J_), J_inv(J_inv_), L(L_), L_o_psi_inv(L_o_psi_inv_), nabla_U(nabla_U_),
+          nabla_U_S(nabla_U_S_) {}
+    TsdfGradient *nabla_phi_n, *nabla_phi_n_o_psi;
+    Jacobian *J, *J_inv;
+    Laplacian *L, *L_o_psi_inv;
+    PotentialGradient *nabla_U, *nabla_U_S;
+};
 // include/sobfu/reductor.hpp:24-50
 struct Reductor {
     Reductor(int3 dims_, float vsz_, float trunc_dist_) : dims(dims_), vsz(vsz_), trunc_dist(trunc_dist_), no_voxels(dims_.x * dims_.y * dims_.z) {
@@ -494,7 +520,29 @@ struct Reductor {
     float4 *updates;
 };
 }  // namespace device
+}  // namespace sobfu
 
+// global-scope helper structs of include/sobfu/solver.hpp:16-47
+struct SolverParams {
+    int verbosity, max_iter, s;
+    float max_update_norm, lambda, alpha, w_reg;
+};
+struct SDFs {
+    SDFs(kfusion::device::TsdfVolume &phi_global_, kfusion::device::TsdfVolume &phi_global_psi_inv_, kfusion::device::TsdfVolume &phi_n_,
+         kfusion::device::TsdfVolume &phi_n_psi_)
+        : phi_global(phi_global_), phi_global_psi_inv(phi_global_psi_inv_), phi_n(phi_n_), phi_n_psi(phi_n_psi_) {}
+    kfusion::device::TsdfVolume phi_global, phi_global_psi_inv, phi_n, phi_n_psi;
+};
+struct Differentiators {
+    Differentiators(sobfu::device::TsdfDifferentiator &tsdf_diff_, sobfu::device::Differentiator &diff_, sobfu::device::Differentiator &diff_inv_,
+                    sobfu::device::SecondOrderDifferentiator &second_order_diff_)
+        : tsdf_diff(tsdf_diff_), diff(diff_), diff_inv(diff_inv_), second_order_diff(second_order_diff_) {}
+    sobfu::device::TsdfDifferentiator tsdf_diff;
+    sobfu::device::Differentiator diff, diff_inv;
+    sobfu::device::SecondOrderDifferentiator second_order_diff;
+};
+
+namespace sobfu {
 namespace cuda {
 class VectorField {
 public:

@@ -30,6 +30,24 @@ std::vector<unsigned short> sphere_depth(int cols, int rows, float fx, float fy,
 }
 }  // namespace
 
+// compile-time check of the device-level helpers of include/sobfu/solver.hpp (never called: the stages are exercised through the
+// C ABI by the Python parity tests)
+static void device_level_api_compiles(kfusion::device::TsdfVolume &a, kfusion::device::TsdfVolume &b, sobfu::device::DeformationField &psi,
+                                      sobfu::device::TsdfGradient &g, sobfu::device::Laplacian &L, sobfu::device::PotentialGradient &u,
+                                      sobfu::device::PotentialGradient &us, sobfu::device::Jacobian &J, float4 *updates, const float *taps) {
+    SolverParams sp{0, 1, 7, 1e-3f, 0.1f, 0.1f, 0.2f};
+    SDFs sdfs(a, b, a, b);
+    sobfu::device::TsdfDifferentiator td(a);
+    sobfu::device::Differentiator d(psi), di(psi);
+    sobfu::device::SecondOrderDifferentiator sd(psi);
+    Differentiators diffs(td, d, di, sd);
+    sobfu::device::SpatialGradients sg(&g, &g, &J, &J, &L, &L, &u, &us);
+    sobfu::device::calculate_potential_gradient(sdfs.phi_n_psi, sdfs.phi_global, *sg.nabla_phi_n_o_psi, *sg.L, *sg.nabla_U, sp.w_reg);
+    sobfu::device::convolve_sobolev(*sg.nabla_U_S, *sg.nabla_U, taps);
+    sobfu::device::update_psi(psi, *sg.nabla_U_S, updates, sp.alpha);
+    (void)diffs;
+}
+
 class DropInTest : public ::testing::Test {
 protected:
     void SetUp() override {
