@@ -84,14 +84,18 @@ struct Huffman {
     }
 };
 
-inline void inflate_block(BitReader &br, const Huffman &lit, const Huffman &dist, std::vector<uint8_t> &out) {
+inline void inflate_block(BitReader &br, const Huffman &lit, const Huffman &dist, std::vector<uint8_t> &out, size_t max_out) {
     static const uint16_t lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
     static const uint8_t lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
     static const uint16_t dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
     static const uint8_t dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
     for (;;) {
         const int sym = lit.decode(br);
-        if (sym < 256) { out.push_back((uint8_t)sym); continue; }
+        if (sym < 256) {
+            if (out.size() >= max_out) throw io_error("inflate: output larger than expected");
+            out.push_back((uint8_t)sym);
+            continue;
+        }
         if (sym == 256) return;
         const int li = sym - 257;
         if (li >= 29) throw io_error("inflate: invalid length symbol");
@@ -100,6 +104,7 @@ inline void inflate_block(BitReader &br, const Huffman &lit, const Huffman &dist
         if (di >= 30) throw io_error("inflate: invalid distance symbol");
         const size_t d = dbase[di] + br.bits(dext[di]);
         if (d > out.size()) throw io_error("inflate: distance beyond the start of the output");
+        if (out.size() + (size_t)len > max_out) throw io_error("inflate: output larger than expected");
         const size_t from = out.size() - d;
         for (int k = 0; k < len; ++k) out.push_back(out[from + k]);     // may overlap: byte by byte
     }
@@ -107,13 +112,15 @@ inline void inflate_block(BitReader &br, const Huffman &lit, const Huffman &dist
 
 }  // namespace detail
 
-inline std::vector<uint8_t> zlib_inflate(const uint8_t *data, size_t n, size_t size_hint = 0) {
+// max_out bounds the output (a corrupt or hostile stream cannot make the reader allocate without limit); 0 = 1 GiB
+inline std::vector<uint8_t> zlib_inflate(const uint8_t *data, size_t n, size_t size_hint = 0, size_t max_out = 0) {
+    if (!max_out) max_out = (size_t)1 << 30;
     using namespace detail;
     if (n < 6) throw io_error("zlib: stream too short");
     if ((data[0] & 0x0f) != 8 || ((data[0] << 8 | data[1]) % 31) != 0 || (data[1] & 0x20)) throw io_error("zlib: bad header");
     BitReader br(data + 2, data + n);
     std::vector<uint8_t> out;
-    out.reserve(size_hint);
+    out.reserve(std::min(size_hint, (size_t)64 << 20));
     Huffman fixed_lit, fixed_dist;
     bool have_fixed = false;
     for (bool last = false; !last;) {
@@ -126,6 +133,7 @@ inline std::vector<uint8_t> zlib_inflate(const uint8_t *data, size_t n, size_t s
             if ((len ^ 0xffffu) != nlen) throw io_error("inflate: stored block length check failed");
             br.p += 4;
             if ((size_t)(br.end - br.p) < len) throw io_error("inflate: truncated stored block");
+            if (out.size() + len > max_out) throw io_error("inflate: output larger than expected");
             out.insert(out.end(), br.p, br.p + len);
             br.p += len;
         } else if (type == 1) {
@@ -140,7 +148,7 @@ inline std::vector<uint8_t> zlib_inflate(const uint8_t *data, size_t n, size_t s
                 fixed_dist.build(d, 30);
                 have_fixed = true;
             }
-            inflate_block(br, fixed_lit, fixed_dist, out);
+            inflate_block(br, fixed_lit, fixed_dist, out, max_out);
         } else if (type == 2) {
             static const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
             const int nlen = (int)br.bits(5) + 257, ndist = (int)br.bits(5) + 1, ncode = (int)br.bits(4) + 4;
@@ -168,7 +176,7 @@ inline std::vector<uint8_t> zlib_inflate(const uint8_t *data, size_t n, size_t s
             Huffman lit, dist;
             lit.build(lengths, nlen);
             dist.build(lengths + nlen, ndist);
-            inflate_block(br, lit, dist, out);
+            inflate_block(br, lit, dist, out, max_out);
         } else {
             throw io_error("inflate: invalid block type");
         }
@@ -260,7 +268,8 @@ inline Image decode_png(const uint8_t *d, size_t n) {
     if (!(bd == 8 || bd == 16 || (bd < 8 && (colour == 0 || colour == 3) && (bd == 1 || bd == 2 || bd == 4)))) throw io_error("png: unsupported bit depth");
     if (colour == 3 && bd == 16) throw io_error("png: bad palette bit depth");
     const size_t bpp_bits = (size_t)ch * bd, stride = ((size_t)im.width * bpp_bits + 7) / 8, bpp = std::max<size_t>(1, bpp_bits / 8);
-    std::vector<uint8_t> raw = zlib_inflate(idat.data(), idat.size(), (stride + 1) * im.height);
+    if ((uint64_t)im.width * (uint64_t)im.height > ((uint64_t)1 << 28)) throw io_error("png: image too large");
+    std::vector<uint8_t> raw = zlib_inflate(idat.data(), idat.size(), (stride + 1) * im.height, (stride + 1) * im.height);
     if (raw.size() < (stride + 1) * (size_t)im.height) throw io_error("png: image data too short");
     // undo the scanline filters in place
     std::vector<uint8_t> pix(stride * im.height);

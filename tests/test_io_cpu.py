@@ -269,3 +269,47 @@ def test_glob_lists_sorted_regular_files(tool, tmp_path):
         (d / n).write_bytes(b"x")
     r = subprocess.run([tool, "glob", str(d)], capture_output=True, text=True)
     assert [os.path.basename(l) for l in r.stdout.splitlines()] == ["depth_000001.png", "depth_000002.png", "depth_000010.png"]
+
+
+def test_png_reader_survives_corrupt_files(tmp_path):
+    """memory safety of the PNG / inflate code on hostile input: the reader (built with AddressSanitizer + UBSan) either decodes or
+    reports an empty image, for truncated files and for image data corrupted UNDER a valid chunk CRC (so the inflate code sees it)"""
+    exe = str(tmp_path / "io_tool_asan")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+                           "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "include", "compat"),
+                           os.path.join(ROOT, "tests", "cpp", "io_tool.cpp"), "-o", exe])
+    rng = np.random.RandomState(7)
+    depth = (500 + 30 * np.sin(np.arange(64)[None, :] / 5.0) + np.arange(48)[:, None]).astype(np.uint16)
+    good = str(tmp_path / "good.png")
+    write_png(good, depth[..., None], 16, 0, level=6)
+    blob = open(good, "rb").read()
+    i0 = blob.index(b"IDAT")
+    n = struct.unpack(">I", blob[i0 - 4:i0])[0]
+    body = bytearray(blob[i0 + 4:i0 + 4 + n])
+
+    def rebuild(new_body, ihdr=None):
+        out = bytearray(blob[:i0 - 4]) if ihdr is None else bytearray(b"\x89PNG\r\n\x1a\n" + struct.pack(">I", 13) + b"IHDR" + ihdr +
+                                                                     struct.pack(">I", zlib.crc32(b"IHDR" + ihdr) & 0xffffffff))
+        out += struct.pack(">I", len(new_body)) + b"IDAT" + bytes(new_body) + struct.pack(">I", zlib.crc32(b"IDAT" + bytes(new_body)) & 0xffffffff)
+        out += struct.pack(">I", 0) + b"IEND" + struct.pack(">I", zlib.crc32(b"IEND") & 0xffffffff)
+        return bytes(out)
+
+    cases = [blob[:k] for k in (0, 7, 8, 20, 33, 40, len(blob) // 2, len(blob) - 5)]
+    for _ in range(150):                                   # bit flips / byte edits inside the deflate stream, CRC kept valid
+        b = bytearray(body)
+        for _ in range(rng.randint(1, 4)):
+            b[rng.randint(0, len(b))] = rng.randint(0, 256)
+        cases.append(rebuild(b))
+    cases.append(rebuild(body[:len(body) // 2]))           # truncated stream
+    cases.append(rebuild(body, struct.pack(">IIBBBBB", 60000, 60000, 16, 0, 0, 0, 0)))      # header claims a huge image
+    cases.append(rebuild(body, struct.pack(">IIBBBBB", 64, 48, 16, 3, 0, 0, 0)))            # palette type with 16 bits
+    cases.append(rebuild(zlib.compress(b"\0" * (1 << 22), 9)))                              # far more data than the header announces
+    bad = str(tmp_path / "bad.png")
+    decoded = 0
+    for c in cases:
+        open(bad, "wb").write(c)
+        r = subprocess.run([exe, "imread", bad, str(ANYDEPTH), str(tmp_path / "o.raw")], capture_output=True, text=True)
+        assert r.returncode == 0 and (r.stdout.startswith("EMPTY") or r.stdout.startswith("OK")), (r.returncode, r.stdout[-300:], r.stderr[-1500:])
+        decoded += r.stdout.startswith("OK")
+    assert decoded < len(cases) // 2                        # most corruptions are detected (the rest only change pixel values)
+    assert imread(exe, good, ANYDEPTH, str(tmp_path)) is not None
