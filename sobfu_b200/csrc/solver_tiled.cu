@@ -372,7 +372,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
 // =============================================================================================================
 #ifndef PA_NW
 #define PA_NW 4         // warps per CTA
+#endif
+#ifndef PA_CTAS
 #define PA_CTAS 4       // CTAs per SM
+#endif
+#ifndef PA_LX
 #define PA_LX 8         // lanes per tile row (4 voxels each)
 #endif
 namespace pa {
@@ -652,8 +656,14 @@ __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
 //                releases position q-2
 #ifndef PAW_NSAMP
 #define PAW_NSAMP 8          // sampler warps (multiple of 4: setmaxnreg works on warpgroups)
+#endif
+#ifndef PAW_CTAS
 #define PAW_CTAS 2           // CTAs per SM
+#endif
+#ifndef PAW_REG_STENCIL
 #define PAW_REG_STENCIL 144   // 128 x 144 + 256 x 48 = 30720 = 384 threads x 80 registers at launch
+#endif
+#ifndef PAW_REG_SAMPLER
 #define PAW_REG_SAMPLER 48
 #endif
 namespace paw {
