@@ -131,13 +131,13 @@ def cpu_baseline(dim=160, min_seconds=4.0):
             "sample": "%d solver iterations at %d^3 (oracle/sobfu_oracle.c, OpenMP on all host cores), %.2f s" % (iters, dim, dt)}
 
 
-def run_ours(args, rank, world, torch, dist):
+def measure_solver(args, rank, world, torch, dist, dim, iters, steps, warmup):
+    """one solver-workload measurement (value, e2e, per-kernel roofline) at `dim`^3; returns (JSON line as a dict, fusion)"""
     import sobfu_b200 as sf
     from sobfu_b200.parallel import SlabFusion
-    dim, iters = args.dim, args.iters
     p = make_params(sf, dim, iters)
     fusion = sf.SobFusion(p) if world == 1 else SlabFusion(p, dist)   # z-slab over the ranks (SURVEY.md 8e)
-    frames = [torch.from_numpy(synth_depth(f).view(np.int16)).pin_memory() for f in range(1 + 2 * (args.warmup + args.steps))]
+    frames = [torch.from_numpy(synth_depth(f).view(np.int16)).pin_memory() for f in range(1 + 2 * (warmup + steps))]
     dev_depth = torch.empty((ROWS, COLS), dtype=torch.int16, device="cuda")
 
     def frame_step(f):
@@ -147,7 +147,7 @@ def run_ours(args, rank, world, torch, dist):
 
     frame_step(0)                                                  # frame 0 only initialises phi_global
     f = 1
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         frame_step(f); f += 1
     solver = fusion.solver
     if args.variant:
@@ -166,7 +166,7 @@ def run_ours(args, rank, world, torch, dist):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches, loop_ms = 0, 0.0
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         info = solver.estimate_psi(fusion.phi_global, fusion.phi_global_psi_inv, fusion.phi_n, fusion.phi_n_psi, fusion.psi, fusion.psi_inv)
         launches += info.launches
         loop_ms += info.loop_ms
@@ -178,7 +178,7 @@ def run_ours(args, rank, world, torch, dist):
     sync_all()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         frame_step(f); f += 1
     e3.record()
     sync_all()
@@ -197,47 +197,218 @@ def run_ours(args, rank, world, torch, dist):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     Nl = N // world                                   # voxels per GPU (z-slab)
-    traffic = {}
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json"))).get("%d^3" % dim, {}) if world == 1 else {}
-    except Exception:
-        pass
     dom, dom_ms, dom_bytes = ("pass_a", ms_a, ALGO_BYTES_PASS_A) if ms_a >= ms_b else ("pass_b", ms_b, ALGO_BYTES_PASS_B)
     achieved = dom_bytes * Nl / (dom_ms * 1e-3) / 1e9
     desc = {"pass_a": "pass_a (warp of the live TSDF + SDF-difference data-term gradient + Laplacian -> nabla_U)",
             "pass_b": "pass_b (Sobolev filter + psi update + max-norm partials)"}
     out = {
-        "metric": "solver_gvoxel_iters_per_s", "value": N * iters * args.steps / (ms * 1e-3) / 1e9, "unit": "Gvoxel-iter/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "metric": "solver_gvoxel_iters_per_s", "value": N * iters * steps / (ms * 1e-3) / 1e9, "unit": "Gvoxel-iter/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%d^3 volume, params_boxing.ini (dims->%d, MAX_ITER->%d), 640x480 synthetic sphere depth, 1 step = 1 frame = "
                                "estimate_psi with %d iterations" % (dim, dim, iters, iters), "l2": ("inputs exceed L2 (%.0f MB of solver state)" if 36 * N > 126e6 else
                           "NOT flushed: the solver state (%.0f MB) fits in the 126 MB L2 at this size; only volumes of >= 192^3 are HBM-bound") % (36 * N / 1e6),
                    "parallelism": "1 GPU" if world == 1 else "z-slab x%d" % world},
-        "solver_iters_per_s": iters * args.steps / (ms * 1e-3), "loop_ms_per_iter": loop_ms / (args.steps * iters),
-        "kernel_ms": {"pass_a": ms_a, "pass_b": ms_b, "iteration": ms_it if world == 1 else loop_ms / (args.steps * iters)},
+        "solver_iters_per_s": iters * steps / (ms * 1e-3), "loop_ms_per_iter": loop_ms / (steps * iters),
+        "kernel_ms": {"pass_a": ms_a, "pass_b": ms_b, "iteration": ms_it if world == 1 else loop_ms / (steps * iters)},
         # whole iteration incl. halo exchanges, from the loop of the timed estimate_psi calls (device events of the library)
-        "iteration_roofline_frac": ALGO_BYTES_ITER * Nl / (loop_ms / (args.steps * iters) * 1e-3) / 1e9 / peak,
+        "iteration_roofline_frac": ALGO_BYTES_ITER * Nl / (loop_ms / (steps * iters) * 1e-3) / 1e9 / peak,
         "pass_b_roofline_frac": ALGO_BYTES_PASS_B * Nl / (ms_b * 1e-3) / 1e9 / peak,
         "pass_a_roofline_frac": ALGO_BYTES_PASS_A * Nl / (ms_a * 1e-3) / 1e9 / peak,
         "clocks": clk,
-        "e2e": {"value": N * iters * args.steps / (ms_e2e * 1e-3) / 1e9, "unit": "Gvoxel-iter/s", "frames_per_s": args.steps / (ms_e2e * 1e-3),
+        "e2e": {"value": N * iters * steps / (ms_e2e * 1e-3) / 1e9, "unit": "Gvoxel-iter/s", "frames_per_s": steps / (ms_e2e * 1e-3),
                 "h2d_bytes_per_step": COLS * ROWS * 2, "d2h_bytes_per_step": 4 + iters * 24 + 16},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": desc[dom], "achieved": achieved,
                      "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                      "unit": "GB/s", "frac": achieved / peak, "algorithmic_bytes_per_voxel": dom_bytes,
-                     "traffic": traffic.get(dom), "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"},
+                     "traffic": None, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"},
     }
+    if world > 1:
+        peer = bool(getattr(fusion.solver, "peer", False))
+        out["config"]["multi_gpu"] = ("z-slab of %d planes per GPU; nabla_U on the 3 halo planes is recomputed locally, so an iteration needs "
+                                      "one psi halo exchange (4 planes) + one scalar MAX; " % (dim // world)) + (
+            "peer mode: pass B on the slab faces stores the planes straight into the neighbours' halo planes over NVLink (CUDA IPC) and "
+            "signals through counters per work item (face chunks first in both passes), maxima are published to every rank's table by the "
+            "last CTA; two kernels per iteration on one stream, no NCCL in the loop" if peer else
+            "NCCL: grouped ncclSend/Recv with both neighbours behind the mid-slab kernels + MAX all-reduce on a second communicator")
+    return out, fusion
+
+
+def _fingerprint(a):
+    import hashlib
+    return hashlib.blake2b(np.ascontiguousarray(a).view(np.uint8), digest_size=8).hexdigest()
+
+
+def _cmp(name, ours, theirs):
+    """bit comparison of two float arrays (host numpy or device tensors of the same kind)"""
+    if isinstance(ours, np.ndarray):
+        a, b = ours.view(np.uint32), theirs.view(np.uint32)
+        nbad = int(np.count_nonzero(a != b))
+        maxd = float(np.nanmax(np.abs(ours - theirs))) if nbad else 0.0
+        return {"bit_exact": nbad == 0, "words_differing": nbad, "max_abs_diff": maxd, "fingerprint": _fingerprint(ours)}
+    import torch
+    a, b = ours.contiguous().view(torch.int32), theirs.contiguous().view(torch.int32)
+    nbad = int((a != b).sum().item())
+    maxd = float((ours - theirs).abs().nan_to_num(0.0).max().item()) if nbad else 0.0
+    return {"bit_exact": nbad == 0, "words_differing": nbad, "max_abs_diff": maxd}
+
+
+def parity_block(args, rank, world, torch, dist, fusion, dim, iters):
+    """AFTER the timed regions (the checker is never inside them): one estimate_psi from the identity on this run's phi_global /
+    phi_n, compared bit for bit
+      N = 1 : with the reference's own CUDA (oracle/_ref, unmodified sources) on the same inputs
+      N > 1 : with a single-GPU solve of the whole volume on rank 0 (slabs gathered there)
+    for psi, psi^-1, phi_n o psi and phi_global o psi^-1."""
+    import sobfu_b200 as sf
+    names = ("psi", "psi_inv", "phi_n_psi", "phi_global_psi_inv")
+    solver = fusion.solver
+    X = Y = Z = dim
+    if world == 1:
+        from oracle import pyoracle as orc
+        if not os.path.exists(orc.REF):
+            return {"checked": False, "why": "oracle/_ref/libsobfu_ref.so is not built on this box"}
+        psi, psi_inv = sf.DeformationField((X, Y, Z)), sf.DeformationField((X, Y, Z))
+        info = solver.estimate_psi(fusion.phi_global, fusion.phi_global_psi_inv, fusion.phi_n, fusion.phi_n_psi, psi, psi_inv)
+        ours = {"psi": psi.get_data().cpu().numpy(), "psi_inv": psi_inv.get_data().cpu().numpy(),
+                "phi_n_psi": fusion.phi_n_psi.data().cpu().numpy(), "phi_global_psi_inv": fusion.phi_global_psi_inv.data().cpu().numpy()}
+        b = BOXING
+        vs = np.float32(b["vol_size"]) / np.float32(dim)
+        ref = orc.Reference((dim,) * 3, (b["vol_size"],) * 3, float(np.float32(b["trunc_vox"]) * vs), float(np.float32(b["eta_vox"]) * vs),
+                            b["max_weight"], 0, iters, b["s"], b["max_update_norm"], b["lam"], b["alpha"], b["w_reg"])
+        ref.upload_tsdf(ref.GLOBAL, fusion.phi_global.data().cpu().numpy())
+        ref.upload_tsdf(ref.N, fusion.phi_n.data().cpu().numpy())
+        ref.psi_clear(0)
+        devnull, saved = os.open(os.devnull, os.O_WRONLY), os.dup(1)
+        sys.stdout.flush()
+        os.dup2(devnull, 1)          # the reference prints from inside its loop
+        try:
+            ref.estimate_psi()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+        theirs = {"psi": ref.download_psi(0), "psi_inv": ref.download_psi(1), "phi_n_psi": ref.download_tsdf(ref.N_PSI),
+                  "phi_global_psi_inv": ref.download_tsdf(ref.GLOBAL_PSI_INV)}
+        ref.close()
+        res = {k: _cmp(k, ours[k], theirs[k]) for k in names}
+        return {"checked": True, "against": "oracle/_ref: the reference's own CUDA (unmodified sources, sm_100a), same inputs, identity start",
+                "volume": "%d^3" % dim, "iterations": int(info.iters), "bit_exact": all(r["bit_exact"] for r in res.values()), **res}
+    # ---- N > 1: the slab solve against a single-GPU solve of the whole volume on rank 0 ----
+    nz, z0 = fusion.nz, fusion.z0
+    psi, psi_inv = sf.DeformationField((X, Y, nz)), sf.DeformationField((X, Y, nz))
+    psi.get_data()[..., 2] += float(z0)
+    info = solver.estimate_psi(fusion.phi_global, fusion.phi_global_psi_inv, fusion.phi_n, fusion.phi_n_psi, psi, psi_inv)
+    mine = {"psi": psi.get_data(), "psi_inv": psi_inv.get_data(), "phi_n_psi": fusion.phi_n_psi.data(), "phi_global_psi_inv": fusion.phi_global_psi_inv.data()}
+
+    def gather0(t):
+        parts = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+        dist.gather(t.contiguous(), parts, dst=0)
+        return torch.cat(parts, 0) if rank == 0 else None
+
+    pg_full = gather0(fusion.phi_global.data())
+    got = {k: gather0(mine[k]) for k in names}
+    res = None
     if rank == 0:
-        if world > 1:
-            peer = bool(getattr(fusion.solver, "peer", False))
-            out["config"]["multi_gpu"] = ("z-slab of %d planes per GPU; nabla_U on the 3 halo planes is recomputed locally, so an iteration needs "
-                                          "one psi halo exchange (4 planes) + one scalar MAX; " % (dim // world)) + (
-                "peer mode: pass B on the slab faces stores the planes straight into the neighbours' halo planes over NVLink (CUDA IPC) and "
-                "signals through counters per work item (face items first), maxima are published to every rank's table by the last CTA; "
-                "two kernels per iteration on one stream, no NCCL in the loop" if peer else
-                "NCCL: grouped ncclSend/Recv with both neighbours behind the mid-slab kernels + MAX all-reduce on a second communicator")
+        p1 = make_params(sf, dim, iters)
+        vols = [sf.TsdfVolume(p1) for _ in range(3)]
+        vols[0].data().copy_(pg_full)
+        f_psi, f_inv = sf.DeformationField((X, Y, Z)), sf.DeformationField((X, Y, Z))
+        one = sf.Solver(p1)
+        info1 = one.estimate_psi(vols[0], vols[1], fusion.phi_n, vols[2], f_psi, f_inv)
+        want = {"psi": f_psi.get_data(), "psi_inv": f_inv.get_data(), "phi_n_psi": vols[2].data(), "phi_global_psi_inv": vols[1].data()}
+        cmp = {k: _cmp(k, got[k], want[k]) for k in names}
+        res = {"checked": True, "against": "a single-GPU solve of the whole volume on rank 0 (the library's one-GPU path, itself compared with the "
+                                          "reference CUDA in the N=1 line), slabs gathered from all ranks, identity start",
+               "volume": "%d^3" % dim, "iterations": int(info.iters), "iterations_single_gpu": int(info1.iters),
+               "max_norm_equal": bool(info.max_norm == info1.max_norm),
+               "bit_exact": all(r["bit_exact"] for r in cmp.values()) and info.iters == info1.iters and info.max_norm == info1.max_norm, **cmp}
+        del one, vols, f_psi, f_inv, want
+    del got, pg_full
+    dist.barrier()
+    return res
+
+
+def traffic_child(args):
+    """hidden mode (run under ncu by measure_traffic): a few solver iterations at --dim, nothing printed"""
+    import torch
+    import sobfu_b200 as sf
+    torch.cuda.set_device(0)
+    p = make_params(sf, args.dim, 6)
+    fusion = sf.SobFusion(p)
+    dev = torch.from_numpy(synth_depth(0).view(np.int16)).cuda()
+    fusion(dev.view(torch.uint16))
+    dev = torch.from_numpy(synth_depth(1).view(np.int16)).cuda()
+    fusion(dev.view(torch.uint16))
+    torch.cuda.synchronize()
+
+
+def measure_traffic(dim):
+    """DRAM bytes per launch of the two loop kernels, measured in THIS run: a child process of this script (6 solver iterations)
+    under `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`; the timed numbers never come from a profiled process."""
+    import csv
+    import io
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    cmd = [ncu, "--csv", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:pass_[ab]_tma",
+           "-s", "4", "-c", "6", sys.executable, os.path.abspath(__file__), "--traffic-child", "--dim", str(dim)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=dict(os.environ, SOBFU_B200_QUIET="1"))
+    except Exception as e:      # noqa: BLE001
+        return None, "ncu failed: %s" % e
+    lines = r.stdout.splitlines()
+    start = next((i for i, ln in enumerate(lines) if ln.startswith('"ID"')), None)
+    if start is None:
+        return None, "ncu produced no table (rc %d): %s" % (r.returncode, (r.stdout + r.stderr)[-300:].replace("\n", " | "))
+    acc = {}
+    for row in csv.DictReader(io.StringIO("\n".join(lines[start:]))):
+        k = "pass_a" if "pass_a" in row.get("Kernel Name", "") else ("pass_b" if "pass_b" in row.get("Kernel Name", "") else None)
+        if k is None or not row.get("Metric Value"):
+            continue
+        v = float(row["Metric Value"].replace(",", ""))
+        unit = row.get("Metric Unit", "byte").lower()
+        v *= {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+        acc.setdefault(k, {}).setdefault(row["ID"], 0.0)
+        acc[k][row["ID"]] += v
+    out = {k: sum(v.values()) / len(v) for k, v in acc.items() if v}
+    return (out or None), "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum in a child process of this run (%s)" % ", ".join(
+        "%s: %d launches" % (k, len(v)) for k, v in acc.items())
+
+
+def run_ours(args, rank, world, torch, dist):
+    out, fusion = measure_solver(args, rank, world, torch, dist, args.dim, args.iters, args.steps, args.warmup)
+    if not args.no_parity:
+        par = parity_block(args, rank, world, torch, dist, fusion, args.dim, args.iters)
+        if rank == 0:
+            out["parity"] = par
+    extra_dim = args.extra_dim if args.extra_dim is not None else (512 if world == 8 else 0)
+    if extra_dim and extra_dim != args.dim:
+        # BASELINE.json configs[3]: the 512^3 volume z-slabbed over the GPUs of the box (params_umbrella.ini has the same solver
+        # parameters as params_boxing.ini but for the truncation band); fewer steps, the same timing rules
+        del fusion
+        torch.cuda.empty_cache()
+        ex, fusion = measure_solver(args, rank, world, torch, dist, extra_dim, args.iters, min(args.steps, 3), 3)
+        if not args.no_parity:
+            par = parity_block(args, rank, world, torch, dist, fusion, extra_dim, args.iters)
+            if rank == 0:
+                ex["parity"] = par
+        if rank == 0:
+            out["extra_%d" % extra_dim] = {k: ex[k] for k in ("value", "unit", "steps", "warmup", "ms_per_step", "config", "solver_iters_per_s", "loop_ms_per_iter",
+                                                               "kernel_ms", "iteration_roofline_frac", "pass_a_roofline_frac", "pass_b_roofline_frac", "e2e",
+                                                               "gpu_launches", "parity") if k in ex}
+    del fusion
+    if rank == 0:
+        if world == 1 and not args.no_traffic:
+            tr, how = measure_traffic(args.dim)
+            r = out["roofline"]
+            dom = "pass_a" if r["kernel"].startswith("pass_a") else "pass_b"
+            r["traffic_source"] = how
+            if tr and dom in tr:
+                r["traffic"] = tr[dom]
+                r["dram_frac"] = tr[dom] / (out["kernel_ms"][dom] * 1e-3) / 1e9 / r["peak"]
+                out["dram_bytes_per_launch"] = tr
+                out["dram_frac"] = {k: tr[k] / (out["kernel_ms"][k] * 1e-3) / 1e9 / r["peak"] for k in tr if k in out["kernel_ms"]}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out), flush=True)
@@ -315,24 +486,30 @@ def run_pipeline(args, rank, world, torch, dist):
         }), flush=True)
 
 
-def run_reference(args, rank, world):
-    """the unmodified reference CUDA through its own host API, same frames / same parameters (rank 0 only)"""
-    if rank != 0:
-        return
+def _silenced(fn):
+    """the reference prints from inside the solver loop (solver.cu:115-117): keep stdout for the JSON line"""
+    devnull, saved = os.open(os.devnull, os.O_WRONLY), os.dup(1)
+    sys.stdout.flush()
+    os.dup2(devnull, 1)
+    try:
+        return fn()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(devnull)
+        os.close(saved)
+
+
+def measure_reference(dim, iters, steps, warmup):
+    """solver workload through the unmodified reference CUDA and its own host classes: (line as a dict)"""
     from oracle import pyoracle as orc
-    if not os.path.exists(orc.REF):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsobfu_ref.so was not built (needs /root/reference at build time)"}))
-        return
     import torch
     b = BOXING
-    dim, iters = args.dim, args.iters
     vs = np.float32(b["vol_size"]) / np.float32(dim)
     ref = orc.Reference((dim,) * 3, (b["vol_size"],) * 3, float(np.float32(b["trunc_vox"]) * vs), float(np.float32(b["eta_vox"]) * vs),
                         b["max_weight"], 0, iters, b["s"], b["max_update_norm"], b["lam"], b["alpha"], b["w_reg"],
                         pose_t=(-b["vol_size"] / 2, -b["vol_size"] / 2, b["pose_tz"]), intr=(b["fx"], b["fy"], b["cx"], b["cy"]))
-    frames = [synth_depth(f) for f in range(1 + 2 * (args.warmup + args.steps))]
-    devnull = os.open(os.devnull, os.O_WRONLY)
-    saved = os.dup(1)
+    frames = [synth_depth(f) for f in range(1 + 2 * (warmup + steps))]
 
     def frame_step(f):     # SobFusion::operator(), sob_fusion.cpp:71-145, through the reference's own classes
         ref.depth_to_dists(frames[f], b["ksz"], b["sigma_spatial"], b["sigma_depth"], b["trunc_depth"])
@@ -344,42 +521,115 @@ def run_reference(args, rank, world):
         ref.estimate_psi()
         ref.fuse(ref.GLOBAL, ref.N_PSI)
 
-    sys.stdout.flush()
-    os.dup2(devnull, 1)    # the reference prints from inside the solver loop (solver.cu:115-117)
-    try:
+    def body():
         frame_step(0)
         f = 1
-        for _ in range(args.warmup):
+        for _ in range(warmup):
             frame_step(f); f += 1
         clocks = ClockSampler(0)
         torch.cuda.synchronize()
         clocks.start()
-        ms = sum(ref.estimate_psi() for _ in range(args.steps))      # cudaEvent pair around Solver::estimate_psi
+        ms = sum(ref.estimate_psi() for _ in range(steps))      # cudaEvent pair around Solver::estimate_psi
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             frame_step(f); f += 1
         torch.cuda.synchronize()
-        ms_e2e = (time.perf_counter() - t0) * 1e3
-        clk = clocks.stop()
-    finally:
-        sys.stdout.flush()
-        os.dup2(saved, 1)
+        return ms, (time.perf_counter() - t0) * 1e3, clocks.stop()
+
+    ms, ms_e2e, clk = _silenced(body)
+    ref.close()
     N = dim ** 3
-    v = N * iters * args.steps / (ms * 1e-3) / 1e9
-    print(json.dumps({
-        "impl": "reference", "metric": "solver_gvoxel_iters_per_s", "value": v, "unit": "Gvoxel-iter/s", "n_gpus": 1, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+    v = N * iters * steps / (ms * 1e-3) / 1e9
+    return {
+        "impl": "reference", "metric": "solver_gvoxel_iters_per_s", "value": v, "unit": "Gvoxel-iter/s", "n_gpus": 1, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%d^3 volume, params_boxing.ini (dims->%d, MAX_ITER->%d), 640x480 synthetic sphere depth, 1 step = 1 frame = "
                                "estimate_psi with %d iterations" % (dim, dim, iters, iters), "parallelism": "1 GPU (the reference is single-GPU)"},
-        "solver_iters_per_s": iters * args.steps / (ms * 1e-3), "clocks": clk,
+        "solver_iters_per_s": iters * steps / (ms * 1e-3), "clocks": clk,
         "cpu_baseline": {"value": v, "unit": "Gvoxel-iter/s", "cores": os.cpu_count(), "kind": "reference",
                          "sample": "the reference has no CPU solver path: this is its own CUDA (sm_100a build of the unmodified sources) on one B200"},
-        "e2e": {"value": N * iters * args.steps / (ms_e2e * 1e-3) / 1e9, "unit": "Gvoxel-iter/s", "frames_per_s": args.steps / (ms_e2e * 1e-3),
+        "e2e": {"value": N * iters * steps / (ms_e2e * 1e-3) / 1e9, "unit": "Gvoxel-iter/s", "frames_per_s": steps / (ms_e2e * 1e-3),
                 "h2d_bytes_per_step": COLS * ROWS * 2, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    }
+
+
+def reference_pipeline(args):
+    """BASELINE.json configs[4] through the reference's own classes: SobFusion::operator() (sob_fusion.cpp:71-145) + marching cubes on
+    phi_global every frame (kfusion::cuda::MarchingCubes::run, the triangles stay on the device as in our arm)"""
+    from oracle import pyoracle as orc
+    import torch
+    b, dim = SNOOPY, args.dim
+    vs = np.float32(b["vol_size"]) / np.float32(dim)
+    ref = orc.Reference((dim,) * 3, (b["vol_size"],) * 3, float(np.float32(b["trunc_vox"]) * vs), float(np.float32(b["eta_vox"]) * vs),
+                        b["max_weight"], 0, args.iters, b["s"], b["max_update_norm"], b["lam"], b["alpha"], b["w_reg"],
+                        pose_t=(-b["vol_size"] / 2, -b["vol_size"] / 2, b["pose_tz"]), intr=(b["fx"], b["fy"], b["cx"], b["cy"]))
+    nframes = args.frames
+    frames = [synth_depth(f, radius=0.15 + 0.01 * np.sin(2 * np.pi * f / 25.0), intr=b) for f in range(nframes)]
+    nverts = []
+
+    def frame_step(f):
+        ref.depth_to_dists(frames[f], b["ksz"], b["sigma_spatial"], b["sigma_depth"], b["trunc_depth"])
+        if f == 0:
+            ref.integrate_dists(ref.GLOBAL)
+        else:
+            ref.tsdf_clear(ref.N)
+            ref.integrate_dists(ref.N)
+            if f < b["start_frame"]:
+                ref.fuse(ref.GLOBAL, ref.N)
+            else:
+                ref.estimate_psi()
+                ref.fuse(ref.GLOBAL, ref.N_PSI)
+        nverts.append(ref.marching_cubes_count(ref.GLOBAL))
+
+    warm = b["start_frame"] + max(1, args.warmup - 2)
+
+    def body():
+        for f in range(warm):
+            frame_step(f)
+        clocks = ClockSampler(0)
+        torch.cuda.synchronize()
+        clocks.start()
+        t0 = time.perf_counter()
+        for f in range(warm, nframes):
+            frame_step(f)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3, clocks.stop()
+
+    ms, clk = _silenced(body)
     ref.close()
+    timed = nframes - warm
+    return {
+        "impl": "reference", "metric": "pipeline_frames_per_s", "value": timed / (ms * 1e-3), "unit": "frames/s", "n_gpus": 1, "steps": timed, "warmup": warm,
+        "ms_per_step": ms / timed, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%d^3 volume, params_snoopy.ini (dims->%d, MAX_ITER->%d), %d-frame synthetic sequence (pulsating, translating sphere), "
+                               "marching cubes on phi_global every frame; 1 step = 1 frame from pinned host memory" % (dim, dim, args.iters, nframes),
+                   "parallelism": "1 GPU (the reference is single-GPU)"},
+        "mesh_vertices_last_frame": nverts[-1], "clocks": clk,
+        "cpu_baseline": {"value": timed / (ms * 1e-3), "unit": "frames/s", "cores": os.cpu_count(), "kind": "reference",
+                         "sample": "the reference has no CPU path: its own CUDA (sm_100a build of the unmodified sources) on one B200, wall clock over %d frames" % timed},
+        "e2e": {"value": timed / (ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": COLS * ROWS * 2, "d2h_bytes_per_step": 4},
+    }
+
+
+def run_reference(args, rank, world):
+    """the unmodified reference CUDA through its own host API, same frames / same parameters (rank 0 only)"""
+    if rank != 0:
+        return
+    from oracle import pyoracle as orc
+    if not os.path.exists(orc.REF):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsobfu_ref.so was not built (needs /root/reference at build time)"}))
+        return
+    if args.workload == "pipeline":
+        print(json.dumps(reference_pipeline(args)), flush=True)
+        return
+    out = measure_reference(args.dim, args.iters, args.steps, args.warmup)
+    extra_dim = args.extra_dim if args.extra_dim is not None else (512 if args.gpus == 8 else 0)
+    if extra_dim and extra_dim != args.dim:      # BASELINE.json configs[3]: the reference fits one B200 at 512^3 (304 B/voxel = 40.8 GB)
+        ex = measure_reference(extra_dim, args.iters, min(args.steps, 2), 1)
+        out["extra_%d" % extra_dim] = {k: ex[k] for k in ("value", "unit", "steps", "warmup", "ms_per_step", "config", "solver_iters_per_s", "e2e")}
+    print(json.dumps(out), flush=True)
 
 
 def main():
@@ -395,7 +645,13 @@ def main():
                     help="solver: BASELINE.json configs[2] (default, the headline metric); pipeline: configs[4], the per-frame pipeline incl. marching cubes")
     ap.add_argument("--frames", type=int, default=50, help="pipeline workload: length of the synthetic sequence")
     ap.add_argument("--variant", type=int, default=0, help="kernel variant of the solver (0 default; 1 generic; 2 tiled; 3 experimental)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-timing parity check (reference CUDA at N=1, single-GPU solve at N>1)")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu child process that measures DRAM bytes per launch (N=1)")
+    ap.add_argument("--extra-dim", type=int, default=None, help="also measure this volume size and report it under extra_<dim> (default: 512 when --gpus 8)")
+    ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.traffic_child:
+        return traffic_child(args)
     args.warmup = max(args.warmup, 3)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":

@@ -205,6 +205,13 @@ int sobfu_b200_solver_time_phases(sobfu_b200_solver *s, int iters, float *out5);
  * X x Y x Zlocal voxels, planned for `sms` SMs: items[i] = {cta, x0, y0, zb, ze, face} in issue order.  For the schedule tests. */
 int sobfu_b200_debug_schedule(int pass, int X, int Y, int Zlocal, int nranges, const int *lo, const int *hi, const int *face, int sms,
                               int *items6, int cap, int *n_items, int *grid);
+/* host-only: how peer mode splits the local planes [lo, hi) of a launch into | lower face chunk | upper face chunk | middle |
+ * (face chunks first, one z chunk each); ranges9 = {lo, hi, face} x 3 */
+int sobfu_b200_debug_peer_ranges(int pass, int X, int Y, int Zlocal, int lo, int hi, int has_lo, int has_hi, int sms, int *ranges9, int *n_ranges);
+/* measurement aid (peer mode, SOBFU_B200_TRACE=1): device-side timeline of the last estimate_psi, 8 words per launch in launch
+ * order (pass A, pass B, ...): first CTA start / last CTA end [ns], sum / max ns waited for the maxima table, sum / max ns
+ * waited for a neighbour's counter, CTAs, reserved */
+int sobfu_b200_solver_get_trace(sobfu_b200_solver *s, unsigned long long *out8, int cap_launches, int *n_launches);
 
 /* ---- file formats of the application layer (host only; src/apps/demo.cpp:237-246, 301-309) ----
  * 16-bit depth PNG (cv::imread(path, CV_LOAD_IMAGE_ANYDEPTH)), 8-bit mask PNG (cv::imread(path, CV_8U)), legacy-VTK mesh

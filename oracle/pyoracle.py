@@ -357,6 +357,14 @@ class Reference:
         return v[:k].copy(), n[:k].copy()
 
 
+def _ref_mc_count(self, which):
+    """marching cubes through the reference's own class, result left on the device (vertex count only)"""
+    return int(self.L.ref_marching_cubes(self.h, which, None, None, 0))
+
+
+Reference.marching_cubes_count = _ref_mc_count
+
+
 def mc_tables():
     lib().orc_mc_num_verts_table.restype = C.POINTER(C.c_int)
     lib().orc_mc_tri_table.restype = C.POINTER(C.c_int)

@@ -34,6 +34,8 @@ SIGNATURES = {
     "sobfu_b200_set_stream": [_P],
     "sobfu_b200_solver_create": [C.POINTER(_P), C.POINTER(Params)],
     "sobfu_b200_solver_time_phases": [_P, _I, _FP],
+    "sobfu_b200_debug_peer_ranges": [_I, _I, _I, _I, _I, _I, _I, _I, _I, _IP, _IP],
+    "sobfu_b200_solver_get_trace": [_P, C.POINTER(C.c_ulonglong), _I, _IP],
     "sobfu_b200_read_depth_png": [C.c_char_p, _P, _I, _IP, _IP],
     "sobfu_b200_read_mask_png": [C.c_char_p, _P, _I, _IP, _IP],
     "sobfu_b200_write_depth_png": [C.c_char_p, _P, _I, _I],

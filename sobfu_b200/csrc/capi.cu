@@ -272,6 +272,10 @@ struct sobfu_b200_solver {
     bool psi_exchange_pending = false;   // ev_p has been recorded and not yet waited for by the compute stream
     bool max_pending = false;            // ev_m (global maximum of the previous iteration) likewise
     int variant = 0;
+    ZRanges peer_za{}, peer_zb{};        // peer mode: face-tagged ranges of the two launches (plan_peer_ranges), computed once
+    bool peer_plan = false;
+    unsigned long long *trace = nullptr; // SOBFU_B200_TRACE: 8 words per launch (solver_kernels.cuh trace_*), 2 launches per iteration
+    int trace_launches = 0, trace_cap = 0;
     TmaMaps *tma = nullptr;
     cudaArray_t pn_array = nullptr;           // phi_n.x gather4 atlas (see LoopArgs::pn_tex)
     cudaTextureObject_t pn_tex = 0;
@@ -309,7 +313,7 @@ static void fill_args(sobfu_b200_solver *s) {
     a.cnt_lo = a.cnt_hi = nullptr; a.my_cnt = nullptr; a.expect_lo = a.expect_hi = 0ull;
     a.ack_lo = a.ack_hi = nullptr; a.my_ack = nullptr; a.expect_ack = 0ull;
     a.allmax = nullptr; a.peer_error = nullptr; a.peer_n = 0; a.push = 0; a.wait_halo = 0;
-    a.tickets = nullptr; a.my_rank = 0;
+    a.tickets = nullptr; a.my_rank = 0; a.trace = nullptr;
     for (int r = 0; r < MAX_PEERS; ++r) a.pub[r] = nullptr;
 }
 
@@ -387,6 +391,7 @@ static int alloc_workspace(sobfu_b200_solver *s, int z0, int nzl) {
         s->ws_bytes += s->Ng * 24;
     }
     fill_args(s);
+    s->peer_plan = false;
     if (tiled_supported(s->d)) s->tma = tma_maps_create(s->args);   // nullptr if the driver entry point is unavailable
     return 0;
 }
@@ -430,7 +435,7 @@ extern "C" int sobfu_b200_solver_destroy(sobfu_b200_solver *s) {
     if (s->pn_tex) cudaDestroyTextureObject(s->pn_tex);
     if (s->pn_surf) cudaDestroySurfaceObject(s->pn_surf);
     if (s->pn_array) cudaFreeArray(s->pn_array);
-    cudaFree(s->state); cudaFree(s->maxkey); cudaFree(s->tickets); cudaFree(s->energies);
+    cudaFree(s->state); cudaFree(s->maxkey); cudaFree(s->tickets); cudaFree(s->energies); cudaFree(s->trace);
     if (s->h_state) cudaFreeHost(s->h_state);
     for (auto &e : s->ev) if (e) cudaEventDestroy(e);
     if (s->ev_user) cudaEventDestroy(s->ev_user);
@@ -718,16 +723,22 @@ static int launch_iteration(sobfu_b200_solver *s, int it, int log, int *launches
     static const bool no_overlap = getenv("SOBFU_B200_NO_OVERLAP") != nullptr;
     if (peer_mode(s)) {
         // Peer mode: TWO launches per iteration on one stream, no NCCL and no events inside the loop.  Work items carry a face
-        // tag.  Pass A: the middle of the slab first, then the items that read halo planes (they wait for the neighbour's
-        // counter of the previous iteration and acknowledge when done).  Pass B: the face items first -- they wait for the
-        // neighbour's acknowledgement, store the new psi planes into the neighbour's halo planes themselves and count the item
-        // there at once, so the halo travels while the middle of the slab is computed; every CTA reads the maxima all ranks
-        // published for the previous iteration, and the last CTA to finish publishes this rank's maximum to every rank.
+        // tag; the face items are ordinary full-length z chunks issued FIRST in both passes (plan_peer_ranges).  Pass A: the
+        // face items are the only ones that read halo planes -- they wait for the neighbour's counter of the previous iteration
+        // and acknowledge when done.  Pass B: the face items wait for that acknowledgement (sent a whole A_mid earlier), store
+        // the new psi planes into the neighbour's halo planes themselves and count the item there, so the halo travels while
+        // the middle of the slab is computed; every CTA reads the maxima all ranks published for the previous iteration (a whole
+        // pass A earlier), and the last CTA to finish publishes this rank's maximum to every rank.
         const bool has_lo = s->rank > 0, has_hi = s->rank < s->nranks - 1;
         const int lo = has_lo ? -3 : 0, hi = has_hi ? n + 3 : n;
-        const ZRanges za{3, {1, lo, n - 1}, {n - 1, 1, hi}, {0, has_lo ? 1 : 0, has_hi ? 2 : 0}};
-        const ZRanges zb{3, {0, n - 4, 4}, {4, n, n - 4}, {has_lo ? 1 : 0, has_hi ? 2 : 0, 0}};
+        if (!s->peer_plan) {
+            s->peer_za = plan_peer_ranges(s->d, 0, lo, hi, has_lo, has_hi);
+            s->peer_zb = plan_peer_ranges(s->d, 1, 0, n, has_lo, has_hi);
+            s->peer_plan = true;
+        }
+        const ZRanges &za = s->peer_za, &zb = s->peer_zb;
         LoopArgs a = s->args;
+        if (s->trace && s->trace_launches + 2 <= s->trace_cap) a.trace = s->trace + 8 * (size_t)s->trace_launches;
         PeerCtl *mine = (PeerCtl *)(s->ctl + (size_t)s->epoch * s->ctl_bytes);
         const size_t pl = (size_t)(n + 2 * PSI_HALO) * s->XY;
         a.a_uses_max = 0;
@@ -761,6 +772,7 @@ static int launch_iteration(sobfu_b200_solver *s, int it, int log, int *launches
         a.wait_halo = 0;
         a.push = 1;
         a.expect_ack = s->acked;
+        if (a.trace) { a.trace += 8; s->trace_launches += 2; }
         if (s->args.check) {
             a.tickets = s->tickets;
             for (int r = 0; r < s->nranks; ++r)
@@ -854,6 +866,11 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
         CK(cudaMemsetAsync(s->energies, 0, 2 * mi * sizeof(double), st));
     }
     if ((rc = peer_begin(s, st))) return rc;
+    if (peer_mode(s) && getenv("SOBFU_B200_TRACE")) {     // measurement aid: device-side timeline of this solve's launches
+        if (!s->trace) { s->trace_cap = 2 * (mi > 0 ? mi : 1); CK(cudaMalloc(&s->trace, (size_t)s->trace_cap * 64)); }
+        CK(cudaMemsetAsync(s->trace, 0, (size_t)s->trace_cap * 64, st));
+        s->trace_launches = 0;
+    }
     launch_unpack(psi, phi_global, phi_n, s->args, st);
     if ((rc = exchange_psi(s, st)) || (rc = exchange_pg(s, st))) return rc;
     launch_initial_warp(s->args, st);
@@ -1083,6 +1100,20 @@ extern "C" int sobfu_b200_solver_time_phases(sobfu_b200_solver *s, int iters, fl
     if (rc) return rc;
     if (e != cudaSuccess) return fail(SOBFU_B200_ECUDA, "time_phases: %s", cudaGetErrorString(e));
     if (got != (size_t)5 * iters) return fail(SOBFU_B200_EINVAL, "time_phases: the overlapped slab schedule was not used (volume too small / generic kernels)");
+    return 0;
+}
+
+// Measurement aid (peer mode, SOBFU_B200_TRACE=1 in the environment): the device-side timeline of the last estimate_psi, 8 words
+// per launch in launch order (pass A, pass B, pass A, ...): first CTA start [ns, %globaltimer], last CTA end, sum / max ns the
+// CTAs waited for the maxima table, sum / max ns they waited for a neighbour's counter, number of CTAs, reserved.
+extern "C" int sobfu_b200_solver_get_trace(sobfu_b200_solver *s, unsigned long long *out, int cap_launches, int *n_launches) {
+    if (!s || !out || !n_launches) return fail(SOBFU_B200_EINVAL, "null argument");
+    const int n = s->trace ? (s->trace_launches < cap_launches ? s->trace_launches : cap_launches) : 0;
+    *n_launches = n;
+    if (n > 0) {
+        CK(cudaMemcpy(out, s->trace, (size_t)n * 64, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; ++i) out[8 * i] = ~out[8 * i];
+    }
     return 0;
 }
 

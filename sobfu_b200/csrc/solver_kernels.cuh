@@ -89,6 +89,8 @@ struct LoopArgs {
     unsigned int *tickets;                   // [max_iter], zeroed per solve; null: no publication (time_loop mode / NCCL mode)
     unsigned long long *pub[16];             // every rank's allmax table (own included)
     int my_rank;
+    // measurement aid (SOBFU_B200_TRACE=1): 8 words per launch, see trace_* below; null otherwise
+    unsigned long long *trace;
 };
 
 // control block of one rank in peer mode, exported through CUDA IPC; `allmax[max_iter * nranks]` follows the header
@@ -126,6 +128,42 @@ static __device__ __noinline__ unsigned long long peer_wait_ge(const unsigned lo
     return v;
 }
 
+// same wait by the lanes r < n of ONE warp, lane r on p[r]: the n polls are in flight together (n serial acquire loads of a
+// table the peers write cost ~1 us each, at the start of every CTA of pass B); returns the maximum of the values, bit 63 cleared
+static __device__ __noinline__ unsigned long long peer_wait_all_max(const unsigned long long *p, int n, unsigned long long *err) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long v = PEER_VALID;
+    if (lane < n) {
+        v = ld_acquire_sys(p + lane);
+        if (v < PEER_VALID && !(err && *reinterpret_cast<volatile unsigned long long *>(err))) {
+            const unsigned long long t0 = global_timer_ns();
+            while ((v = ld_acquire_sys(p + lane)) < PEER_VALID) {
+                __nanosleep(32);
+                if (global_timer_ns() - t0 > 4000000000ull) { if (err) *err = 1ull; break; }
+            }
+        }
+    }
+    v &= ~PEER_VALID;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+        v = other > v ? other : v;
+    }
+    return v;
+}
+
+// trace slot of one launch (device-side timeline, %globaltimer): [0] max(~start) [1] max(end) [2] sum / [3] max ns the CTAs waited
+// for the maxima table, [4] sum / [5] max ns they waited for a neighbour's counter, [6] CTAs, [7] max(~time the first wait ended)
+SB_DEV void trace_begin(unsigned long long *tr) {
+    if (tr) { atomicMax(tr + 0, ~global_timer_ns()); atomicAdd(tr + 6, 1ull); }
+}
+SB_DEV void trace_end(unsigned long long *tr) {
+    if (tr) atomicMax(tr + 1, global_timer_ns());
+}
+SB_DEV void trace_wait(unsigned long long *tr, int k, unsigned long long t0) {
+    if (tr) { const unsigned long long dt = global_timer_ns() - t0; atomicAdd(tr + k, dt); atomicMax(tr + k + 1, dt); }
+}
+
 // z ranges (local planes) a launch works on: the whole slab, or the planes next to / away from the slab faces
 // face: 0 = no neighbour involved, 1 = next to the lower neighbour, 2 = next to the upper one (peer mode only).  Work items
 // are issued in the order of the ranges.
@@ -150,16 +188,12 @@ SB_DEV bool loop_finished(const LoopArgs &a, int it) {
     return __fsqrt_rd(s) <= a.thr;      // norm = __fsqrt_rd(sum of squares), utils.hpp:279-281
 }
 // same decision in peer mode: the maximum of iteration it-1 over all ranks, from the table the ranks publish into (ONE
-// thread per block calls this and broadcasts the result)
+// whole warp per block calls this -- lane r polls rank r's entry -- and broadcasts the result)
 SB_DEV bool loop_finished_peer(const LoopArgs &a, int it) {
     if (!a.check) return false;
     if (a.state->converged) return true;
     if (it == 0) return false;
-    unsigned long long m = 0ull;
-    for (int r = 0; r < a.peer_n; ++r) {
-        const unsigned long long v = peer_wait_ge(a.allmax + (size_t)(it - 1) * a.peer_n + r, PEER_VALID, a.peer_error) & ~PEER_VALID;
-        m = v > m ? v : m;
-    }
+    const unsigned long long m = peer_wait_all_max(a.allmax + (size_t)(it - 1) * a.peer_n, a.peer_n, a.peer_error);
     const float s = __uint_as_float((unsigned)(m >> 32));
     return __fsqrt_rd(s) <= a.thr;
 }
@@ -180,6 +214,8 @@ void tma_maps_destroy(TmaMaps *m);
 LaunchInfo launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, const ZRanges &zr, cudaStream_t st);
 void set_pass_a_variant(int v);   // 0: default kernel, 3: warp-specialised sampling (experimental); per host thread
 LaunchInfo launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, const ZRanges &zr, cudaStream_t st);   // grid 0: generic path
+// peer mode: the planes [lo, hi) of a launch (pass 0 = A, 1 = B) as | lower face chunk | upper face chunk | middle |
+ZRanges plan_peer_ranges(const Dims d, int pass, int lo, int hi, bool has_lo, bool has_hi, int sms = 0);
 
 // free-standing field kernels (field_ops.cu)
 void launch_init_identity(float4 *psi, Dims d, cudaStream_t st);

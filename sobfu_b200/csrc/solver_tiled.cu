@@ -22,6 +22,7 @@
 // (nabla_U 12, psi 12 + 12); the reference's layouts and kernel split would need 48 + 64.  Results are bit-identical to the
 // generic kernels and to the oracle (tests/test_parity_gpu.py).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <utility>
@@ -31,6 +32,32 @@
 #include "tma_utils.cuh"
 
 namespace sb {
+
+// Programmatic dependent launch: the two kernels of an iteration alternate on one stream, and every kernel boundary costs ~5 us of
+// launch latency + CTA scheduling (device-side timeline, profiles/r2_peer_trace_n2.json) -- 3 % of an iteration at 256^3 on one
+// GPU, 15 % on a 32-plane slab.  Each CTA allows the next launch to start at once (griddepcontrol.launch_dependents): its CTAs are
+// scheduled as the SMs drain, run their prologue (barrier init) and then block in griddepcontrol.wait until this grid has
+// completed and flushed -- same ordering as a plain stream launch, minus the exposed latency.  Kernels launched without the
+// attribute (or behind an event wait) see both instructions as no-ops.
+SB_DEVI void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+SB_DEVI void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args &&...args) {
+    static const bool off = getenv("SOBFU_B200_PDL") == nullptr;   // opt-in: measured neutral at 256^3 on one GPU (profiles/r2_tuning_log.md)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = off ? 0 : 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 struct TmaMaps {
     CUtensorMap g[3];      // nabla_U components (padded), pass B input
@@ -159,10 +186,27 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
                       const __grid_constant__ CUtensorMap mapz, const __grid_constant__ CUtensorMap mpx,
                       const __grid_constant__ CUtensorMap mpy, const __grid_constant__ CUtensorMap mpz, LoopArgs a, int it,
                       Sched sc) {
+    pdl_launch_dependents();
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned smem = (smem_u32(smem_raw) + 127u) & ~127u;
+    __shared__ unsigned long long bars[2 * NSTAGE];
+    __shared__ unsigned long long skey[NW];
+    const unsigned full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[NSTAGE]);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NW); }
+        mbar_fence_init();
+    }
+    pdl_wait();        // everything below reads what the previous launches wrote
     bool fin;
-    if (PEER && a.peer_n > 0) {      // peer mode: one thread waits for the maxima every rank published, the block follows
+    if (PEER && threadIdx.x == 0) trace_begin(a.trace);
+    if (PEER && a.peer_n > 0) {      // peer mode: one warp waits for the maxima every rank published (lane r: rank r), the block follows
         __shared__ int s_fin;
-        if (threadIdx.x == 0) s_fin = loop_finished_peer(a, it) ? 1 : 0;
+        if (threadIdx.x < 32) {
+            const unsigned long long t0 = a.trace ? global_timer_ns() : 0ull;
+            const bool f = loop_finished_peer(a, it);
+            if (threadIdx.x == 0) { s_fin = f ? 1 : 0; trace_wait(a.trace, 2, t0); }
+        }
         __syncthreads();
         fin = s_fin != 0;
     } else {
@@ -175,24 +219,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
         }
         return;
     }
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const unsigned smem = (smem_u32(smem_raw) + 127u) & ~127u;
-    __shared__ unsigned long long bars[2 * NSTAGE];
-    __shared__ unsigned long long skey[NW];
-    const unsigned full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[NSTAGE]);
-
     const Dims d = a.d;
     const int X = d.X, XY = d.X * d.Y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lx = lane % LX, ty = warp * RW + lane / LX;
     const unsigned own_off = (unsigned)(((ty + 3) * SX + 4 * lx + 4) * 4);
     const unsigned psi0 = smem + NSTAGE * STAGE_BYTES, psi_own = (unsigned)((ty * TX + 4 * lx) * 4);
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NW); }
-        mbar_fence_init();
-    }
-    __syncthreads();
+    __syncthreads();   // barrier init (above) visible to the block
 
     typedef Stream<TX, TY, 3, 3> St;
     if (warp == NW) {
@@ -257,7 +290,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
         const int row = min(x0, X - 4) + X * min(y, d.Y - 1);
         const bool face_item = PEER && a.push && cs.face != 0;
         if (face_item && !(ack_seen & cs.face)) {   // peer mode: the neighbour has read the halo planes this item is about to overwrite
-            if (tid == 0) peer_wait_ge(a.my_ack + (cs.face - 1), a.expect_ack, a.peer_error);
+            if (tid == 0) {
+                const unsigned long long t0 = a.trace ? global_timer_ns() : 0ull;
+                peer_wait_ge(a.my_ack + (cs.face - 1), a.expect_ack, a.peer_error);
+                trace_wait(a.trace, 4, t0);
+            }
             asm volatile("bar.sync 1, %0;" ::"r"(NW * 32) : "memory");
             ack_seen |= cs.face;
         }
@@ -338,9 +375,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
             if (lane == 0 && q >= 4u) mbar_arrive(empty0 + 8 * ((q - 4u) % NSTAGE));
         }
         if (face_item) {   // the planes of this item are in the neighbour's halo: count the item there
-            __threadfence_system();                                      // this thread's stores to the neighbour are performed ...
+            // every consumer's stores to the neighbour are issued (block barrier), then ONE thread's system-scope fence orders them
+            // -- cumulatively -- before the counter the neighbour polls; the other warps go on with the next item meanwhile
             asm volatile("bar.sync 1, %0;" ::"r"(NW * 32) : "memory");
-            if (tid == 0) {                                              // ... before the neighbour can see the item counted
+            if (tid == 0) {
+                __threadfence_system();
                 if (cs.face == 1 && a.cnt_lo) atomicAdd_system(a.cnt_lo, 1ull);
                 if (cs.face == 2 && a.cnt_hi) atomicAdd_system(a.cnt_hi, 1ull);
             }
@@ -358,11 +397,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
         if (PEER && a.tickets) {   // peer mode: the last CTA of the launch publishes this rank's maximum into every rank's table
             __threadfence();
             if (atomicAdd(&a.tickets[it], 1u) == gridDim.x - 1u) {
+                // the word carries everything its readers need (value + valid bit): relaxed stores, all in flight together
                 const unsigned long long v = atomicMax(&a.maxkey[it], 0ull) | PEER_VALID;
                 for (int r = 0; r < a.peer_n; ++r)
-                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.pub[r] + (size_t)it * a.peer_n + a.my_rank), "l"(v) : "memory");
+                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a.pub[r] + (size_t)it * a.peer_n + a.my_rank), "l"(v) : "memory");
             }
         }
+        if (PEER) trace_end(a.trace);
     }
 }
 }  // namespace pb
@@ -413,6 +454,18 @@ template <bool TEX, bool PEER>
 __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
     pass_a_tma_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__ CUtensorMap m1,
                       const __grid_constant__ CUtensorMap m2, LoopArgs a, int it, Sched sc) {
+    pdl_launch_dependents();
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned smem = (smem_u32(smem_raw) + 127u) & ~127u;
+    const unsigned wbuf0 = smem + NSTAGE * STAGE_BYTES;
+    __shared__ unsigned long long bars[NSTAGE];
+    const unsigned full0 = smem_u32(&bars[0]);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(full0 + 8 * s, 1);
+        mbar_fence_init();
+    }
+    pdl_wait();        // everything below reads what the previous launches wrote
     if (a.a_uses_max ? loop_finished(a, it) : (a.check && a.state->converged)) {
         if (a.check && blockIdx.x == 0 && threadIdx.x == 0 && !a.state->converged) {
             a.state->iters = it;
@@ -420,21 +473,12 @@ __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
         }
         return;
     }
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const unsigned smem = (smem_u32(smem_raw) + 127u) & ~127u;
-    const unsigned wbuf0 = smem + NSTAGE * STAGE_BYTES;
-    __shared__ unsigned long long bars[NSTAGE];
-    const unsigned full0 = smem_u32(&bars[0]);
+    if (PEER && threadIdx.x == 0) trace_begin(a.trace);
 
     const Dims d = a.d, dg = a.dg;           // local slab extent / global volume
     const int X = d.X, XY = d.X * d.Y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < NSTAGE; ++s) mbar_init(full0 + 8 * s, 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
+    __syncthreads();   // barrier init (above) visible to the block
 
     typedef Stream<TX, TY, 1, 1> St;
     St pr;                                    // position of the feeder (thread 0) in the CTA's plane stream
@@ -446,7 +490,11 @@ __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
             // peer mode: the first item of this CTA that reads the halo planes of that face -- the neighbour's pass B of the
             // previous iteration has stored into them once the counter says so
             const unsigned long long want = pr.face == 1 ? a.expect_lo : a.expect_hi;
-            if (want) peer_wait_ge(a.my_cnt + (pr.face - 1), want, a.peer_error);
+            if (want) {
+                const unsigned long long t0 = a.trace ? global_timer_ns() : 0ull;
+                peer_wait_ge(a.my_cnt + (pr.face - 1), want, a.peer_error);
+                trace_wait(a.trace, 4, t0);
+            }
             asm volatile("fence.proxy.async;" ::: "memory");     // the planes are read by TMA (async proxy)
             halo_seen |= pr.face;
         }
@@ -637,6 +685,7 @@ __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
             if (cs.face == 2 && a.ack_hi) atomicAdd_system(a.ack_hi, 1ull);
         }
     }
+    if (PEER && tid == 0) trace_end(a.trace);
 }
 }  // namespace pa
 
@@ -929,7 +978,7 @@ int sm_count() {
 // c planes costs c + halo_planes * halo_cost plane-steps.  Ranges of fewer than 16 planes stay one chunk; for the others the
 // chunk count that minimises the busiest CTA's load -- given the items already placed before it -- is taken (chunks of >= 16
 // planes -- 8 for ranges under 64 planes or when 16-plane chunks cannot fill the CTAs -- so that the pipeline prologue stays a small share).
-Sched make_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_planes, double halo_cost, int ctas) {
+Sched make_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_planes, double halo_cost, int ctas, double *worst_load = nullptr) {
     Sched s;
     s.tiles_x = (d.X + TX - 1) / TX;
     s.tiles_y = (d.Y + TY - 1) / TY;
@@ -950,6 +999,7 @@ Sched make_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_plane
         for (int nz = 1; nz <= 64; ++nz) {
             const int chunk = (Z + nz - 1) / nz;
             if (chunk < min_chunk && nz > 1) break;
+            if (zr.face[r] != 0 && nz > 1) break;      // a face range is ONE chunk: every rank counts tiles_x * tiles_y items per face
             const int nch = (Z + chunk - 1) / chunk;
             trial = load;
             int item = s.nitems;
@@ -970,6 +1020,11 @@ Sched make_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_plane
             for (int t = 0; t < xy; ++t, ++item) load[item % ctas] += planes + halo_planes * halo_cost + 1.0;
         }
         s.nitems += xy * s.nz[r];
+    }
+    if (worst_load) {
+        double w = 0.0;
+        for (int b = 0; b < ctas; ++b) w = load[b] > w ? load[b] : w;
+        *worst_load = w;
     }
     return s;
 }
@@ -999,6 +1054,36 @@ LaunchInfo launch_info(const Sched &sc, int grid) {
 }
 
 }  // namespace
+
+// Peer mode: the local planes [lo, hi) of a launch as | lower face chunk [lo, lo+c) | upper face chunk [hi-c, hi) | middle |.
+// The face chunks are ordinary full-length work items (no extra pipeline prologue for a handful of planes), exactly one z chunk
+// each and issued FIRST: in pass B they carry the planes the neighbours need (stored into the neighbour's halo planes and counted
+// there long before the middle of the slab is done), in pass A they are the only items that read halo planes (so they can
+// acknowledge early, and the neighbour's next pass B never waits).  c is the face chunk that minimises the busiest CTA's load
+// under the static round-robin assignment (>= 4: the planes a neighbour needs / the planes that read halo planes).
+ZRanges plan_peer_ranges(const Dims d, int pass, int lo, int hi, bool has_lo, bool has_hi, int sms) {
+    if (sms <= 0) sms = sm_count();
+    const int TX = pass ? pb::TX : pa::TX, TY = pass ? pb::TY : pa::TY;
+    const int ctas = pass ? sms : PA_CTAS * sms;
+    const int halo_planes = pass ? 6 : 2;
+    const double halo_cost = pass ? 0.35 : 0.5;
+    const int nfaces = (has_lo ? 1 : 0) + (has_hi ? 1 : 0), Z = hi - lo;
+    ZRanges best{1, {lo, 0, 0}, {hi, 0, 0}, {0, 0, 0}};
+    if (nfaces == 0) return best;
+    double best_w = 1e300;
+    const int cmax = Z / nfaces < 32 ? Z / nfaces : 32;
+    for (int c = 4; c <= cmax; ++c) {
+        ZRanges zr{0, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        int mlo = lo, mhi = hi;
+        if (has_lo) { zr.lo[zr.n] = lo; zr.hi[zr.n] = lo + c; zr.face[zr.n] = 1; ++zr.n; mlo = lo + c; }
+        if (has_hi) { zr.lo[zr.n] = hi - c; zr.hi[zr.n] = hi; zr.face[zr.n] = 2; ++zr.n; mhi = hi - c; }
+        if (mhi > mlo) { zr.lo[zr.n] = mlo; zr.hi[zr.n] = mhi; zr.face[zr.n] = 0; ++zr.n; }
+        double w = 0.0;
+        make_sched(d, zr, TX, TY, halo_planes, halo_cost, ctas, &w);
+        if (w < best_w - 1e-9) { best_w = w; best = zr; }
+    }
+    return best;
+}
 
 // 16 B vector accesses and TMA row pitches need X % 4 == 0
 bool tiled_supported(const Dims d) { return d.X % 4 == 0 && d.X >= 32 && d.Y >= 8 && d.Z >= 8; }
@@ -1035,8 +1120,8 @@ LaunchInfo launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, const 
     const Sched sc = cached_sched(a.d, zr, pb::TX, pb::TY, 6, 0.35, ctas);
     if (sc.nitems == 0) return LaunchInfo{0, {0, 0, 0}};
     const int grid = sc.nitems < ctas ? sc.nitems : ctas;
-    if (a.peer_n > 0) pb::pass_b_tma_kernel<true><<<grid, (pb::NW + 1) * 32, pb::SMEM_BYTES, st>>>(m->g[0], m->g[1], m->g[2], m->pb_psi[0], m->pb_psi[1], m->pb_psi[2], a, it, sc);
-    else pb::pass_b_tma_kernel<false><<<grid, (pb::NW + 1) * 32, pb::SMEM_BYTES, st>>>(m->g[0], m->g[1], m->g[2], m->pb_psi[0], m->pb_psi[1], m->pb_psi[2], a, it, sc);
+    if (a.peer_n > 0) launch_pdl(pb::pass_b_tma_kernel<true>, grid, (pb::NW + 1) * 32, pb::SMEM_BYTES, st, m->g[0], m->g[1], m->g[2], m->pb_psi[0], m->pb_psi[1], m->pb_psi[2], a, it, sc);
+    else launch_pdl(pb::pass_b_tma_kernel<false>, grid, (pb::NW + 1) * 32, pb::SMEM_BYTES, st, m->g[0], m->g[1], m->g[2], m->pb_psi[0], m->pb_psi[1], m->pb_psi[2], a, it, sc);
     return launch_info(sc, grid);
 }
 
@@ -1071,14 +1156,24 @@ LaunchInfo launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int lo
     const Sched sc = cached_sched(a.d, zr, pa::TX, pa::TY, 2, 0.5, ctas);
     if (sc.nitems == 0) return LaunchInfo{0, {0, 0, 0}};
     const int grid = sc.nitems < ctas ? sc.nitems : ctas;
-    if (a.pn_tex && peer) pa::pass_a_tma_kernel<true, true><<<grid, pa::NTHREADS, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
-    else if (a.pn_tex) pa::pass_a_tma_kernel<true, false><<<grid, pa::NTHREADS, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
-    else if (peer) pa::pass_a_tma_kernel<false, true><<<grid, pa::NTHREADS, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
-    else pa::pass_a_tma_kernel<false, false><<<grid, pa::NTHREADS, pa::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, sc);
+    if (a.pn_tex && peer) launch_pdl(pa::pass_a_tma_kernel<true, true>, grid, pa::NTHREADS, pa::SMEM_BYTES, st, m->in[0], m->in[1], m->in[2], a, it, sc);
+    else if (a.pn_tex) launch_pdl(pa::pass_a_tma_kernel<true, false>, grid, pa::NTHREADS, pa::SMEM_BYTES, st, m->in[0], m->in[1], m->in[2], a, it, sc);
+    else if (peer) launch_pdl(pa::pass_a_tma_kernel<false, true>, grid, pa::NTHREADS, pa::SMEM_BYTES, st, m->in[0], m->in[1], m->in[2], a, it, sc);
+    else launch_pdl(pa::pass_a_tma_kernel<false, false>, grid, pa::NTHREADS, pa::SMEM_BYTES, st, m->in[0], m->in[1], m->in[2], a, it, sc);
     return launch_info(sc, grid);
 }
 
 }  // namespace sb
+
+// Host-only view of plan_peer_ranges (tests/test_schedule_cpu.py): ranges[9] = {lo, hi, face} x 3
+extern "C" int sobfu_b200_debug_peer_ranges(int pass, int X, int Y, int Zlocal, int lo, int hi, int has_lo, int has_hi, int sms, int *ranges, int *n_ranges) {
+    using namespace sb;
+    if (!ranges || !n_ranges || (pass != 0 && pass != 1) || hi - lo < 8 || sms < 1) return -1;
+    const ZRanges zr = plan_peer_ranges(Dims{X, Y, Zlocal}, pass, lo, hi, has_lo != 0, has_hi != 0, sms);
+    *n_ranges = zr.n;
+    for (int r = 0; r < MAX_ZRANGES; ++r) { ranges[3 * r] = zr.lo[r]; ranges[3 * r + 1] = zr.hi[r]; ranges[3 * r + 2] = zr.face[r]; }
+    return 0;
+}
 
 // Host-only view of the work decomposition of a launch (no GPU needed): the items in issue order with the CTA that takes them
 // under the static round-robin assignment.  pass 0 = A, 1 = B; `sms` = number of SMs to plan for (148 on B200).

@@ -46,7 +46,7 @@ def main():
     p = sf.Params(volume_dims=dims, volume_size=tuple(float(vs[i]) * dims[i] for i in range(3)), max_iter=iters, max_update_norm=1e-10, s=7,
                   lambda_=0.1, alpha=0.001, w_reg=0.6, verbosity=0, tsdf_max_weight=64.0, tsdf_trunc_dist=float(trunc), eta=float(eta))
     out = {}
-    for mode in ("peer", "nccl"):
+    for mode in os.environ.get("PEER_CHECK_MODES", "peer,nccl").split(","):
         if mode == "nccl":
             os.environ["SOBFU_B200_NO_PEER"] = "1"
         solver = sf.SlabSolver(p, dist)
@@ -73,6 +73,8 @@ def main():
                 best = min(best, float(t.item()))
         assert info.iters == iters
         out[mode] = {"peer_attached": bool(getattr(solver, "peer", False)), "loop_ms_per_iter": best / iters, "iters_per_s": iters / (best * 1e-3), "launches": info.launches}
+        if mode == "peer" and os.environ.get("SOBFU_B200_TRACE"):
+            out[mode]["trace_per_rank"] = trace_summary(solver, iters, dist, world)
         if mode == "nccl":      # where the time of an iteration goes on this rank: A_mid | wait + A_edge | wait + B_edge | B_mid | iteration
             ph = torch.tensor(solver.time_phases(50), device="cuda")
             dist.all_reduce(ph, op=dist.ReduceOp.MAX)
@@ -84,6 +86,29 @@ def main():
         print(json.dumps({"n_gpus": world, "dim": dim, "iters": iters, **out}), flush=True)
     dist.barrier()
     dist.destroy_process_group()
+
+
+def trace_summary(solver, iters, dist, world):
+    """device-side timeline of the last peer-mode solve (sobfu_b200_solver_get_trace): mean microseconds over the middle iterations"""
+    import ctypes as C
+    from sobfu_b200 import _capi
+    cap = 2 * iters
+    buf, n = (C.c_ulonglong * (8 * cap))(), C.c_int()
+    _capi.check(_capi.lib().sobfu_b200_solver_get_trace(solver._h, buf, cap, C.byref(n)))
+    t = np.array(buf[:8 * n.value], dtype=np.float64).reshape(-1, 8)
+    res = None
+    if len(t) >= 40:
+        a, b = t[0::2], t[1::2]
+        k = slice(len(a) // 4, 3 * len(a) // 4)
+        us = lambda x: round(float(np.mean(x)) * 1e-3, 2)  # noqa: E731
+        res = {"A_us": us(a[k, 1] - a[k, 0]), "B_us": us(b[k, 1] - b[k, 0]), "gap_A_to_B_us": us(b[k, 0] - a[k, 1]),
+               "gap_B_to_nextA_us": us(a[1:][k, 0] - b[:-1][k, 1]), "iter_us": us(a[1:][k, 0] - a[:-1][k, 0]),
+               "A_face_wait_max_us": us(a[k, 5]), "A_face_wait_sum_per_cta_us": us(a[k, 4] / np.maximum(a[k, 6], 1)),
+               "B_table_wait_max_us": us(b[k, 3]), "B_table_wait_mean_us": us(b[k, 2] / np.maximum(b[k, 6], 1)),
+               "B_ack_wait_max_us": us(b[k, 5]), "ctas": [int(a[k, 6].mean()), int(b[k, 6].mean())]}
+    allr = [None] * world
+    dist.all_gather_object(allr, res)
+    return allr
 
 
 if __name__ == "__main__":

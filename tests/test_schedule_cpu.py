@@ -26,6 +26,13 @@ def schedule(built, pas, dims, ranges, sms=148):
     return np.array(items[:6 * n_items.value], dtype=np.int64).reshape(-1, 6), grid.value
 
 
+def peer_ranges(built, pas, dims, lo, hi, has_lo, has_hi, sms=148):
+    from sobfu_b200 import _capi
+    out, n = (C.c_int * 9)(), C.c_int()
+    assert _capi.lib().sobfu_b200_debug_peer_ranges(pas, dims[0], dims[1], dims[2], lo, hi, int(has_lo), int(has_hi), sms, out, C.byref(n)) == 0
+    return [(out[3 * r], out[3 * r + 1], out[3 * r + 2]) for r in range(n.value)]
+
+
 def check(built, pas, dims, ranges, max_imbalance):
     X, Y, Z = dims
     TX, TY = TILE[pas]
@@ -82,13 +89,21 @@ def test_slab_schedules(built, nranks, dim):
         check(built, 0, dims, [(lo, 1, 0), (n - 1, hi, 0)], 1e9)
         check(built, 1, dims, [(0, 4, 0), (n - 4, n, 0)], 1e9)
         check(built, 1, dims, [(4, n - 4, 0)], 1.9)
-        # peer schedule: three face-tagged ranges per launch
-        a = check(built, 0, dims, [(1, n - 1, 0), (lo, 1, 1 if has_lo else 0), (n - 1, hi, 2 if has_hi else 0)], 2.2)
-        b = check(built, 1, dims, [(0, 4, 1 if has_lo else 0), (n - 4, n, 2 if has_hi else 0), (4, n - 4, 0)], 2.2)
-        if has_lo and has_hi:      # what the neighbours count: the same number of items on either face, on every rank
-            assert (a[:, 5] == 1).sum() == (a[:, 5] == 2).sum() == (dim // 32) * (dim // 16)
-            assert (b[:, 5] == 1).sum() == (b[:, 5] == 2).sum() == -(-dim // 64) * -(-dim // 24)
-            assert (b[:44, 5] != 0).all() or dim != 256      # pass B issues its face items first
+        # peer schedule: | lower face chunk | upper face chunk | middle | per launch, the face chunks first and ONE z chunk each
+        ra, rb = peer_ranges(built, 0, dims, lo, hi, has_lo, has_hi), peer_ranges(built, 1, dims, 0, n, has_lo, has_hi)
+        for r, (l, h) in ((ra, (lo, hi)), (rb, (0, n))):
+            faces = [x for x in r if x[2]]
+            assert [x[2] for x in faces] == ([1] if has_lo else []) + ([2] if has_hi else [])
+            assert r[:len(faces)] == faces                                   # issued first
+            assert all(x[1] - x[0] >= 4 for x in faces)                      # the planes a neighbour needs / that read halo planes
+            cover = sorted((x[0], x[1]) for x in r)
+            assert cover[0][0] == l and cover[-1][1] == h and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+        a = check(built, 0, dims, ra, 2.0)
+        b = check(built, 1, dims, rb, 2.0)
+        # what the neighbours count: tiles_x * tiles_y items per face, on every rank
+        for f, on in ((1, has_lo), (2, has_hi)):
+            assert (a[:, 5] == f).sum() == ((dim // 32) * (dim // 16) if on else 0)
+            assert (b[:, 5] == f).sum() == (-(-dim // 64) * -(-dim // 24) if on else 0)
 
 
 def test_bad_arguments(built):
