@@ -6,7 +6,8 @@
  * Config-file grammar as boost implements it: one `NAME=VALUE` per line, `#` starts a comment, blank lines are skipped,
  * whitespace around the name and the value is trimmed, `[section]` headers prefix the following names with `section.`;
  * an option the description does not know raises unknown_option, a value that does not parse raises invalid_option_value,
- * the first occurrence of an option wins.  Boost is not a dependency of sobfu_b200; with Boost installed, put it first on
+ * an option given twice in one file raises multiple_occurrences (options here are non-composing), and across several store()
+ * calls the value stored first wins.  Boost is not a dependency of sobfu_b200; with Boost installed, put it first on
  * the include path.
  */
 #pragma once
@@ -28,6 +29,7 @@ struct unknown_option : error { explicit unknown_option(const std::string &n) : 
 struct invalid_option_value : error {
     invalid_option_value(const std::string &n, const std::string &v) : error("the argument ('" + v + "') for option '" + n + "' is invalid") {}
 };
+struct multiple_occurrences : error { explicit multiple_occurrences(const std::string &n) : error("option '" + n + "' cannot be specified more than once") {} };
 struct invalid_config_file_syntax : error { explicit invalid_config_file_syntax(const std::string &l) : error("the options configuration file contains an invalid line '" + l + "'") {} };
 
 /* holder of one typed value (boost::any in the original) */
@@ -209,8 +211,11 @@ private:
 };
 
 inline void store(const parsed_options &parsed, variables_map &vm) {
+    std::map<std::string, int> seen;                              // occurrences inside THIS parse
+    for (const auto &o : parsed.options)
+        if (++seen[o.string_key] > 1) throw multiple_occurrences(o.string_key);
     for (const auto &o : parsed.options) {
-        if (vm.count(o.string_key)) continue;                     // the first occurrence wins
+        if (vm.count(o.string_key)) continue;                     // stored by an earlier store(): the first value wins
         const option_description *d = parsed.description->find_nothrow(o.string_key);
         if (!d || !d->semantic) continue;
         std::shared_ptr<value_holder> h;

@@ -46,7 +46,8 @@ typedef struct {
     float trunc_dist, eta, max_weight;
     int   verbosity;      /* 0 silent, 1 log at iter 1, %50, last (solver.cu:132), 2 every iteration */
     int   max_iter;
-    int   s;              /* Sobolev filter length; only 7 is valid (KERNEL_RADIUS 3, solver.cu:211) */
+    int   s;              /* Sobolev filter length: 7 is what the reference's kernels are compiled for (KERNEL_RADIUS 3, solver.cu:211);
+                             3, 9 and 11 -- tabulated by the reference too (solver.cpp:160-251) -- run here as well (single GPU) */
     float max_update_norm;
     float lambda;         /* one of .05 .1 .2 .4 (solver.cpp:160-262); anything else -> SOBFU_B200_EINVAL */
     float alpha, w_reg;
@@ -88,12 +89,12 @@ int sobfu_b200_solver_estimate_psi_host(sobfu_b200_solver *s, const void *phi_gl
                                         void *psi_host, void *psi_inv_host, sobfu_b200_solve_info *info);
 /* copies min(n, iters) records of the last solve */
 int sobfu_b200_solver_get_log(sobfu_b200_solver *s, sobfu_b200_iter_log *out, int n);
-/* the 7 normalised taps (decompose_sobolev_filter, src/sobfu/solver.cpp:160-262) */
-int sobfu_b200_solver_get_taps(sobfu_b200_solver *s, float *taps7);
+/* the s normalised taps (decompose_sobolev_filter, src/sobfu/solver.cpp:160-262); room for 11 floats */
+int sobfu_b200_solver_get_taps(sobfu_b200_solver *s, float *taps);
 /* bytes of device scratch owned by the handle */
 size_t sobfu_b200_solver_workspace_bytes(sobfu_b200_solver *s);
-/* kernel variant: 0 = auto (fastest applicable), 1 = generic per-voxel kernels, 2 = TMA pipelines for both passes
- */
+/* kernel variant: 0 = auto (fastest applicable), 1 = generic per-voxel kernels, 2 = TMA pipelines for both passes,
+ * 4 = TMA pipelines, pass A with software-pipelined gathers (fetches of a plane consumed one step later) */
 int sobfu_b200_solver_set_variant(sobfu_b200_solver *s, int variant);
 /* benchmarking aid: run `iters` gradient-descent iterations on the state left by the last estimate_psi
  * without convergence checks; returns device ms of pass A, pass B and the whole loop */
@@ -122,6 +123,8 @@ int sobfu_b200_jacobian(const void *psi, void *J_mat4f, int X, int Y, int Z, int
 int sobfu_b200_potential_gradient(const void *phi_n_psi, const void *phi_global, const void *grad4, const void *L4,
                                   void *nabla_U4, float w_reg, int X, int Y, int Z);   /* solver.cu:15-47 */
 int sobfu_b200_sobolev_filter(void *dst4, const void *src4, const float *taps7_host, int X, int Y, int Z); /* solver.cu:237-459 */
+/* the same three sweeps for an odd number s <= 11 of taps (radius (s - 1) / 2; the reference compiles radius 3 only, solver.cu:211) */
+int sobfu_b200_sobolev_filter_s(void *dst4, const void *src4, const float *taps_host, int s, int X, int Y, int Z);
 int sobfu_b200_update_psi(void *psi, const void *nabla_U_S4, void *updates4, float alpha, int X, int Y, int Z); /* solver.cu:53-79 */
 
 /* ---- Reductor (include/sobfu/reductor.hpp:24-50, src/sobfu/reductor.cpp:38-57) ---- */
@@ -180,9 +183,14 @@ int sobfu_b200_slab_range(int Z, int rank, int nranks, int *z0, int *nz);
 /* switches the solver (created for the GLOBAL dims) to slab mode: afterwards estimate_psi takes the rank's slab of
  * phi_global, phi_global_psi_inv, phi_n_psi, psi, psi_inv and the WHOLE phi_n (replicated: every rank integrates the
  * depth frame itself).  Per iteration: ONE psi halo exchange (4 planes; nabla_U on the halo planes is recomputed) with both
- * neighbours and a scalar MAX all-reduce over NCCL; per frame: one all-gather of psi and phi_global for psi^-1 /
- * phi_global o psi^-1. */
+ * neighbours and a scalar MAX all-reduce over NCCL; per frame: one neighbour exchange of a window of psi and phi_global for
+ * psi^-1 / phi_global o psi^-1 (all-gather only when a displacement leaves the window, see sobfu_b200_solver_tail_fallbacks). */
 int sobfu_b200_solver_attach_comm(sobfu_b200_solver *s, const void *id128_host, int rank, int nranks);
+/* slab mode: psi^-1 and phi_global o psi^-1 read a window of psi / phi_global (the rank's planes + up to 16 planes of either
+ * neighbour, SOBFU_B200_TAIL_HALO overrides) instead of all-gathered volumes; a gather that leaves the window is detected on the
+ * device and the step is repeated on the all-gathered volumes, so results do not depend on the bound.  Returns how many solves of
+ * this handle took that fallback. */
+int sobfu_b200_solver_tail_fallbacks(sobfu_b200_solver *s);
 
 /* Peer mode (ranks on one NVLink / NVSwitch domain, e.g. the 8 GPUs of a B200 node): the per-iteration psi halo exchange
  * and the convergence test leave NCCL.  Pass B on the slab faces stores its new psi planes straight into the neighbours'
@@ -207,6 +215,9 @@ int sobfu_b200_debug_schedule(int pass, int X, int Y, int Zlocal, int nranges, c
                               int *items6, int cap, int *n_items, int *grid);
 /* host-only: how peer mode splits the local planes [lo, hi) of a launch into | lower face chunk | upper face chunk | middle |
  * (face chunks first, one z chunk each); ranges9 = {lo, hi, face} x 3 */
+/* test aid: Reductor::max_update_norm through the running-candidate form the tiled pass B uses in the loop (ties on the NORM,
+ * first in the reference's traversal order wins; reductor.cu:357-368) */
+int sobfu_b200_debug_max_update_norm_cand(const void *updates_f4, int N, float *value, float *index_as_float, long long *index);
 int sobfu_b200_debug_peer_ranges(int pass, int X, int Y, int Zlocal, int lo, int hi, int has_lo, int has_hi, int sms, int *ranges9, int *n_ranges);
 /* measurement aid (peer mode, SOBFU_B200_TRACE=1): device-side timeline of the last estimate_psi, 8 words per launch in launch
  * order (pass A, pass B, ...): first CTA start / last CTA end [ns], sum / max ns waited for the maxima table, sum / max ns

@@ -132,7 +132,8 @@ def sobolev_filter(src, taps):
     X, Y, Z = dims_of(src)
     dst = np.empty_like(src)
     t = np.ascontiguousarray(taps, dtype=np.float32)
-    lib().orc_sobolev_filter(_p(dst), _p(src), _p(t), X, Y, Z)
+    assert t.ndim == 1 and t.size % 2 == 1
+    lib().orc_sobolev_filter_r(_p(dst), _p(src), _p(t), int(t.size // 2), X, Y, Z)
     return dst
 
 
@@ -163,8 +164,8 @@ def estimate_inverse(psi, psi_inv, iters=48):
 
 
 def estimate_psi(phi_global, phi_n, psi, max_iter, max_update_norm, s, lam, alpha, w_reg, log_energies=0, taps=None):
-    """returns dict(phi_n_psi, phi_global_psi_inv, psi (updated copy), psi_inv, result, log); taps: seven explicit filter taps
-    (then s / lam are ignored)"""
+    """returns dict(phi_n_psi, phi_global_psi_inv, psi (updated copy), psi_inv, result, log); taps: explicit filter taps, an odd
+    number of them (then s / lam are ignored)"""
     X, Y, Z = dims_of(phi_global)
     psi = psi.copy()
     phi_n_psi = np.zeros_like(phi_n)
@@ -174,10 +175,10 @@ def estimate_psi(phi_global, phi_n, psi, max_iter, max_update_norm, s, lam, alph
     log = np.zeros((max(max_iter, 1), 4), dtype=np.float32)
     if taps is not None:
         t7 = np.ascontiguousarray(taps, dtype=np.float32)
-        assert t7.shape == (7,)
-        rc = lib().orc_estimate_psi_taps(_p(phi_global), _p(pgpi), _p(phi_n), _p(phi_n_psi), _p(psi), _p(psi_inv), X, Y, Z, int(max_iter),
-                                         C.c_float(max_update_norm), _p(t7), C.c_float(alpha), C.c_float(w_reg), int(log_energies),
-                                         C.byref(res), _p(log))
+        assert t7.ndim == 1 and t7.size % 2 == 1
+        rc = lib().orc_estimate_psi_taps_r(_p(phi_global), _p(pgpi), _p(phi_n), _p(phi_n_psi), _p(psi), _p(psi_inv), X, Y, Z, int(max_iter),
+                                           C.c_float(max_update_norm), _p(t7), int(t7.size // 2), C.c_float(alpha), C.c_float(w_reg),
+                                           int(log_energies), C.byref(res), _p(log))
     else:
         rc = lib().orc_estimate_psi(_p(phi_global), _p(pgpi), _p(phi_n), _p(phi_n_psi), _p(psi), _p(psi_inv), X, Y, Z, int(max_iter),
                                     C.c_float(max_update_norm), int(s), C.c_float(lam), C.c_float(alpha), C.c_float(w_reg),

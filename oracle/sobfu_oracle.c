@@ -240,6 +240,12 @@ static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ?
 /* solver.cu:237-446.  rows: dst = sum ; columns: dst += sum ; depth: dst += sum.  Taps S[KERNEL_RADIUS - j]
  * for j = -3..3 accumulated from 0 with un-fused mul/add; borders clamp to edge (:256,:263,:270). */
 void orc_sobolev_filter(orc_f4 *dst, const orc_f4 *src, const float *S, int X, int Y, int Z) {
+    orc_sobolev_filter_r(dst, src, S, 3, X, Y, Z);
+}
+
+/* the same three sweeps for a filter of 2 * R + 1 taps (the reference compiles KERNEL_RADIUS = 3 only, solver.cu:211; its tables
+ * solver.cpp:160-251 also hold 3-, 9- and 11-tap filters): taps S[R - j], j = -R..R, same accumulation order, clamp to edge */
+void orc_sobolev_filter_r(orc_f4 *dst, const orc_f4 *src, const float *S, int R, int X, int Y, int Z) {
 #pragma omp parallel
     {
         const unsigned csr__ = orc_ftz_on();
@@ -248,8 +254,8 @@ void orc_sobolev_filter(orc_f4 *dst, const orc_f4 *src, const float *S, int X, i
             for (int y = 0; y < Y; ++y)
                 for (int x = 0; x < X; ++x) {
                     float sx[3] = {0.f, 0.f, 0.f}, sy[3] = {0.f, 0.f, 0.f}, sz[3] = {0.f, 0.f, 0.f};
-                    for (int j = -3; j <= 3; ++j) {
-                        float s = S[3 - j];
+                    for (int j = -R; j <= R; ++j) {
+                        float s = S[R - j];
                         const orc_f4 a = src[IDX(clampi(x + j, 0, X - 1), y, z)];
                         const orc_f4 b = src[IDX(x, clampi(y + j, 0, Y - 1), z)];
                         const orc_f4 c = src[IDX(x, y, clampi(z + j, 0, Z - 1))];
@@ -485,12 +491,17 @@ void orc_estimate_inverse(const orc_f4 *psi, orc_f4 *psi_inv, int X, int Y, int 
 void orc_solver_iteration(const orc_f2 *phi_global, const orc_f2 *phi_n, orc_f2 *phi_n_psi, orc_f4 *psi,
                           orc_f4 *scratch, const float *taps7, float alpha, float w_reg, int X, int Y, int Z,
                           float *max_norm, float *max_idx) {
+    orc_solver_iteration_r(phi_global, phi_n, phi_n_psi, psi, scratch, taps7, 3, alpha, w_reg, X, Y, Z, max_norm, max_idx);
+}
+void orc_solver_iteration_r(const orc_f2 *phi_global, const orc_f2 *phi_n, orc_f2 *phi_n_psi, orc_f4 *psi,
+                            orc_f4 *scratch, const float *taps, int R, float alpha, float w_reg, int X, int Y, int Z,
+                            float *max_norm, float *max_idx) {
     size_t N = (size_t)X * Y * Z;
     orc_f4 *grad = scratch, *L = scratch + N, *nU = scratch + 2 * N, *nUS = scratch + 3 * N, *upd = scratch + 4 * N;
     orc_tsdf_gradient(phi_n_psi, grad, X, Y, Z);                                   /* solver.cu:120 */
     orc_laplacian(psi, L, X, Y, Z);                                                /* solver.cu:127 */
     orc_potential_gradient(phi_n_psi, phi_global, grad, L, nU, w_reg, (int)N);     /* solver.cu:149 */
-    orc_sobolev_filter(nUS, nU, taps7, X, Y, Z);                                   /* solver.cu:155-160 */
+    orc_sobolev_filter_r(nUS, nU, taps, R, X, Y, Z);                               /* solver.cu:155-160 */
     orc_update_psi(psi, nUS, upd, alpha, (int)N);                                  /* solver.cu:163 */
     orc_apply(phi_n, phi_n_psi, psi, X, Y, Z);                                     /* solver.cu:168 */
     orc_max_update_norm(upd, (int)N, max_norm, max_idx);                           /* solver.cu:172 */
@@ -512,6 +523,14 @@ int orc_estimate_psi_taps(const orc_f2 *phi_global, orc_f2 *phi_global_psi_inv, 
                           orc_f2 *phi_n_psi, orc_f4 *psi, orc_f4 *psi_inv, int X, int Y, int Z, int max_iter,
                           float max_update_norm, const float *taps, float alpha, float w_reg, int log_energies,
                           orc_solve_result *res, orc_iter_log *log) {
+    return orc_estimate_psi_taps_r(phi_global, phi_global_psi_inv, phi_n, phi_n_psi, psi, psi_inv, X, Y, Z, max_iter, max_update_norm,
+                                   taps, 3, alpha, w_reg, log_energies, res, log);
+}
+/* ... and with a filter of 2 * R + 1 explicit taps */
+int orc_estimate_psi_taps_r(const orc_f2 *phi_global, orc_f2 *phi_global_psi_inv, const orc_f2 *phi_n,
+                            orc_f2 *phi_n_psi, orc_f4 *psi, orc_f4 *psi_inv, int X, int Y, int Z, int max_iter,
+                            float max_update_norm, const float *taps, int R, float alpha, float w_reg, int log_energies,
+                            orc_solve_result *res, orc_iter_log *log) {
     size_t N = (size_t)X * Y * Z;
     orc_f4 *scratch = (orc_f4 *)malloc(sizeof(orc_f4) * 5 * N);
     float *J = log_energies ? (float *)malloc(sizeof(float) * 16 * N) : NULL;
@@ -528,7 +547,7 @@ int orc_estimate_psi_taps(const orc_f2 *phi_global, orc_f2 *phi_global_psi_inv, 
             e_data = orc_data_energy(phi_global, phi_n_psi, (int)N);
             e_reg = orc_reg_energy(J, (int)N);
         }
-        orc_solver_iteration(phi_global, phi_n, phi_n_psi, psi, scratch, taps, alpha, w_reg, X, Y, Z, &mv, &mi);
+        orc_solver_iteration_r(phi_global, phi_n, phi_n_psi, psi, scratch, taps, R, alpha, w_reg, X, Y, Z, &mv, &mi);
         if (log) { log[iter - 1].max_norm = mv; log[iter - 1].max_idx = mi; log[iter - 1].e_data = e_data; log[iter - 1].e_reg = e_reg; }
         if (mv <= max_update_norm) { converged = 1; break; } /* solver.cu:183 */
         iter++;

@@ -64,6 +64,8 @@ void  orc_potential_gradient(const orc_f2 *phi_n_psi, const orc_f2 *phi_global, 
                              const orc_f4 *L, orc_f4 *nabla_U, float w_reg, int N);
 /* solver.cu:237-446 : dst = S*x src ; dst += S*y src ; dst += S*z src (clamp to edge) */
 void  orc_sobolev_filter(orc_f4 *dst, const orc_f4 *src, const float *taps7, int X, int Y, int Z);
+/* 2 * R + 1 taps (generalisation of the reference's compile-time KERNEL_RADIUS 3, solver.cu:211) */
+void  orc_sobolev_filter_r(orc_f4 *dst, const orc_f4 *src, const float *taps, int R, int X, int Y, int Z);
 /* solver.cu:53-69 */
 void  orc_update_psi(orc_f4 *psi, const orc_f4 *nabla_U_S, orc_f4 *updates, float alpha, int N);
 /* reductor.cu:342-456 + reductor.cpp:81-94 : value (sqrt_rd) and index-as-float of the arg max */
@@ -88,6 +90,13 @@ int   orc_estimate_psi(const orc_f2 *phi_global, orc_f2 *phi_global_psi_inv, con
 
 /* one solver iteration on caller-provided state (used by the cpu_baseline timing leg);
  * scratch = 4*N float4 (grad, L, nabla_U, nabla_U_S) + N float4 updates */
+void  orc_solver_iteration_r(const orc_f2 *phi_global, const orc_f2 *phi_n, orc_f2 *phi_n_psi, orc_f4 *psi,
+                             orc_f4 *scratch, const float *taps, int R, float alpha, float w_reg, int X, int Y, int Z,
+                             float *max_norm, float *max_idx);
+int   orc_estimate_psi_taps_r(const orc_f2 *phi_global, orc_f2 *phi_global_psi_inv, const orc_f2 *phi_n,
+                              orc_f2 *phi_n_psi, orc_f4 *psi, orc_f4 *psi_inv, int X, int Y, int Z, int max_iter,
+                              float max_update_norm, const float *taps, int R, float alpha, float w_reg, int log_energies,
+                              orc_solve_result *res, orc_iter_log *log);
 void  orc_solver_iteration(const orc_f2 *phi_global, const orc_f2 *phi_n, orc_f2 *phi_n_psi, orc_f4 *psi,
                            orc_f4 *scratch, const float *taps7, float alpha, float w_reg, int X, int Y, int Z,
                            float *max_norm, float *max_idx);

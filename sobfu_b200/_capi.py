@@ -60,10 +60,12 @@ SIGNATURES = {
     "sobfu_b200_jacobian": [_P, _P, _I, _I, _I, _I],
     "sobfu_b200_potential_gradient": [_P, _P, _P, _P, _P, _F, _I, _I, _I],
     "sobfu_b200_sobolev_filter": [_P, _P, _FP, _I, _I, _I],
+    "sobfu_b200_sobolev_filter_s": [_P, _P, _FP, _I, _I, _I, _I],
     "sobfu_b200_update_psi": [_P, _P, _P, _F, _I, _I, _I],
     "sobfu_b200_data_energy": [_P, _P, _I, _FP],
     "sobfu_b200_reg_energy": [_P, _I, _FP],
     "sobfu_b200_max_update_norm": [_P, _I, _FP, _FP, C.POINTER(C.c_longlong)],
+    "sobfu_b200_debug_max_update_norm_cand": [_P, _I, _FP, _FP, C.POINTER(C.c_longlong)],
     "sobfu_b200_tsdf_clear": [_P, _I, _I, _I],
     "sobfu_b200_tsdf_init_sphere": [_P, _I, _I, _I, _FP, _F, _F, _FP, _F],
     "sobfu_b200_tsdf_init_box": [_P, _I, _I, _I, _FP, _F, _FP],
@@ -83,7 +85,8 @@ SIGNATURES = {
     "sobfu_b200_solver_peer_attach": [_P, _P],
     "sobfu_b200_slab_range": [_I, _I, _I, _IP, _IP],
 }
-OTHER_SYMBOLS = ["sobfu_b200_last_error", "sobfu_b200_version", "sobfu_b200_solver_workspace_bytes", "sobfu_b200_io_last_error"]
+OTHER_SYMBOLS = ["sobfu_b200_last_error", "sobfu_b200_version", "sobfu_b200_solver_workspace_bytes", "sobfu_b200_io_last_error",
+                 "sobfu_b200_solver_tail_fallbacks"]
 
 _lib = None
 
@@ -107,6 +110,8 @@ def lib():
     L.sobfu_b200_io_last_error.restype = C.c_char_p
     L.sobfu_b200_solver_workspace_bytes.restype = C.c_size_t
     L.sobfu_b200_solver_workspace_bytes.argtypes = [_P]
+    L.sobfu_b200_solver_tail_fallbacks.restype = C.c_int
+    L.sobfu_b200_solver_tail_fallbacks.argtypes = [_P]
     _lib = L
     return L
 

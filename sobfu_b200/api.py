@@ -21,9 +21,28 @@ import numpy as np
 import torch
 
 from . import _capi
-from ._capi import check, fvec, lib
+from ._capi import check, fvec
 
 f32 = np.float32
+
+
+class _StreamBoundLib:
+    """The library issues the free functions on -- and orders solver calls against -- the stream set with
+    sobfu_b200_set_stream (include/sobfu_b200.h).  Every function fetched through this proxy first binds the caller's CURRENT
+    torch stream, so work queued under `with torch.cuda.stream(s):` is ordered with the library's kernels."""
+
+    def __getattr__(self, name):
+        L = _capi.lib()
+        if torch.cuda.is_available() and torch.cuda.is_initialized():
+            L.sobfu_b200_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        return getattr(L, name)
+
+
+_BOUND = _StreamBoundLib()
+
+
+def lib():
+    return _BOUND
 
 
 @dataclass
@@ -249,9 +268,9 @@ class Solver:
         return [(buf[i].max_norm, buf[i].max_idx_f, buf[i].e_data, buf[i].e_reg) for i in range(n)]
 
     def get_taps(self):
-        t = (C.c_float * 7)()
+        t = (C.c_float * 11)()
         check(lib().sobfu_b200_solver_get_taps(self._h, t))
-        return np.array(list(t), dtype=f32)
+        return np.array(list(t)[:int(self.params.s)], dtype=f32)
 
     def set_variant(self, v):
         check(lib().sobfu_b200_solver_set_variant(self._h, int(v)))
@@ -266,6 +285,10 @@ class Solver:
         out = (C.c_float * 5)()
         check(lib().sobfu_b200_solver_time_phases(self._h, int(iters), out))
         return tuple(out)
+
+    def tail_fallbacks(self):
+        """slab mode: solves whose psi^-1 / final warp left the neighbour window and were repeated on all-gathered volumes"""
+        return int(lib().sobfu_b200_solver_tail_fallbacks(self._h))
 
     def workspace_bytes(self):
         return int(lib().sobfu_b200_solver_workspace_bytes(self._h))

@@ -29,11 +29,12 @@ void launch_laplacian(const float4 *psi, float4 *L, Dims d, cudaStream_t st);
 void launch_jacobian(const float4 *psi, float4 *J, Dims d, int mode, cudaStream_t st);
 void launch_potential_gradient(const float2 *pnp, const float2 *pg, const float4 *grad, const float4 *L, float4 *out,
                                float w_reg, size_t n, cudaStream_t st);
-void launch_sobolev_filter(float4 *dst, const float4 *src, const float *taps7, Dims d, cudaStream_t st);
+void launch_sobolev_filter(float4 *dst, const float4 *src, const float *taps, int ntaps, Dims d, cudaStream_t st);
 void launch_update_psi(float4 *psi, const float4 *g, float4 *upd, float alpha, size_t n, cudaStream_t st);
-void launch_data_energy(const float2 *a, const float2 *b, size_t n, double *out, cudaStream_t st);
-void launch_reg_energy(const float4 *J, size_t n, double *out, cudaStream_t st);
+void launch_data_energy(const float2 *a, const float2 *b, size_t n, double *out, float *partial, cudaStream_t st);
+void launch_reg_energy(const float4 *J, size_t n, double *out, float *partial, cudaStream_t st);
 void launch_max_norm(const float4 *u, size_t n, RankMap rm, unsigned long long *out, cudaStream_t st);
+void launch_max_norm_cand(const float4 *u, size_t n, RankMap rm, unsigned long long *out, cudaStream_t st);
 // tsdf_ops.cu
 void launch_tsdf_clear(float2 *vol, size_t n, cudaStream_t st);
 void launch_tsdf_init_sphere(float2 *vol, Dims d, float3 vs, float trunc, float eta, float3 c, float r, cudaStream_t st);
@@ -175,14 +176,6 @@ extern "C" int sobfu_b200_sobolev_taps_computed(int s, float lambda, float *h) {
     return 0;
 }
 
-// __fsqrt_rd on the host: largest float r with r*r <= x (the product of two floats is exact in double)
-static float host_sqrt_rd(float x) {
-    if (!(x > 0.f)) return 0.f;
-    float r = sqrtf(x);
-    if ((double)r * (double)r > (double)x) r = nextafterf(r, 0.f);
-    return r;
-}
-
 // reference reduction sizing, src/sobfu/precomp.cpp:20-43 with (65536, 512) (reductor.cpp:17)
 static RankMap rank_map_for(size_t n) {
     unsigned threads;
@@ -226,13 +219,22 @@ struct sobfu_b200_solver {
     Dims d;                        // local slab (== dg on a single GPU)
     int z0 = 0;                    // global z of local plane 0
     size_t Ng = 0, Nl = 0, XY = 0; // voxels: global, local, per plane
-    float taps[7];
+    float taps[MAX_TAPS];          // 2 * radius + 1 of them, radius = (p.s - 1) / 2
     GLayout gl;
     // z-slab decomposition over ranks (one process per GPU)
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
     ncclComm_t comm_max = nullptr;   // second communicator: the scalar MAX all-reduce runs concurrently with the halo exchange
-    float4 *psi_full = nullptr;    // all-gathered psi / phi_global for the once-per-frame tail (slab mode only)
+    // once-per-frame tail in slab mode: psi^-1 and phi_global o psi^-1 gather psi / phi_global at data-dependent positions.  They
+    // read a WINDOW -- the rank's planes + tail_halo planes of either neighbour, one neighbour exchange -- and raise a flag when
+    // a gather leaves it; only then the whole volumes are all-gathered (allocated on first use) and the two kernels repeated.
+    float4 *psi_win = nullptr;
+    float2 *phig_win = nullptr;
+    int tail_halo = 0, win_z0 = 0, win_nz = 0;
+    int *overflow = nullptr;       // device flag (all-reduced over the ranks)
+    int *h_overflow = nullptr;     // pinned copy
+    int tail_fallbacks = 0;        // how many solves needed the all-gather
+    float4 *psi_full = nullptr;    // all-gathered psi / phi_global (fallback only)
     float2 *phig_full = nullptr;
     // device scratch
     float *psi_alloc = nullptr;    // 3 x (nzl + 2) planes: psi x/y/z with one halo plane on either side
@@ -243,6 +245,7 @@ struct sobfu_b200_solver {
     LoopState *state = nullptr;
     unsigned long long *maxkey = nullptr;
     double *energies = nullptr;    // e_data[max_iter], e_reg[max_iter]
+    float *energy_partial = nullptr;   // block results of the reference-order energy reduction (2 x 65536 floats)
     // host side
     LoopState *h_state = nullptr;  // pinned
     std::vector<unsigned long long> h_maxkey;
@@ -289,7 +292,7 @@ struct sobfu_b200_solver {
 };
 
 static bool use_tiled(const sobfu_b200_solver *s) {
-    if (s->variant == 1) return false;
+    if (s->variant == 1 || s->p.s != 7) return false;      // the tiled pass B is a 7-tap kernel
     return tiled_supported(s->d) && s->tma != nullptr;
 }
 
@@ -302,7 +305,8 @@ static void fill_args(sobfu_b200_solver *s) {
     a.pg = s->pg + (size_t)PG_HALO * s->XY; a.pn = s->pn;
     a.gx = s->g; a.gy = s->g + s->gl.total; a.gz = s->g + 2 * s->gl.total;
     a.d = s->d; a.dg = s->dg; a.z0 = s->z0; a.gl = s->gl;
-    for (int i = 0; i < 7; ++i) a.S[i] = s->taps[i];
+    for (int i = 0; i < MAX_TAPS; ++i) a.S[i] = i < s->p.s ? s->taps[i] : 0.f;
+    a.radius = (s->p.s - 1) / 2;
     a.alpha = s->p.alpha; a.w_reg = s->p.w_reg; a.thr = s->p.max_update_norm;
     a.state = s->state; a.maxkey = s->maxkey; a.e_data = s->energies; a.e_reg = s->energies + (s->p.max_iter > 0 ? s->p.max_iter : 1);
     a.rm = rank_map_for(s->Ng);
@@ -348,9 +352,9 @@ static void create_atlas(sobfu_b200_solver *s) {
 static void free_workspace(sobfu_b200_solver *s) {
     if (s->tma) { tma_maps_destroy(s->tma); s->tma = nullptr; }
     cudaFree(s->psi_alloc); cudaFree(s->w_alloc); cudaFree(s->pg); cudaFree(s->pn); cudaFree(s->g);
-    cudaFree(s->psi_full); cudaFree(s->phig_full);
+    cudaFree(s->psi_full); cudaFree(s->phig_full); cudaFree(s->psi_win); cudaFree(s->phig_win);
     s->psi_alloc = s->w_alloc = s->pg = s->pn = s->g = nullptr;
-    s->psi_full = nullptr; s->phig_full = nullptr;
+    s->psi_full = nullptr; s->phig_full = nullptr; s->psi_win = nullptr; s->phig_win = nullptr;
     for (int i = 0; i < 6; ++i) {
         if (s->stage_dev[i]) { cudaFree(s->stage_dev[i]); s->stage_dev[i] = nullptr; }
         if (s->stage_pinned[i]) { cudaFreeHost(s->stage_pinned[i]); s->stage_pinned[i] = nullptr; }
@@ -386,9 +390,21 @@ static int alloc_workspace(sobfu_b200_solver *s, int z0, int nzl) {
     CKA(cudaMemset(s->g, 0, 3 * s->gl.total * sizeof(float)));
     s->ws_bytes = (4 * pl + pgl + s->Ng + 3 * s->gl.total) * sizeof(float);
     if (s->nranks > 1) {
-        CKA(cudaMalloc(&s->psi_full, s->Ng * sizeof(float4)));
-        CKA(cudaMalloc(&s->phig_full, s->Ng * sizeof(float2)));
-        s->ws_bytes += s->Ng * 24;
+        // window of the tail: up to 16 planes of either neighbour (SOBFU_B200_TAIL_HALO overrides; 0 = always all-gather), never
+        // more than a neighbour owns
+        int H = 16;
+        if (const char *e = getenv("SOBFU_B200_TAIL_HALO")) H = atoi(e);
+        if (H > nzl) H = nzl;
+        if (H < 0) H = 0;
+        s->tail_halo = H;
+        s->win_z0 = z0 - H > 0 ? z0 - H : 0;
+        const int zend = z0 + nzl + H < s->dg.Z ? z0 + nzl + H : s->dg.Z;
+        s->win_nz = zend - s->win_z0;
+        if (H > 0) {
+            CKA(cudaMalloc(&s->psi_win, (size_t)s->win_nz * s->XY * sizeof(float4)));
+            CKA(cudaMalloc(&s->phig_win, (size_t)s->win_nz * s->XY * sizeof(float2)));
+            s->ws_bytes += (size_t)s->win_nz * s->XY * 24;
+        }
     }
     fill_args(s);
     s->peer_plan = false;
@@ -435,8 +451,10 @@ extern "C" int sobfu_b200_solver_destroy(sobfu_b200_solver *s) {
     if (s->pn_tex) cudaDestroyTextureObject(s->pn_tex);
     if (s->pn_surf) cudaDestroySurfaceObject(s->pn_surf);
     if (s->pn_array) cudaFreeArray(s->pn_array);
-    cudaFree(s->state); cudaFree(s->maxkey); cudaFree(s->tickets); cudaFree(s->energies); cudaFree(s->trace);
+    cudaFree(s->state); cudaFree(s->maxkey); cudaFree(s->tickets); cudaFree(s->energies); cudaFree(s->energy_partial); cudaFree(s->trace);
     if (s->h_state) cudaFreeHost(s->h_state);
+    cudaFree(s->overflow);
+    if (s->h_overflow) cudaFreeHost(s->h_overflow);
     for (auto &e : s->ev) if (e) cudaEventDestroy(e);
     if (s->ev_user) cudaEventDestroy(s->ev_user);
     for (cudaEvent_t e : {s->ev_b, s->ev_bm, s->ev_p, s->ev_m}) if (e) cudaEventDestroy(e);
@@ -451,14 +469,17 @@ extern "C" int sobfu_b200_solver_create(sobfu_b200_solver **out, const sobfu_b20
     if (!out || !p) return fail(SOBFU_B200_EINVAL, "null argument");
     *out = nullptr;
     if (!dims_ok(p->dims[0], p->dims[1], p->dims[2])) return fail(SOBFU_B200_EINVAL, "volume dims must be >= 2 per axis and < 2^31 voxels");
-    if (p->s != 7) return fail(SOBFU_B200_EINVAL, "s=%d: the reference's convolution kernels are compiled for 7 taps only (solver.cu:211)", p->s);
+    // the reference's convolution kernels are compiled for 7 taps (solver.cu:211) although its tables also hold 3-, 9- and 11-tap
+    // filters (solver.cpp:160-251); here those run too (generic kernels, single GPU)
+    if (p->s != 3 && p->s != 7 && p->s != 9 && p->s != 11)
+        return fail(SOBFU_B200_EINVAL, "s=%d: the Sobolev filter has 3, 7, 9 or 11 taps (solver.cpp:160-251)", p->s);
     if (p->max_iter < 0) return fail(SOBFU_B200_EINVAL, "max_iter < 0");
     sobfu_b200_solver *s = new sobfu_b200_solver();
     s->p = *p;
     int rc = sobfu_b200_sobolev_taps(p->s, p->lambda, s->taps);
     // opt-in (SOBFU_B200_COMPUTE_FILTER=1 or sobfu_b200_solver_create_ex): a lambda the reference does not tabulate gets the
     // filter its tables were derived by, instead of being refused
-    if (rc && p->s == 7 && (g_compute_filter || getenv("SOBFU_B200_COMPUTE_FILTER"))) rc = sobfu_b200_sobolev_taps_computed(p->s, p->lambda, s->taps);
+    if (rc && (g_compute_filter || getenv("SOBFU_B200_COMPUTE_FILTER"))) rc = sobfu_b200_sobolev_taps_computed(p->s, p->lambda, s->taps);
     if (rc) { delete s; return rc; }
     s->dg = Dims{p->dims[0], p->dims[1], p->dims[2]};
     s->Ng = (size_t)s->dg.X * s->dg.Y * s->dg.Z;
@@ -476,7 +497,10 @@ extern "C" int sobfu_b200_solver_create(sobfu_b200_solver **out, const sobfu_b20
     CKD(cudaMalloc(&s->maxkey, mi * sizeof(unsigned long long)));
     CKD(cudaMalloc(&s->tickets, mi * sizeof(unsigned int)));
     CKD(cudaMalloc(&s->energies, 2 * mi * sizeof(double)));
+    CKD(cudaMalloc(&s->energy_partial, 2 * 65536 * sizeof(float)));
     CKD(cudaMallocHost(&s->h_state, sizeof(LoopState)));
+    CKD(cudaMalloc(&s->overflow, sizeof(int)));
+    CKD(cudaMallocHost(&s->h_overflow, sizeof(int)));
     CKD(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (auto &e : s->ev) CKD(cudaEventCreate(&e));
     CKD(cudaEventCreateWithFlags(&s->ev_user, cudaEventDisableTiming));
@@ -497,13 +521,14 @@ extern "C" int sobfu_b200_solver_create_ex(sobfu_b200_solver **out, const sobfu_
 }
 
 extern "C" size_t sobfu_b200_solver_workspace_bytes(sobfu_b200_solver *s) { return s ? s->ws_bytes : 0; }
+extern "C" int sobfu_b200_solver_tail_fallbacks(sobfu_b200_solver *s) { return s ? s->tail_fallbacks : -1; }
 extern "C" int sobfu_b200_solver_get_taps(sobfu_b200_solver *s, float *t) {
     if (!s || !t) return fail(SOBFU_B200_EINVAL, "null argument");
-    memcpy(t, s->taps, sizeof s->taps);
+    memcpy(t, s->taps, sizeof(float) * (size_t)s->p.s);
     return 0;
 }
 extern "C" int sobfu_b200_solver_set_variant(sobfu_b200_solver *s, int v) {
-    if (!s || v < 0 || v > 3) return fail(SOBFU_B200_EINVAL, "variant must be 0 (default), 1 (generic), 2 (tiled) or 3 (tiled, warp-specialised pass A: experimental)");
+    if (!s || v < 0 || v > 4 || v == 3) return fail(SOBFU_B200_EINVAL, "variant must be 0 (default), 1 (generic), 2 (tiled) or 4 (tiled, pass A with software-pipelined gathers)");
     if (v >= 2 && !(tiled_supported(s->d) && s->tma)) return fail(SOBFU_B200_EINVAL, "tiled/TMA kernels do not support dims %dx%dx%d", s->d.X, s->d.Y, s->d.Z);
     s->variant = v;
     return 0;
@@ -531,6 +556,7 @@ extern "C" int sobfu_b200_slab_range(int Z, int rank, int nranks, int *z0, int *
 extern "C" int sobfu_b200_solver_attach_comm(sobfu_b200_solver *s, const void *id128, int rank, int nranks) {
     if (!s || !id128) return fail(SOBFU_B200_EINVAL, "null argument");
     if (s->comm) return fail(SOBFU_B200_EINVAL, "a communicator is already attached");
+    if (s->p.s != 7 && nranks > 1) return fail(SOBFU_B200_EINVAL, "slab mode carries 3 halo planes of nabla_U: filters of s=%d taps run on a single GPU only", s->p.s);
     int z0 = 0, nz = 0;
     int rc = sobfu_b200_slab_range(s->dg.Z, rank, nranks, &z0, &nz);
     if (rc) return rc;
@@ -543,10 +569,26 @@ extern "C" int sobfu_b200_solver_attach_comm(sobfu_b200_solver *s, const void *i
     if (r != ncclSuccess) { s->comm = nullptr; return fail(SOBFU_B200_ECOMM, "ncclCommInitRank: %s", n.GetErrorString(r)); }
     s->rank = rank; s->nranks = nranks;
     if (n.CommSplit && n.CommSplit(s->comm, 0, rank, &s->comm_max, nullptr) != ncclSuccess) s->comm_max = nullptr;
-    CK(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&s->max_stream, cudaStreamNonBlocking));
-    for (cudaEvent_t *e : {&s->ev_b, &s->ev_bm, &s->ev_p, &s->ev_m}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-    return alloc_workspace(s, z0, nz);
+    // any failure from here on leaves the handle as it was before the call: a single-GPU solver of the whole volume
+    auto attach = [&]() -> int {
+        CK(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&s->max_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t *e : {&s->ev_b, &s->ev_bm, &s->ev_p, &s->ev_m}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        return alloc_workspace(s, z0, nz);
+    };
+    rc = attach();
+    if (rc) {
+        const std::string why = g_err;
+        if (s->comm_max) { n.CommDestroy(s->comm_max); s->comm_max = nullptr; }
+        n.CommDestroy(s->comm); s->comm = nullptr;
+        s->rank = 0; s->nranks = 1;
+        for (cudaEvent_t *e : {&s->ev_b, &s->ev_bm, &s->ev_p, &s->ev_m}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
+        if (s->comm_stream) { cudaStreamDestroy(s->comm_stream); s->comm_stream = nullptr; }
+        if (s->max_stream) { cudaStreamDestroy(s->max_stream); s->max_stream = nullptr; }
+        if (alloc_workspace(s, 0, s->dg.Z)) return fail(rc, "attach_comm failed (%s) and the single-GPU workspace could not be restored: the solver is unusable", why.c_str());
+        g_err = why;
+    }
+    return rc;
 }
 
 // ---- peer mode: halo exchange and convergence test over NVLink peer memory instead of NCCL (same node, CUDA IPC) ----
@@ -662,10 +704,15 @@ static inline bool log_iter(const sobfu_b200_params &p, int iter1) {   // iter1 
 }
 
 static ZRanges whole_slab(const sobfu_b200_solver *s) { return ZRanges{1, {0, 0, 0}, {s->d.Z, 0, 0}, {0, 0, 0}}; }
+// logging iterations: on a single GPU (and >= 1024 voxels) the two energies are summed in the reference's fp32 order
+// (launch_energy_trees) and match its console output digit for digit; slabs accumulate in double and all-reduce
+static int log_mode(const sobfu_b200_solver *s, int log) { return !log ? 0 : ((s->nranks == 1 && s->Nl >= 1024) ? 2 : 1); }
 static void run_pass_a(sobfu_b200_solver *s, int it, int log) {
-    set_pass_a_variant(s->variant == 3 ? 3 : 0);
-    if (!use_tiled(s)) launch_pass_a_generic(s->args, it, log, s->stream);
-    else launch_pass_a_tma(s->args, s->tma, it, log, whole_slab(s), s->stream);
+    set_pass_a_variant(s->variant == 4 ? 4 : 0);
+    const int lm = log_mode(s, log);
+    if (!use_tiled(s)) launch_pass_a_generic(s->args, it, lm, s->stream);
+    else launch_pass_a_tma(s->args, s->tma, it, lm, whole_slab(s), s->stream);
+    if (lm == 2) launch_energy_trees(s->args, it, s->energy_partial, s->stream);   // w is current: generic kernels keep it, the tiled path just materialised it
 }
 static void run_pass_b(sobfu_b200_solver *s, int it) {
     if (!use_tiled(s)) launch_pass_b_generic(s->args, it, s->stream);
@@ -718,7 +765,7 @@ static int peer_check_error(sobfu_b200_solver *s) {   // stream already synchron
 // one gradient-descent iteration
 static int launch_iteration(sobfu_b200_solver *s, int it, int log, int *launches) {
     int rc = 0;
-    set_pass_a_variant(s->variant == 3 ? 3 : 0);
+    set_pass_a_variant(s->variant == 4 ? 4 : 0);
     const int n = s->d.Z;
     static const bool no_overlap = getenv("SOBFU_B200_NO_OVERLAP") != nullptr;
     if (peer_mode(s)) {
@@ -847,6 +894,52 @@ static int launch_iteration(sobfu_b200_solver *s, int it, int log, int *launches
     return 0;
 }
 
+// tail of a slab solve, all-gather form: psi^-1 (48 fixed-point steps from the identity) and phi_global o psi^-1 on the whole
+// psi / phi_global (vector_fields.cu:111-138, solver.cu:199)
+static int tail_gathered(sobfu_b200_solver *s, const float2 *phi_global, float2 *phi_global_psi_inv, const float4 *psi, float4 *psi_inv,
+                         cudaStream_t st) {
+    NcclApi &n = nccl_api();
+    if (!s->psi_full) {
+        CK(cudaMalloc(&s->psi_full, s->Ng * sizeof(float4)));
+        CK(cudaMalloc(&s->phig_full, s->Ng * sizeof(float2)));
+        s->ws_bytes += s->Ng * 24;
+    }
+    CKN(n.AllGather(psi, s->psi_full, s->Nl * 4, ncclFloat, s->comm, st));
+    CKN(n.AllGather(phi_global, s->phig_full, s->Nl * 2, ncclFloat, s->comm, st));
+    launch_estimate_inverse_slab(s->psi_full, psi_inv, s->dg, s->z0, s->d.Z, 48, ZWindow{0, s->dg.Z, s->overflow}, st);
+    launch_apply_slab(s->phig_full, phi_global_psi_inv, psi_inv, s->dg, s->d.Z, ZWindow{0, s->dg.Z, s->overflow}, st);
+    return 0;
+}
+// window form: the rank's planes + tail_halo planes of either neighbour (one grouped send/recv), overflow flag all-reduced
+static int tail_windowed(sobfu_b200_solver *s, const float2 *phi_global, float2 *phi_global_psi_inv, const float4 *psi, float4 *psi_inv,
+                         cudaStream_t st) {
+    NcclApi &n = nccl_api();
+    const size_t XY = s->XY, nzl = s->d.Z, H = s->tail_halo;
+    const size_t own = (size_t)(s->z0 - s->win_z0) * XY;          // first own voxel inside the window
+    CK(cudaMemsetAsync(s->overflow, 0, sizeof(int), st));
+    CK(cudaMemcpyAsync(s->psi_win + own, psi, s->Nl * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(s->phig_win + own, phi_global, s->Nl * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    CKN(n.GroupStart());
+    if (s->rank > 0) {                    // lower neighbour: my first H planes go down, its last H planes come up
+        CKN(n.Send(psi, H * XY * 4, ncclFloat, s->rank - 1, s->comm, st));
+        CKN(n.Send(phi_global, H * XY * 2, ncclFloat, s->rank - 1, s->comm, st));
+        CKN(n.Recv(s->psi_win, H * XY * 4, ncclFloat, s->rank - 1, s->comm, st));
+        CKN(n.Recv(s->phig_win, H * XY * 2, ncclFloat, s->rank - 1, s->comm, st));
+    }
+    if (s->rank < s->nranks - 1) {
+        CKN(n.Send(psi + (nzl - H) * XY, H * XY * 4, ncclFloat, s->rank + 1, s->comm, st));
+        CKN(n.Send(phi_global + (nzl - H) * XY, H * XY * 2, ncclFloat, s->rank + 1, s->comm, st));
+        CKN(n.Recv(s->psi_win + own + nzl * XY, H * XY * 4, ncclFloat, s->rank + 1, s->comm, st));
+        CKN(n.Recv(s->phig_win + own + nzl * XY, H * XY * 2, ncclFloat, s->rank + 1, s->comm, st));
+    }
+    CKN(n.GroupEnd());
+    const ZWindow w{s->win_z0, s->win_nz, s->overflow};
+    launch_estimate_inverse_slab(s->psi_win, psi_inv, s->dg, s->z0, s->d.Z, 48, w, st);
+    launch_apply_slab(s->phig_win, phi_global_psi_inv, psi_inv, s->dg, s->d.Z, w, st);
+    CKN(n.AllReduce(s->overflow, s->overflow, 1, ncclInt32, ncclMax, s->comm, st));
+    return 0;
+}
+
 static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *phi_global_psi_inv, const float2 *phi_n,
                         float2 *phi_n_psi, float4 *psi, float4 *psi_inv, sobfu_b200_solve_info *info, bool order_with_user) {
     const sobfu_b200_params &p = s->p;
@@ -903,12 +996,12 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
         launch_estimate_inverse(psi, psi_inv, s->dg, 48, true, st);
         launch_apply(phi_global, phi_global_psi_inv, psi_inv, s->dg, st);
     } else {
-        // psi^-1 and phi_global o psi^-1 gather anywhere in the volume: all-gather psi and phi_global once per frame
         NcclApi &n = nccl_api();
-        CKN(n.AllGather(psi, s->psi_full, s->Nl * 4, ncclFloat, s->comm, st));
-        CKN(n.AllGather(phi_global, s->phig_full, s->Nl * 2, ncclFloat, s->comm, st));
-        launch_estimate_inverse_slab(s->psi_full, psi_inv, s->dg, s->z0, s->d.Z, 48, st);
-        launch_apply_slab(s->phig_full, phi_global_psi_inv, psi_inv, s->dg, s->z0, s->d.Z, st);
+        if (s->tail_halo > 0) {
+            if ((rc = tail_windowed(s, phi_global, phi_global_psi_inv, psi, psi_inv, st))) return rc;
+        } else {
+            if ((rc = tail_gathered(s, phi_global, phi_global_psi_inv, psi, psi_inv, st))) return rc;
+        }
         if (mi > 0) CKN(n.AllReduce(s->energies, s->energies, 2 * mi, ncclDouble, ncclSum, s->comm, st));
         // peer mode keeps the per-rank maxima in maxkey[] (the global ones live in the allmax tables): reduce them for the log
         if (mi > 0 && peer_mode(s)) CKN(n.AllReduce(s->maxkey, s->maxkey, mi, ncclUint64, ncclMax, s->comm, st));
@@ -921,12 +1014,21 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
         CK(cudaMemcpyAsync(s->h_maxkey.data(), s->maxkey, mi * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(s->h_energies.data(), s->energies, 2 * mi * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
+    if (s->nranks > 1 && s->tail_halo > 0) CK(cudaMemcpyAsync(s->h_overflow, s->overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if ((rc = peer_check_error(s))) return rc;
+    if (s->nranks > 1 && s->tail_halo > 0 && *s->h_overflow) {
+        // some rank's gather left its window (displacements beyond tail_halo planes): every rank saw the same all-reduced flag
+        // and repeats the two kernels on the all-gathered volumes
+        ++s->tail_fallbacks;
+        if ((rc = tail_gathered(s, phi_global, phi_global_psi_inv, psi, psi_inv, st))) return rc;
+        CK(cudaStreamSynchronize(st));
+        launches += 2;
+    }
     s->have_state = true;
 
     if (s->h_state->converged) { converged = 1; iters = s->h_state->iters; }
-    auto norm_of = [&](int it) { return host_sqrt_rd(__builtin_bit_cast(float, (unsigned)(s->h_maxkey[it] >> 32))); };
+    auto norm_of = [&](int it) { return __builtin_bit_cast(float, (unsigned)(s->h_maxkey[it] >> 32)); };   // the key carries the norm
     // the last enqueued iteration has no successor to evaluate its convergence test: do it here (solver.cu:183)
     if (!converged && mi > 0 && norm_of(mi - 1) <= p.max_update_norm) { converged = 1; iters = mi; }
     s->last_iters = iters;
@@ -1172,7 +1274,12 @@ extern "C" int sobfu_b200_potential_gradient(const void *pnp, const void *pg, co
 }
 extern "C" int sobfu_b200_sobolev_filter(void *dst, const void *src, const float *taps7, int X, int Y, int Z) {
     NEED(dst && src && taps7 && dst != src && dims_ok(X, Y, Z), "sobolev_filter: bad argument");
-    launch_sobolev_filter((float4 *)dst, (const float4 *)src, taps7, Dims{X, Y, Z}, g_stream);
+    launch_sobolev_filter((float4 *)dst, (const float4 *)src, taps7, 7, Dims{X, Y, Z}, g_stream);
+    SYNC_RET();
+}
+extern "C" int sobfu_b200_sobolev_filter_s(void *dst, const void *src, const float *taps, int s, int X, int Y, int Z) {
+    NEED(dst && src && taps && dst != src && dims_ok(X, Y, Z) && s >= 1 && s <= MAX_TAPS && (s & 1), "sobolev_filter_s: bad argument (odd s <= 11)");
+    launch_sobolev_filter((float4 *)dst, (const float4 *)src, taps, s, Dims{X, Y, Z}, g_stream);
     SYNC_RET();
 }
 extern "C" int sobfu_b200_update_psi(void *psi, const void *g, void *upd, float alpha, int X, int Y, int Z) {
@@ -1181,17 +1288,32 @@ extern "C" int sobfu_b200_update_psi(void *psi, const void *g, void *upd, float 
     SYNC_RET();
 }
 
+// 16 bytes of device scratch for the scalar reductions, one per (host thread, device): the buffer handed out always lives on
+// the device that is current at the call
+static int reduce_partials(float **pbuf) {      // 65536 floats: block results of the reference-order energy reductions
+    static thread_local float *buf[64] = {};
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(SOBFU_B200_EINVAL, "device ordinal %d out of range", dev);
+    if (!buf[dev]) { cudaError_t e = cudaMalloc(&buf[dev], 65536 * sizeof(float)); if (e != cudaSuccess) { buf[dev] = nullptr; return fail(SOBFU_B200_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); } }
+    *pbuf = buf[dev];
+    return 0;
+}
 static int reduce_scalar(double **dbuf) {
-    static thread_local double *buf = nullptr;
-    if (!buf) { cudaError_t e = cudaMalloc(&buf, 16); if (e != cudaSuccess) return fail(SOBFU_B200_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); }
-    *dbuf = buf;
+    static thread_local double *buf[64] = {};
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(SOBFU_B200_EINVAL, "device ordinal %d out of range", dev);
+    if (!buf[dev]) { cudaError_t e = cudaMalloc(&buf[dev], 16); if (e != cudaSuccess) { buf[dev] = nullptr; return fail(SOBFU_B200_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); } }
+    *dbuf = buf[dev];
     return 0;
 }
 extern "C" int sobfu_b200_data_energy(const void *a, const void *b, int N, float *out) {
     NEED(a && b && out && N > 0, "data_energy: bad argument");
     double *d; int rc = reduce_scalar(&d); if (rc) return rc;
+    float *pt; if ((rc = reduce_partials(&pt))) return rc;
     CK(cudaMemsetAsync(d, 0, 8, g_stream));
-    launch_data_energy((const float2 *)a, (const float2 *)b, (size_t)N, d, g_stream);
+    launch_data_energy((const float2 *)a, (const float2 *)b, (size_t)N, d, pt, g_stream);
     double h; CK_LAST(); CK(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, g_stream)); CK(cudaStreamSynchronize(g_stream));
     *out = 0.5f * (float)h;   // reductor.cpp:42
     return 0;
@@ -1199,18 +1321,20 @@ extern "C" int sobfu_b200_data_energy(const void *a, const void *b, int N, float
 extern "C" int sobfu_b200_reg_energy(const void *J, int N, float *out) {
     NEED(J && out && N > 0, "reg_energy: bad argument");
     double *d; int rc = reduce_scalar(&d); if (rc) return rc;
+    float *pt; if ((rc = reduce_partials(&pt))) return rc;
     CK(cudaMemsetAsync(d, 0, 8, g_stream));
-    launch_reg_energy((const float4 *)J, (size_t)N, d, g_stream);
+    launch_reg_energy((const float4 *)J, (size_t)N, d, pt, g_stream);
     double h; CK_LAST(); CK(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, g_stream)); CK(cudaStreamSynchronize(g_stream));
     *out = 0.5f * (float)h;   // reductor.cpp:49
     return 0;
 }
-extern "C" int sobfu_b200_max_update_norm(const void *u, int N, float *value, float *index_f, long long *index) {
+static int max_update_norm_impl(const void *u, int N, float *value, float *index_f, long long *index, bool cand) {
     NEED(u && N > 0, "max_update_norm: bad argument");
     double *d; int rc = reduce_scalar(&d); if (rc) return rc;
     const RankMap rm = rank_map_for((size_t)N);
     CK(cudaMemsetAsync(d, 0, 8, g_stream));
-    launch_max_norm((const float4 *)u, (size_t)N, rm, (unsigned long long *)d, g_stream);
+    if (cand) launch_max_norm_cand((const float4 *)u, (size_t)N, rm, (unsigned long long *)d, g_stream);
+    else launch_max_norm((const float4 *)u, (size_t)N, rm, (unsigned long long *)d, g_stream);
     unsigned long long h; CK_LAST(); CK(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, g_stream)); CK(cudaStreamSynchronize(g_stream));
     const float v = __builtin_bit_cast(float, (unsigned)(h >> 32));
     const long long idx = v > 0.f ? unrank(0xffffffffu - (unsigned)(h & 0xffffffffull), rm) : 0;
@@ -1218,6 +1342,13 @@ extern "C" int sobfu_b200_max_update_norm(const void *u, int N, float *value, fl
     if (index) *index = idx;
     if (index_f) *index_f = v > 0.f ? idx_as_ref_float(idx, rm) : 0.f;
     return 0;
+}
+extern "C" int sobfu_b200_max_update_norm(const void *u, int N, float *value, float *index_f, long long *index) {
+    return max_update_norm_impl(u, N, value, index_f, index, false);
+}
+// test aid: the same reduction through the running-candidate form of the tiled pass B (few threads, many elements each)
+extern "C" int sobfu_b200_debug_max_update_norm_cand(const void *u, int N, float *value, float *index_f, long long *index) {
+    return max_update_norm_impl(u, N, value, index_f, index, true);
 }
 
 // ---- TSDF / depth / marching cubes --------------------------------------------------------------------------

@@ -101,4 +101,26 @@ SB_DEV unsigned rank_of(unsigned idx, const RankMap m) {
     return ((b * m.bs + tr) * m.npass + pass) * 2u + half;
 }
 
+// Running arg-max candidate of a thread under the reference's rule (reductor.cu:357-368): NORMS are compared, i.e.
+// __fsqrt_rd(sum of squares), and among equal norms the first element in traversal order (rank_of) wins -- two different sums
+// of squares that round down to the same square root ARE a tie.  The square root is only taken for the few candidates that
+// can matter: lo_bits is the smallest sum of squares whose norm equals the current best (r * r rounded up), so one integer
+// compare rejects everything below it exactly.
+struct MaxCand {
+    unsigned norm_bits, lo_bits, idx;
+};
+SB_DEV void max_cand_update(MaxCand &m, float nsq, unsigned idx, const RankMap rm) {
+    const unsigned b = __float_as_uint(nsq);
+    if (b >= m.lo_bits && b != 0u) {
+        const float r = __fsqrt_rd(nsq);
+        const unsigned rb = __float_as_uint(r);
+        if (rb > m.norm_bits) { m.norm_bits = rb; m.lo_bits = __float_as_uint(__fmul_ru(r, r)); m.idx = idx; }
+        else if (rb == m.norm_bits && rank_of(idx, rm) < rank_of(m.idx, rm)) m.idx = idx;
+    }
+}
+// 64-bit key of a candidate: norm in the high word, inverted traversal rank in the low word (max of keys = the reference's winner)
+SB_DEV unsigned long long max_cand_key(const MaxCand &m, const RankMap rm) {
+    return m.norm_bits ? (((unsigned long long)m.norm_bits << 32) | (unsigned long long)(0xffffffffu - rank_of(m.idx, rm))) : 0ull;
+}
+
 }  // namespace sb

@@ -23,32 +23,46 @@ __global__ void init_identity_kernel(float4 *__restrict__ psi, Dims d) {
     psi[x + (size_t)d.X * (y + (size_t)d.Y * z)] = make_float4((float)x, (float)y, (float)z, 0.f);
 }
 
-// apply_kernel, vector_fields.cu:81-100 + interpolate_tsdf, utils.hpp:50-86.  phi covers the whole volume `dg`;
-// psi and out cover the z-slab [z0, z0 + nzl) (the whole volume on a single GPU).
+// The array a gather reads covers the planes [z0, z0 + nz) of the volume: the whole volume, or -- z-slab mode -- the rank's own
+// planes plus a halo of the neighbours' (a bounded-displacement window).  A gather that leaves the window raises *overflow
+// and reads a clamped plane instead; the host then repeats the step on the all-gathered volume (capi.cu), so the result never
+// depends on the bound.
+SB_DEV int win_plane(int z, const ZWindow w, bool &bad) {
+    int k = z - w.z0;
+    if (k < 0 || k >= w.nz) { bad = true; k = k < 0 ? 0 : w.nz - 1; }
+    return k;
+}
+
+// apply_kernel, vector_fields.cu:81-100 + interpolate_tsdf, utils.hpp:50-86.  phi covers the window `w` of the volume `dg`;
+// psi and out cover the z-slab of nzl planes the launch writes (the whole volume on a single GPU).
 __global__ void apply_kernel(const float2 *__restrict__ phi, float2 *__restrict__ out, const float4 *__restrict__ psi,
-                             Dims dg, int nzl) {
+                             Dims dg, int nzl, ZWindow w) {
     int x, y, z;
     if (!voxel_of_thread(Dims{dg.X, dg.Y, nzl}, x, y, z)) return;
     const size_t i = x + (size_t)dg.X * (y + (size_t)dg.Y * z);
     const float4 p = psi[i];
-    const TriCoord t = tri_coord(p.x, p.y, p.z, dg);
+    TriCoord t = tri_coord(p.x, p.y, p.z, dg);
+    bool bad = false;
+    t.gz = win_plane(t.gz, w, bad);
+    t.z1 = win_plane(t.z1, w, bad);
     const float v = sample_scalar<2>(reinterpret_cast<const float *>(phi), t, dg);
     const float wgt = phi[(size_t)t.gx + (size_t)dg.X * ((size_t)t.gy + (size_t)dg.Y * t.gz)].y;
     out[i] = make_float2(v, wgt);
+    if (bad) *w.overflow = 1;
 }
 
 // estimate_inverse_kernel x iters, vector_fields.cu:111-138 with interpolate_field_inv, utils.hpp:124-164.
 // Every launch of the reference reads only psi and the voxel's own psi_inv value, so the launches collapse into a
 // per-voxel loop in registers: psi_inv <- (x,y,z) - 1.f * trilerp(psi - id)(psi_inv).
-SB_DEV float3 disp(const float4 *__restrict__ psi, int x, int y, int z, const Dims d) {
-    const float4 p = __ldg(psi + (size_t)x + (size_t)d.X * ((size_t)y + (size_t)d.Y * z));
+SB_DEV float3 disp(const float4 *__restrict__ psi, int x, int y, int z, int zk, const Dims d) {
+    const float4 p = __ldg(psi + (size_t)x + (size_t)d.X * ((size_t)y + (size_t)d.Y * zk));
     return make_float3(sub(p.x, (float)x), sub(p.y, (float)y), sub(p.z, (float)z));   // get_displacement
 }
-// psi covers the whole volume `d`; psi_inv covers the z-slab [z0, z0 + nzl).  The fixed-point loop stops as soon as a
-// step reproduces its input bit for bit: every later step of the reference would return the same value.
+// psi covers the window `w` of the volume `d`; psi_inv covers the z-slab [z0, z0 + nzl).  The fixed-point loop stops as soon as
+// a step reproduces its input bit for bit: every later step of the reference would return the same value.
 __global__ void __launch_bounds__(BX *BY *BZ) estimate_inverse_kernel(const float4 *__restrict__ psi,
                                                                     float4 *__restrict__ psi_inv, Dims d, int z0, int nzl,
-                                                                    int iters, int from_identity) {
+                                                                    int iters, int from_identity, ZWindow w) {
     int x, y, zl;
     if (!voxel_of_thread(Dims{d.X, d.Y, nzl}, x, y, zl)) return;
     const int z = z0 + zl;
@@ -56,12 +70,14 @@ __global__ void __launch_bounds__(BX *BY *BZ) estimate_inverse_kernel(const floa
     float vx, vy, vz, vw;
     if (from_identity) { vx = (float)x; vy = (float)y; vz = (float)z; vw = 0.f; }
     else { const float4 v = psi_inv[i]; vx = v.x; vy = v.y; vz = v.z; vw = v.w; }
+    bool bad = false;
     for (int it = 0; it < iters; ++it) {
         const TriCoord t = tri_coord(vx, vy, vz, d);
-        const float3 d111 = disp(psi, t.x1, t.y1, t.z1, d), d110 = disp(psi, t.x1, t.y1, t.gz, d);
-        const float3 d101 = disp(psi, t.x1, t.gy, t.z1, d), d100 = disp(psi, t.x1, t.gy, t.gz, d);
-        const float3 d011 = disp(psi, t.gx, t.y1, t.z1, d), d010 = disp(psi, t.gx, t.y1, t.gz, d);
-        const float3 d001 = disp(psi, t.gx, t.gy, t.z1, d), d000 = disp(psi, t.gx, t.gy, t.gz, d);
+        const int kg = win_plane(t.gz, w, bad), k1 = win_plane(t.z1, w, bad);
+        const float3 d111 = disp(psi, t.x1, t.y1, t.z1, k1, d), d110 = disp(psi, t.x1, t.y1, t.gz, kg, d);
+        const float3 d101 = disp(psi, t.x1, t.gy, t.z1, k1, d), d100 = disp(psi, t.x1, t.gy, t.gz, kg, d);
+        const float3 d011 = disp(psi, t.gx, t.y1, t.z1, k1, d), d010 = disp(psi, t.gx, t.y1, t.gz, kg, d);
+        const float3 d001 = disp(psi, t.gx, t.gy, t.z1, k1, d), d000 = disp(psi, t.gx, t.gy, t.gz, kg, d);
         const float ix = tri_lerp(d111.x, d110.x, d101.x, d100.x, d011.x, d010.x, d001.x, d000.x, t);
         const float iy = tri_lerp(d111.y, d110.y, d101.y, d100.y, d011.y, d010.y, d001.y, d000.y, t);
         const float iz = tri_lerp(d111.z, d110.z, d101.z, d100.z, d011.z, d010.z, d001.z, d000.z, t);
@@ -74,6 +90,7 @@ __global__ void __launch_bounds__(BX *BY *BZ) estimate_inverse_kernel(const floa
         if (same) break;
     }
     psi_inv[i] = make_float4(vx, vy, vz, vw);
+    if (bad) *w.overflow = 1;
 }
 
 // TsdfDifferentiator::operator(), vector_fields.cu:157-208
@@ -143,15 +160,15 @@ __global__ void potential_gradient_kernel(const float2 *__restrict__ pnp, const 
 }
 
 // convolution_{rows,columns,depth}_kernel, solver.cu:237-446 (AoS, clamp-to-edge) -- test API
-struct Taps { float S[7]; };
+struct Taps { float S[MAX_TAPS]; int R; };     // 2 * R + 1 taps
 __global__ void sobolev_filter_kernel(float4 *__restrict__ dst, const float4 *__restrict__ src, Taps tp, Dims d) {
     int x, y, z;
     if (!voxel_of_thread(d, x, y, z)) return;
     const size_t sy = d.X, sz = (size_t)d.X * d.Y;
     float ax[3] = {0.f, 0.f, 0.f}, ay[3] = {0.f, 0.f, 0.f}, az[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int j = -3; j <= 3; ++j) {
-        const float s = tp.S[3 - j];
+    const int R = tp.R;
+    for (int j = -R; j <= R; ++j) {
+        const float s = tp.S[R - j];
         const int xx = min(max(x + j, 0), d.X - 1), yy = min(max(y + j, 0), d.Y - 1), zz = min(max(z + j, 0), d.Z - 1);
         const float4 a = src[xx + sy * y + sz * z], b = src[x + sy * yy + sz * z], c = src[x + sy * y + sz * zz];
         ax[0] = add(ax[0], mul(s, a.x)); ax[1] = add(ax[1], mul(s, a.y)); ax[2] = add(ax[2], mul(s, a.z));
@@ -223,23 +240,83 @@ __global__ void max_norm_kernel(const float4 *__restrict__ u, size_t n, RankMap 
     __syncthreads();
     if (threadIdx.x == 0) { unsigned long long m = 0; for (int k = 0; k < (int)(blockDim.x >> 5); ++k) m = sm[k] > m ? sm[k] : m; atomicMax(out, m); }
 }
+// Reductor::data_energy / reg_energy_sobolev in the reference's fp32 summation order (reductor.cu:11-112, 114-214; see
+// energy_tree_kernel in solver_generic.cu for the order): WHICH = 0 data term (contracted to an fma by nvcc, as in the
+// reference build), 1 regulariser term (rows of the Jacobian)
+template <int WHICH>
+__global__ void __launch_bounds__(512) reductor_tree_kernel(const void *__restrict__ pa, const void *__restrict__ pb, unsigned n, unsigned grid_size,
+                                                            float *__restrict__ partial) {
+    __shared__ float sm[512];
+    const unsigned bs = blockDim.x, tid = threadIdx.x;
+    float acc = 0.f;
+    for (unsigned i = blockIdx.x * bs * 2u + tid; i < n; i += grid_size) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const unsigned e = i + (h ? bs : 0u);
+            if (e >= n) continue;
+            if (WHICH == 0) {
+                const float df = sub(reinterpret_cast<const float2 *>(pa)[e].x, reinterpret_cast<const float2 *>(pb)[e].x);
+                acc = __fmaf_rn(df, df, acc);
+            } else {
+                const float4 *J = reinterpret_cast<const float4 *>(pa) + 4 * (size_t)e;
+                float rows = 0.f;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float4 v = J[r];
+                    const float nsq = add(add(mul(v.x, v.x), mul(v.y, v.y)), mul(v.z, v.z));
+                    rows = (r == 0) ? nsq : add(rows, nsq);
+                }
+                acc = add(acc, rows);
+            }
+        }
+    }
+    sm[tid] = acc;
+    __syncthreads();
+    for (unsigned s = bs / 2; s >= 64; s >>= 1) {
+        if (tid < s) sm[tid] = acc = add(acc, sm[tid + s]);
+        __syncthreads();
+    }
+    if (tid < 32) {
+        acc = add(acc, sm[tid + 32]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc = add(acc, __shfl_down_sync(0xffffffffu, acc, off));
+        if (tid == 0) partial[blockIdx.x] = acc;
+    }
+}
+__global__ void reductor_final_kernel(const float *__restrict__ partial, unsigned blocks, double *out) {   // final_reduce, reductor.cpp:68-79
+    float r = 0.f;
+    for (unsigned b = 0; b < blocks; ++b) r = add(r, partial[b]);
+    *out = (double)r;
+}
+
+// the same reduction through the running-candidate form the tiled pass B uses (common.cuh MaxCand): a few threads, many
+// elements per thread, so that the candidate logic -- not the final key maximum -- decides
+__global__ void max_norm_cand_kernel(const float4 *__restrict__ u, size_t n, RankMap rm, unsigned long long *out) {
+    MaxCand best{0u, 0u, 0u};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = u[i];
+        max_cand_update(best, add(add(mul(v.x, v.x), mul(v.y, v.y)), mul(v.z, v.z)), (unsigned)i, rm);
+    }
+    const unsigned long long key = warp_max_u64(max_cand_key(best, rm));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, key);
+}
 }  // namespace
 
 static int sgrid(size_t n) { size_t b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b ? b : 1)); }
 
 void launch_init_identity(float4 *psi, Dims d, cudaStream_t st) { init_identity_kernel<<<grid3(d), block3(), 0, st>>>(psi, d); }
 void launch_apply(const float2 *phi, float2 *out, const float4 *psi, Dims d, cudaStream_t st) {
-    apply_kernel<<<grid3(d), block3(), 0, st>>>(phi, out, psi, d, d.Z);
+    apply_kernel<<<grid3(d), block3(), 0, st>>>(phi, out, psi, d, d.Z, ZWindow{0, d.Z, nullptr});
 }
-void launch_apply_slab(const float2 *phi_full, float2 *out_local, const float4 *psi_local, Dims dg, int z0, int nzl, cudaStream_t st) {
-    (void)z0;   // psi holds absolute coordinates: the slab offset only selects which voxels are written
-    apply_kernel<<<grid3(Dims{dg.X, dg.Y, nzl}), block3(), 0, st>>>(phi_full, out_local, psi_local, dg, nzl);
+// psi_local holds absolute coordinates: the slab offset only selects which voxels are written; phi_win covers the window `w`
+void launch_apply_slab(const float2 *phi_win, float2 *out_local, const float4 *psi_local, Dims dg, int nzl, ZWindow w, cudaStream_t st) {
+    apply_kernel<<<grid3(Dims{dg.X, dg.Y, nzl}), block3(), 0, st>>>(phi_win, out_local, psi_local, dg, nzl, w);
 }
 void launch_estimate_inverse(const float4 *psi, float4 *psi_inv, Dims d, int iters, bool from_identity, cudaStream_t st) {
-    estimate_inverse_kernel<<<grid3(d), block3(), 0, st>>>(psi, psi_inv, d, 0, d.Z, iters, from_identity ? 1 : 0);
+    estimate_inverse_kernel<<<grid3(d), block3(), 0, st>>>(psi, psi_inv, d, 0, d.Z, iters, from_identity ? 1 : 0, ZWindow{0, d.Z, nullptr});
 }
-void launch_estimate_inverse_slab(const float4 *psi_full, float4 *psi_inv_local, Dims dg, int z0, int nzl, int iters, cudaStream_t st) {
-    estimate_inverse_kernel<<<grid3(Dims{dg.X, dg.Y, nzl}), block3(), 0, st>>>(psi_full, psi_inv_local, dg, z0, nzl, iters, 1);
+void launch_estimate_inverse_slab(const float4 *psi_win, float4 *psi_inv_local, Dims dg, int z0, int nzl, int iters, ZWindow w, cudaStream_t st) {
+    estimate_inverse_kernel<<<grid3(Dims{dg.X, dg.Y, nzl}), block3(), 0, st>>>(psi_win, psi_inv_local, dg, z0, nzl, iters, 1, w);
 }
 void launch_tsdf_gradient(const float2 *phi, float4 *grad, Dims d, cudaStream_t st) { tsdf_gradient_kernel<<<grid3(d), block3(), 0, st>>>(phi, grad, d); }
 void launch_laplacian(const float4 *psi, float4 *L, Dims d, cudaStream_t st) { laplacian_kernel<<<grid3(d), block3(), 0, st>>>(psi, L, d); }
@@ -248,16 +325,29 @@ void launch_potential_gradient(const float2 *pnp, const float2 *pg, const float4
                                float w_reg, size_t n, cudaStream_t st) {
     potential_gradient_kernel<<<sgrid(n), 256, 0, st>>>(pnp, pg, grad, L, out, w_reg, n);
 }
-void launch_sobolev_filter(float4 *dst, const float4 *src, const float *taps7, Dims d, cudaStream_t st) {
+void launch_sobolev_filter(float4 *dst, const float4 *src, const float *taps, int ntaps, Dims d, cudaStream_t st) {
     Taps t;
-    for (int i = 0; i < 7; ++i) t.S[i] = taps7[i];
+    t.R = ntaps / 2;
+    for (int i = 0; i < MAX_TAPS; ++i) t.S[i] = i < ntaps ? taps[i] : 0.f;
     sobolev_filter_kernel<<<grid3(d), block3(), 0, st>>>(dst, src, t, d);
 }
 void launch_update_psi(float4 *psi, const float4 *g, float4 *upd, float alpha, size_t n, cudaStream_t st) {
     update_psi_kernel<<<sgrid(n), 256, 0, st>>>(psi, g, upd, alpha, n);
 }
-void launch_data_energy(const float2 *a, const float2 *b, size_t n, double *out, cudaStream_t st) { data_energy_kernel<<<sgrid(n), 256, 0, st>>>(a, b, n, out); }
-void launch_reg_energy(const float4 *J, size_t n, double *out, cudaStream_t st) { reg_energy_kernel<<<sgrid(n), 256, 0, st>>>(J, n, out); }
+// n >= 1024 and a scratch of 65536 floats: the reference's summation order, digit for digit; otherwise double accumulation
+void launch_data_energy(const float2 *a, const float2 *b, size_t n, double *out, float *partial, cudaStream_t st) {
+    if (n < 1024 || !partial) { data_energy_kernel<<<sgrid(n), 256, 0, st>>>(a, b, n, out); return; }
+    const unsigned blocks = energy_tree_blocks(n);
+    reductor_tree_kernel<0><<<blocks, 512, 0, st>>>(a, b, (unsigned)n, 1024u * blocks, partial);
+    reductor_final_kernel<<<1, 1, 0, st>>>(partial, blocks, out);
+}
+void launch_reg_energy(const float4 *J, size_t n, double *out, float *partial, cudaStream_t st) {
+    if (n < 1024 || !partial) { reg_energy_kernel<<<sgrid(n), 256, 0, st>>>(J, n, out); return; }
+    const unsigned blocks = energy_tree_blocks(n);
+    reductor_tree_kernel<1><<<blocks, 512, 0, st>>>(J, nullptr, (unsigned)n, 1024u * blocks, partial);
+    reductor_final_kernel<<<1, 1, 0, st>>>(partial, blocks, out);
+}
 void launch_max_norm(const float4 *u, size_t n, RankMap rm, unsigned long long *out, cudaStream_t st) { max_norm_kernel<<<sgrid(n), 256, 0, st>>>(u, n, rm, out); }
+void launch_max_norm_cand(const float4 *u, size_t n, RankMap rm, unsigned long long *out, cudaStream_t st) { max_norm_cand_kernel<<<2, 64, 0, st>>>(u, n, rm, out); }
 
 }  // namespace sb

@@ -148,16 +148,15 @@ bool upload_tables(std::string &err) {
 }  // namespace
 
 // scratch (counts + scan + cub temp), kept between calls and grown on demand: a cudaMalloc/cudaFree pair per frame would
-// serialise the device twice per extraction
+// serialise the device twice per extraction.  One set per (host thread, device): no lock is held across the extraction, and a
+// thread that moves between devices keeps (and re-uses) the scratch of each of them.
 struct McScratch {
-    std::mutex mu;
-    int device = -1;
     unsigned long long *buf = nullptr;
     size_t buf_elems = 0;
     void *tmp = nullptr;
     size_t tmp_bytes = 0;
 };
-static McScratch g_mc;
+static thread_local McScratch g_mc_dev[64];
 
 int marching_cubes_run(const float2 *vol, Dims dg, int z0, int nz, int nz_avail, float3 size, const float *R, const float *t,
                        float4 *verts, float4 *normals, int vertex_cap, int *n_vertices, int *occ_voxel, int *occ_cube,
@@ -166,14 +165,15 @@ int marching_cubes_run(const float2 *vol, Dims dg, int z0, int nz, int nz_avail,
     const Dims d{dg.X, dg.Y, nz_avail};               // what is addressable at `vol`
     const size_t n = (size_t)d.X * d.Y * nz;
     if (n > 0x7fffffffull) { err = "marching cubes: more than 2^31 voxels in one call"; return -1; }
-    std::lock_guard<std::mutex> lock(g_mc.mu);
     int dev = 0;
     cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) { err = "marching cubes: device ordinal out of range"; return -1; }
+    McScratch &g_mc = g_mc_dev[dev];
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int)n, st);
-    if (g_mc.device != dev || g_mc.buf_elems < 2 * n || g_mc.tmp_bytes < tmp_bytes) {
-        if (g_mc.device == dev) { cudaFree(g_mc.buf); cudaFree(g_mc.tmp); }      // another device's scratch is left to that device
-        g_mc.buf = nullptr; g_mc.tmp = nullptr; g_mc.buf_elems = 0; g_mc.tmp_bytes = 0; g_mc.device = dev;
+    if (g_mc.buf_elems < 2 * n || g_mc.tmp_bytes < tmp_bytes) {
+        cudaFree(g_mc.buf); cudaFree(g_mc.tmp);
+        g_mc.buf = nullptr; g_mc.tmp = nullptr; g_mc.buf_elems = 0; g_mc.tmp_bytes = 0;
         if (cudaMalloc(&g_mc.buf, 2 * n * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&g_mc.tmp, tmp_bytes) != cudaSuccess) {
             err = std::string("marching cubes scratch: ") + cudaGetErrorString(cudaGetLastError());
             cudaFree(g_mc.buf);

@@ -65,6 +65,87 @@ SB_DEV float lap_comp(const float *__restrict__ p, size_t i, size_t ixa, size_t 
     return mul(v, -1.f);
 }
 
+// sum over the three rows of the displacement Jacobian (Differentiator mode 1, vector_fields.cu:415-472) of their squared norms
+// at local voxel (x, y, z): get_displacement subtracts the neighbour's own coordinates (vector_fields.cu:24-26); the term of
+// Reductor::reg_energy_sobolev (reductor.cu:114-214), in its association (row0 + row1) + row2
+SB_DEV float jacobian_rows_nsq(const LoopArgs &a, int x, int y, int z) {
+    const Dims d = a.d;
+    const size_t sy = (size_t)d.X, sz = (size_t)d.X * d.Y;
+    const size_t i = x + sy * y + sz * z;
+    const int zg = a.z0 + z;
+    const bool z_lo = (zg == 0), z_hi = (zg == a.dg.Z - 1);
+    const size_t gxa = (x == d.X - 1) ? i - 1 : i + 1, gxb = (x == 0) ? i + 1 : i - 1;
+    const size_t gya = (y == d.Y - 1) ? i - sy : i + sy, gyb = (y == 0) ? i + sy : i - sy;
+    const size_t gza = z_hi ? i - sz : i + sz, gzb = z_lo ? i + sz : i - sz;
+    const float *P[3] = {a.px, a.py, a.pz};
+    const int cxa = (x == d.X - 1) ? x - 1 : x + 1, cxb = (x == 0) ? x + 1 : x - 1;
+    const int cya = (y == d.Y - 1) ? y - 1 : y + 1, cyb = (y == 0) ? y + 1 : y - 1;
+    const int cza = z_hi ? zg - 1 : zg + 1, czb = z_lo ? zg + 1 : zg - 1;
+    float rows = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float ox_a = (c == 0) ? (float)cxa : (c == 1 ? (float)y : (float)zg);
+        const float ox_b = (c == 0) ? (float)cxb : (c == 1 ? (float)y : (float)zg);
+        const float oy_a = (c == 0) ? (float)x : (c == 1 ? (float)cya : (float)zg);
+        const float oy_b = (c == 0) ? (float)x : (c == 1 ? (float)cyb : (float)zg);
+        const float oz_a = (c == 0) ? (float)x : (c == 1 ? (float)y : (float)cza);
+        const float oz_b = (c == 0) ? (float)x : (c == 1 ? (float)y : (float)czb);
+        const float jx = mul(sub(sub(P[c][gxa], ox_a), sub(P[c][gxb], ox_b)), 0.5f);
+        const float jy = mul(sub(sub(P[c][gya], oy_a), sub(P[c][gyb], oy_b)), 0.5f);
+        const float jz = mul(sub(sub(P[c][gza], oz_a), sub(P[c][gzb], oz_b)), 0.5f);
+        const float nsq = add(add(mul(jx, jx), mul(jy, jy)), mul(jz, jz));   // norm_sq, utils.hpp:283-285
+        rows = (c == 0) ? nsq : add(rows, nsq);
+    }
+    return rows;
+}
+
+// ---- the two logged energies with the reference's fp32 summation (single GPU, N >= 1024) ---------------------------------
+// Reductor::data_energy / reg_energy_sobolev (reductor.cpp:38-50): reduce6-style kernels (reductor.cu:11-112, 114-214) of
+// `blocks` x `bs` threads -- thread t of block b sums elements b*2*bs + t (+ bs), stride 2*bs*blocks, the data term contracted
+// to an fma by nvcc -- a shared-memory tree down to 64, the last two steps in registers with shuffle-down, and the block
+// results added up serially in block order on the host (final_reduce, reductor.cpp:68-79).  Same geometry, same order here, so
+// the logged energies match the reference's digit for digit; the serial sum runs in one thread of a second launch.
+__global__ void __launch_bounds__(512) energy_tree_kernel(LoopArgs a, unsigned n, unsigned grid_size, float *__restrict__ partial) {
+    __shared__ float sdat[512], sreg[512];
+    const unsigned bs = blockDim.x, tid = threadIdx.x;
+    const int X = a.d.X, XY = a.d.X * a.d.Y;
+    float sd = 0.f, sr = 0.f;
+    for (unsigned i = blockIdx.x * bs * 2u + tid; i < n; i += grid_size) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const unsigned e = i + (h ? bs : 0u);
+            if (e < n) {
+                const float df = sub(a.pg[e], a.w[e]);               // phi_global.x - (phi_n o psi).x, reductor.cu:26-35
+                sd = __fmaf_rn(df, df, sd);
+                const int z = (int)(e / (unsigned)XY), r = (int)(e - (unsigned)z * (unsigned)XY), y = r / X, x = r - y * X;
+                sr = add(sr, jacobian_rows_nsq(a, x, y, z));
+            }
+        }
+    }
+    sdat[tid] = sd; sreg[tid] = sr;
+    __syncthreads();
+    for (unsigned s = bs / 2; s >= 64; s >>= 1) {
+        if (tid < s) { sdat[tid] = sd = add(sd, sdat[tid + s]); sreg[tid] = sr = add(sr, sreg[tid + s]); }
+        __syncthreads();
+    }
+    if (tid < 32) {
+        sd = add(sd, sdat[tid + 32]); sr = add(sr, sreg[tid + 32]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            sd = add(sd, __shfl_down_sync(0xffffffffu, sd, off));
+            sr = add(sr, __shfl_down_sync(0xffffffffu, sr, off));
+        }
+        if (tid == 0) { partial[blockIdx.x] = sd; partial[gridDim.x + blockIdx.x] = sr; }
+    }
+}
+__global__ void energy_final_kernel(const float *__restrict__ partial, unsigned blocks, double *e_data, double *e_reg) {
+    if (threadIdx.x >= 2) return;
+    const float *p = partial + threadIdx.x * blocks;
+    float r = 0.f;
+    for (unsigned b = 0; b < blocks; ++b) r = add(r, p[b]);
+    *(threadIdx.x ? e_reg : e_data) = (double)r;
+}
+
 template <bool LOG>
 __global__ void __launch_bounds__(BX *BY *BZ) pass_a_generic_kernel(LoopArgs a, int it) {
     if (loop_finished(a, it)) {
@@ -125,26 +206,7 @@ __global__ void __launch_bounds__(BX *BY *BZ) pass_a_generic_kernel(LoopArgs a, 
 
         if (LOG) {
             ed = (double)diff * (double)diff;
-            // displacement Jacobian: get_displacement subtracts the neighbour's own coordinates (vector_fields.cu:24-26)
-            const float *P[3] = {a.px, a.py, a.pz};
-            const int cxa = (x == d.X - 1) ? x - 1 : x + 1, cxb = (x == 0) ? x + 1 : x - 1;
-            const int cya = (y == d.Y - 1) ? y - 1 : y + 1, cyb = (y == 0) ? y + 1 : y - 1;
-            const int cza = z_hi ? zg - 1 : zg + 1, czb = z_lo ? zg + 1 : zg - 1;
-            float rows = 0.f;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float ox_a = (c == 0) ? (float)cxa : (c == 1 ? (float)y : (float)zg);
-                const float ox_b = (c == 0) ? (float)cxb : (c == 1 ? (float)y : (float)zg);
-                const float oy_a = (c == 0) ? (float)x : (c == 1 ? (float)cya : (float)zg);
-                const float oy_b = (c == 0) ? (float)x : (c == 1 ? (float)cyb : (float)zg);
-                const float oz_a = (c == 0) ? (float)x : (c == 1 ? (float)y : (float)cza);
-                const float oz_b = (c == 0) ? (float)x : (c == 1 ? (float)y : (float)czb);
-                const float jx = mul(sub(sub(P[c][gxa], ox_a), sub(P[c][gxb], ox_b)), 0.5f);
-                const float jy = mul(sub(sub(P[c][gya], oy_a), sub(P[c][gyb], oy_b)), 0.5f);
-                const float jz = mul(sub(sub(P[c][gza], oz_a), sub(P[c][gzb], oz_b)), 0.5f);
-                const float nsq = add(add(mul(jx, jx), mul(jy, jy)), mul(jz, jz));   // norm_sq, utils.hpp:283-285
-                rows = (c == 0) ? nsq : add(rows, nsq);
-            }
+            const float rows = jacobian_rows_nsq(a, x, y, z);
             er = (double)rows;
         }
     }
@@ -169,10 +231,23 @@ __global__ void __launch_bounds__(BX *BY *BZ) pass_a_generic_kernel(LoopArgs a, 
 //   update : update_psi_kernel, solver.cu:53-69
 //   max    : reduce_max_kernel + final_reduce_max, reductor.cu:342-456, reductor.cpp:81-94
 //   warp   : apply_kernel, vector_fields.cu:81-100 (solver.cu:168)
-SB_DEV float tap7(const float *__restrict__ g, size_t o, long stride, const float (&S)[7]) {
+SB_DEV float tap7(const float *__restrict__ g, size_t o, long stride, const float (&S)[MAX_TAPS]) {
     float s = 0.f;
 #pragma unroll
     for (int j = -3; j <= 3; ++j) s = add(s, mul(S[3 - j], g[o + (long)j * stride]));
+    return s;
+}
+
+// 2 * R + 1 taps for R != 3 (the reference's tables also hold 3-, 9- and 11-tap filters, solver.cpp:160-251; its kernels are
+// compiled for 7, solver.cu:211): same order of operations, taps S[R - j] for j = -R..R, clamp to edge by clamping the
+// coordinate (the replicated halo of the nabla_U planes is 3 deep).  Single GPU only.
+SB_DEV float tap_r(const float *__restrict__ g, const GLayout gl, int x, int y, int z, int axis, const Dims d, const float *S, int R) {
+    float s = 0.f;
+    for (int j = -R; j <= R; ++j) {
+        const int xx = axis == 0 ? min(max(x + j, 0), d.X - 1) : x, yy = axis == 1 ? min(max(y + j, 0), d.Y - 1) : y;
+        const int zz = axis == 2 ? min(max(z + j, 0), d.Z - 1) : z;
+        s = add(s, mul(S[R - j], g[gl.at(xx, yy, zz)]));
+    }
     return s;
 }
 
@@ -194,16 +269,25 @@ __global__ void __launch_bounds__(BX *BY *BZ) pass_b_generic_kernel(LoopArgs a, 
         const GLayout gl = a.gl;
         const size_t o = gl.at(x, y, z);
         const long sy = gl.PX, sz = (long)gl.plane;
-        const float fx = add(add(tap7(a.gx, o, 1, a.S), tap7(a.gx, o, sy, a.S)), tap7(a.gx, o, sz, a.S));
-        const float fy = add(add(tap7(a.gy, o, 1, a.S), tap7(a.gy, o, sy, a.S)), tap7(a.gy, o, sz, a.S));
-        const float fz = add(add(tap7(a.gz, o, 1, a.S), tap7(a.gz, o, sy, a.S)), tap7(a.gz, o, sz, a.S));
+        float fx, fy, fz;
+        if (a.radius == 3) {
+            fx = add(add(tap7(a.gx, o, 1, a.S), tap7(a.gx, o, sy, a.S)), tap7(a.gx, o, sz, a.S));
+            fy = add(add(tap7(a.gy, o, 1, a.S), tap7(a.gy, o, sy, a.S)), tap7(a.gy, o, sz, a.S));
+            fz = add(add(tap7(a.gz, o, 1, a.S), tap7(a.gz, o, sy, a.S)), tap7(a.gz, o, sz, a.S));
+        } else {
+            const int R = a.radius;
+            fx = add(add(tap_r(a.gx, gl, x, y, z, 0, d, a.S, R), tap_r(a.gx, gl, x, y, z, 1, d, a.S, R)), tap_r(a.gx, gl, x, y, z, 2, d, a.S, R));
+            fy = add(add(tap_r(a.gy, gl, x, y, z, 0, d, a.S, R), tap_r(a.gy, gl, x, y, z, 1, d, a.S, R)), tap_r(a.gy, gl, x, y, z, 2, d, a.S, R));
+            fz = add(add(tap_r(a.gz, gl, x, y, z, 0, d, a.S, R), tap_r(a.gz, gl, x, y, z, 1, d, a.S, R)), tap_r(a.gz, gl, x, y, z, 2, d, a.S, R));
+        }
         const float ux = mul(fx, a.alpha), uy = mul(fy, a.alpha), uz = mul(fz, a.alpha);
         const float npx = sub(a.px[i], ux), npy = sub(a.py[i], uy), npz = sub(a.pz[i], uz);
         a.px[i] = npx; a.py[i] = npy; a.pz[i] = npz;
         const float nsq = add(add(mul(ux, ux), mul(uy, uy)), mul(uz, uz));
         const unsigned ig = (unsigned)(i + (size_t)a.z0 * d.X * d.Y);     // global voxel index
-        key = ((unsigned long long)__float_as_uint(nsq) << 32) | (unsigned long long)(0xffffffffu - rank_of(ig, a.rm));
-        // NaN/negative never occur for a sum of squares; -0 cannot occur either
+        // the reference compares norms (__fsqrt_rd of the sum of squares, utils.hpp:279-281): ties are ties of the norm
+        const float nr = __fsqrt_rd(nsq);
+        key = nr > 0.f ? (((unsigned long long)__float_as_uint(nr) << 32) | (unsigned long long)(0xffffffffu - rank_of(ig, a.rm))) : 0ull;
         const TriCoord t = tri_coord(npx, npy, npz, a.dg);
         a.w[i] = sample_scalar<1>(a.pn, t, a.dg);
     }
@@ -251,8 +335,22 @@ void launch_initial_warp(const LoopArgs &a, cudaStream_t st) {
     initial_warp_kernel<<<stream_grid(n), 256, 0, st>>>(a);
 }
 void launch_pass_a_generic(const LoopArgs &a, int it, int log, cudaStream_t st) {
-    if (log) pass_a_generic_kernel<true><<<grid_for(a.d), dim3(BX, BY, BZ), 0, st>>>(a, it);
+    // log == 2: the energies of this iteration come from launch_energy_trees (the reference's fp32 summation order)
+    if (log == 1) pass_a_generic_kernel<true><<<grid_for(a.d), dim3(BX, BY, BZ), 0, st>>>(a, it);
     else pass_a_generic_kernel<false><<<grid_for(a.d), dim3(BX, BY, BZ), 0, st>>>(a, it);
+}
+// reduction sizing of the reference (precomp.cpp:20-43 with 65536 blocks / 512 threads, reductor.cpp:17) for n >= 1024
+unsigned energy_tree_blocks(size_t n) {
+    const size_t b = (n + 1023) / 1024;
+    return (unsigned)(b > 65536 ? 65536 : b);
+}
+// e_data[it], e_reg[it] <- the reference's fp32 sums (not yet halved); `partial` holds 2 * energy_tree_blocks(n) floats; the
+// warped plane a.w must be current
+void launch_energy_trees(const LoopArgs &a, int it, float *partial, cudaStream_t st) {
+    const size_t n = (size_t)a.d.X * a.d.Y * a.d.Z;
+    const unsigned blocks = energy_tree_blocks(n);
+    energy_tree_kernel<<<blocks, 512, 0, st>>>(a, (unsigned)n, 1024u * blocks, partial);
+    energy_final_kernel<<<1, 32, 0, st>>>(partial, blocks, a.e_data + it, a.e_reg + it);
 }
 void launch_pass_b_generic(const LoopArgs &a, int it, cudaStream_t st) {
     pass_b_generic_kernel<<<grid_for(a.d), dim3(BX, BY, BZ), 0, st>>>(a, it);

@@ -15,6 +15,7 @@ namespace sb {
 // halo depths (planes) of the slab-local arrays: one iteration depends on psi within 4 planes (1 for the stencils of pass A
 // + 3 for the filter of pass B), so with 4 halo planes of psi a rank can compute nabla_U on its own 3 halo planes itself
 // and the iteration needs ONE exchange (psi) instead of two (nabla_U and psi)
+constexpr int MAX_TAPS = 11;           // longest filter the reference tabulates (solver.cpp:160-251: s = 3, 7, 9, 11)
 constexpr int PSI_HALO = 4;
 constexpr int PG_HALO = 3;
 
@@ -46,8 +47,10 @@ struct LoopArgs {
     Dims d, dg;
     int z0;
     GLayout gl;
-    // parameters
-    float S[7];
+    // parameters: the filter has 2 * radius + 1 taps; the tiled kernels are built for radius 3 (the reference's KERNEL_RADIUS,
+    // solver.cu:211), other radii run the generic kernels
+    float S[MAX_TAPS];
+    int radius;
     float alpha, w_reg, thr;
     // convergence / logging
     LoopState *state;
@@ -184,8 +187,7 @@ SB_DEV bool loop_finished(const LoopArgs &a, int it) {
     if (!a.check) return false;
     if (a.state->converged) return true;
     if (it == 0) return false;
-    const float s = __uint_as_float((unsigned)(a.maxkey[it - 1] >> 32));
-    return __fsqrt_rd(s) <= a.thr;      // norm = __fsqrt_rd(sum of squares), utils.hpp:279-281
+    return __uint_as_float((unsigned)(a.maxkey[it - 1] >> 32)) <= a.thr;      // the key carries the norm (common.cuh MaxCand)
 }
 // same decision in peer mode: the maximum of iteration it-1 over all ranks, from the table the ranks publish into (ONE
 // whole warp per block calls this -- lane r polls rank r's entry -- and broadcasts the result)
@@ -194,15 +196,21 @@ SB_DEV bool loop_finished_peer(const LoopArgs &a, int it) {
     if (a.state->converged) return true;
     if (it == 0) return false;
     const unsigned long long m = peer_wait_all_max(a.allmax + (size_t)(it - 1) * a.peer_n, a.peer_n, a.peer_error);
-    const float s = __uint_as_float((unsigned)(m >> 32));
-    return __fsqrt_rd(s) <= a.thr;
+    return __uint_as_float((unsigned)(m >> 32)) <= a.thr;
 }
 
 void launch_unpack(const float4 *psi, const float2 *phi_global, const float2 *phi_n, const LoopArgs &a, cudaStream_t st);
-void launch_estimate_inverse_slab(const float4 *psi_full, float4 *psi_inv_local, Dims dg, int z0, int nzl, int iters, cudaStream_t st);
-void launch_apply_slab(const float2 *phi_full, float2 *out_local, const float4 *psi_local, Dims dg, int z0, int nzl, cudaStream_t st);
+// planes [z0, z0 + nz) of the volume that an array covers, and where a gather outside of it is reported (see field_ops.cu)
+struct ZWindow {
+    int z0, nz;
+    int *overflow;
+};
+void launch_estimate_inverse_slab(const float4 *psi_win, float4 *psi_inv_local, Dims dg, int z0, int nzl, int iters, ZWindow w, cudaStream_t st);
+void launch_apply_slab(const float2 *phi_win, float2 *out_local, const float4 *psi_local, Dims dg, int nzl, ZWindow w, cudaStream_t st);
 void launch_initial_warp(const LoopArgs &a, cudaStream_t st);
-void launch_pass_a_generic(const LoopArgs &a, int it, int log, cudaStream_t st);
+void launch_pass_a_generic(const LoopArgs &a, int it, int log, cudaStream_t st);   // log: 0 none, 1 energies in double (atomics), 2 energies elsewhere
+unsigned energy_tree_blocks(size_t n);
+void launch_energy_trees(const LoopArgs &a, int it, float *partial, cudaStream_t st);
 void launch_pass_b_generic(const LoopArgs &a, int it, cudaStream_t st);
 void launch_pack(float4 *psi, float2 *phi_n_psi, const float2 *phi_n, const LoopArgs &a, cudaStream_t st);
 
@@ -212,7 +220,7 @@ struct TmaMaps;   // opaque: CUtensorMaps of the nabla_U components (pass B) and
 TmaMaps *tma_maps_create(const LoopArgs &a);
 void tma_maps_destroy(TmaMaps *m);
 LaunchInfo launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, const ZRanges &zr, cudaStream_t st);
-void set_pass_a_variant(int v);   // 0: default kernel, 3: warp-specialised sampling (experimental); per host thread
+void set_pass_a_variant(int v);   // 0: default kernel, 4: software-pipelined gathers; per host thread
 LaunchInfo launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, const ZRanges &zr, cudaStream_t st);   // grid 0: generic path
 // peer mode: the planes [lo, hi) of a launch (pass 0 = A, 1 = B) as | lower face chunk | upper face chunk | middle |
 ZRanges plan_peer_ranges(const Dims d, int pass, int lo, int hi, bool has_lo, bool has_hi, int sms = 0);

@@ -97,19 +97,30 @@ struct TexSample {
     float a, b, c;       // fractional weights
     bool sx, sy;
 };
-SB_DEVI void tex_issue(TexSample &s, cudaTextureObject_t tex, int ashift, int amask, float px, float py, float pz, const Dims d) {
+// the fractional weights and the two "upper index not advanced" flags of utils.hpp:61-75 alone (no fetch)
+SB_DEVI void tex_weights(TexSample &s, float px, float py, float pz, const Dims d) {
+    const float mx = (float)d.X - 1.f, my = (float)d.Y - 1.f, mz = (float)d.Z - 1.f;
+    const float cx = fminf(fmaxf(0.f, px), mx), cy = fminf(fmaxf(0.f, py), my), cz = fminf(fmaxf(0.f, pz), mz);
+    s.sx = (cx == 0.f || cx == mx);
+    s.sy = (cy == 0.f || cy == my);
+    s.a = __fsub_rn(cx, floorf(cx)); s.b = __fsub_rn(cy, floorf(cy)); s.c = __fsub_rn(cz, floorf(cz));
+}
+// the two gather4 fetches alone: their 8 result registers are all a sample in flight needs (the software-pipelined pass A
+// recomputes the weights from psi when it consumes them a step later)
+SB_DEVI void tex_fetch(float4 &lo, float4 &hi, cudaTextureObject_t tex, int ashift, int amask, float px, float py, float pz, const Dims d) {
     const float mx = (float)d.X - 1.f, my = (float)d.Y - 1.f, mz = (float)d.Z - 1.f;
     const float cx = fminf(fmaxf(0.f, px), mx), cy = fminf(fmaxf(0.f, py), my), cz = fminf(fmaxf(0.f, pz), mz);
     const float fx = floorf(cx), fy = floorf(cy), fz = floorf(cz);
-    s.sx = (cx == 0.f || cx == mx);
-    s.sy = (cy == 0.f || cy == my);
-    s.a = __fsub_rn(cx, fx); s.b = __fsub_rn(cy, fy); s.c = __fsub_rn(cz, fz);
     const float kxf = (float)(amask + 1), ikx = __int_as_float((127 - ashift) << 23);      // kx = 2^ashift and 1 / kx
     const float u = fx + 1.f, v = fy + 1.f;                           // footprint (gx, gx+1) x (gy, gy+1)
     const float z1 = (cz == 0.f || cz == mz) ? fz : fz + 1.f;
     const float r0 = floorf(fz * ikx), r1 = floorf(z1 * ikx);         // atlas row of the slice; column = z - row * kx
-    s.lo = tex2Dgather<float4>(tex, __fmaf_rn(__fmaf_rn(-r0, kxf, fz), (float)d.X, u), __fmaf_rn(r0, (float)d.Y, v), 0);
-    s.hi = tex2Dgather<float4>(tex, __fmaf_rn(__fmaf_rn(-r1, kxf, z1), (float)d.X, u), __fmaf_rn(r1, (float)d.Y, v), 0);
+    lo = tex2Dgather<float4>(tex, __fmaf_rn(__fmaf_rn(-r0, kxf, fz), (float)d.X, u), __fmaf_rn(r0, (float)d.Y, v), 0);
+    hi = tex2Dgather<float4>(tex, __fmaf_rn(__fmaf_rn(-r1, kxf, z1), (float)d.X, u), __fmaf_rn(r1, (float)d.Y, v), 0);
+}
+SB_DEVI void tex_issue(TexSample &s, cudaTextureObject_t tex, int ashift, int amask, float px, float py, float pz, const Dims d) {
+    tex_weights(s, px, py, pz, d);
+    tex_fetch(s.lo, s.hi, tex, ashift, amask, px, py, pz, d);
 }
 SB_DEVI float tex_finish(const TexSample &s) {
     const float v000 = s.lo.w, v100 = s.sx ? s.lo.w : s.lo.z;
@@ -279,7 +290,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
     // ---- consumers ----
     float *__restrict__ P[3] = {a.px, a.py, a.pz};
     unsigned q = 0;                       // planes consumed so far
-    unsigned best_bits = 0u, best_idx = 0u;
+    MaxCand best{0u, 0u, 0u};
     const unsigned zoff = (unsigned)a.z0 * (unsigned)XY;
     float4 win[7][3];                     // nabla_U of this thread's 4 voxels at planes c-3 .. c+3
     int ack_seen = 0;                     // faces whose acknowledgement this CTA has already waited for
@@ -363,11 +374,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
                             *reinterpret_cast<float4 *>(a.peer_lo[c] + o) = make_float4(np[c][0], np[c][1], np[c][2], np[c][3]);
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const unsigned bits = __float_as_uint(nsq[j]), idx = (unsigned)(o + j) + zoff;   // global voxel index
-                        if (bits > best_bits) { best_bits = bits; best_idx = idx; }
-                        else if (bits == best_bits && bits != 0u && rank_of(idx, a.rm) < rank_of(best_idx, a.rm)) best_idx = idx;
-                    }
+                    for (int j = 0; j < 4; ++j) max_cand_update(best, nsq[j], (unsigned)(o + j) + zoff, a.rm);   // global voxel index
                 }
             }
             // hand the stage of plane q-4 (0-based: the centre plane just used) back to the producer
@@ -385,9 +392,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
             }
         }
     }
-    unsigned long long best = best_bits ? (((unsigned long long)best_bits << 32) | (unsigned long long)(0xffffffffu - rank_of(best_idx, a.rm))) : 0ull;
-    best = warp_max_u64(best);
-    if (lane == 0) skey[warp] = best;
+    const unsigned long long bkey = warp_max_u64(max_cand_key(best, a.rm));
+    if (lane == 0) skey[warp] = bkey;
     asm volatile("bar.sync 1, %0;" ::"r"(NW * 32) : "memory");   // consumers only (the producer warp has left)
     if (tid == 0) {
         unsigned long long m = 0ull;
@@ -420,6 +426,114 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
 #ifndef PA_LX
 #define PA_LX 8         // lanes per tile row (4 voxels each)
 #endif
+
+SB_DEVI void sts4(unsigned saddr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+SB_DEVI void sts1(unsigned saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
+
+// ---- the stencil half of pass A, shared by its kernels: one thread = 4 consecutive voxels (a "quad") of one tile row ----
+struct Quad {
+    int x0, y;                        // volume coordinates of the first voxel
+    bool active, x_lo, x_hi, y_lo, y_hi;
+};
+// w_reg * laplacian(psi) at the centre plane (vector_fields.cu:291-337); on a boundary plane both neighbours of that axis are
+// the voxel itself.  sC / sM: shared addresses of the quad in the staged psi planes zc and zc-1 (component stride ARR bytes, row
+// pitch SX floats), Zpl: the quad of psi at zc+1; bz: zc is the first or last plane of the VOLUME
+template <int SX, int ARR>
+SB_DEVI void laplacian_quad(float (&Lw)[3][4], const Quad &qd, bool bz, unsigned sC, unsigned sM, const float4 (&Zpl)[3], float w_reg) {
+    const bool by = qd.y_lo || qd.y_hi, edge = by || bz;   // y / z faces are rare: their selects live in a branch interior threads skip
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const unsigned p0 = sC + c * ARR;
+        const float4 C = lds4(p0);
+        float4 Ym = lds4(p0 - SX * 4), Yp = lds4(p0 + SX * 4), Zp = Zpl[c], Zm = lds4(sM + c * ARR);
+        const float xl = lds1(p0 - 4), xr = lds1(p0 + 16);
+        // only the first / last voxel of a row can sit on an x face (X % 4 == 0)
+        const float xm[4] = {qd.x_lo ? C.x : xl, C.x, C.y, qd.x_hi ? C.w : C.z}, xp[4] = {qd.x_lo ? C.x : C.y, C.z, C.w, qd.x_hi ? C.w : xr};
+        if (edge) {
+            if (by) Yp = Ym = C;
+            if (bz) Zp = Zm = C;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v = mul(c4(C, j), -6.f);
+            v = add(v, xp[j]);
+            v = add(v, xm[j]);
+            v = add(v, c4(Yp, j));
+            v = add(v, c4(Ym, j));
+            v = add(v, c4(Zp, j));
+            v = add(v, c4(Zm, j));
+            Lw[c][j] = mul(mul(v, -1.f), w_reg);
+        }
+    }
+}
+// central differences of the warped TSDF at the centre plane (vector_fields.cu:157-208; both taps on the in-range neighbour at
+// a boundary -> +0), nabla_U = (w - phi_global) * grad(w) + w_reg * L (solver.cu:15-33), stored with the replicated halo of 3
+// that turns the filter's clamp to edge into plain loads (solver.cu:256,263,270).  w0: shared address of the quad in the warped
+// plane zc (row pitch SX floats); wm / wc / wp: the quad of w at zc-1, zc, zc+1; zc is a LOCAL plane
+template <int SX>
+SB_DEVI void gradient_store_quad(const LoopArgs &a, const Quad &qd, int zc, bool z_lo, bool z_hi, unsigned w0, float4 wm, float4 wc, float4 wp,
+                                 float4 g4, const float (&Lw)[3][4]) {
+    const bool edge = qd.y_lo || qd.y_hi || z_lo || z_hi;
+    float nx[4], ny[4], nz[4], df[4];
+    {
+        const float4 C = wc, Ym = lds4(w0 - SX * 4), Yp = lds4(w0 + SX * 4);
+        const float xl = lds1(w0 - 4), xr = lds1(w0 + 16);
+        const float xm[4] = {qd.x_lo ? C.y : xl, C.x, C.y, C.z}, xp[4] = {C.y, C.z, C.w, qd.x_hi ? C.z : xr};
+        float4 Y1 = Yp, Y2 = Ym, Z1 = wp, Z2 = wm;
+        if (edge) {
+            if (qd.y_hi) Y1 = Ym;
+            if (qd.y_lo) Y2 = Yp;
+            if (z_hi) Z1 = wm;
+            if (z_lo) Z2 = wp;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            nx[j] = mul(sub(xp[j], xm[j]), 0.5f);      // __fdividef(., 2.f)
+            ny[j] = mul(sub(c4(Y1, j), c4(Y2, j)), 0.5f);
+            nz[j] = mul(sub(c4(Z1, j), c4(Z2, j)), 0.5f);
+            df[j] = sub(c4(C, j), c4(g4, j));
+        }
+    }
+    const GLayout gl = a.gl;
+    const int X = a.d.X;
+    const size_t o = gl.at(min(qd.x0, X - 4), min(qd.y, a.d.Y - 1), zc);
+    float *__restrict__ G[3] = {a.gx, a.gy, a.gz};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float u[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float n = (c == 0) ? nx[j] : (c == 1 ? ny[j] : nz[j]);
+            u[j] = add(mul(n, df[j]), Lw[c][j]);
+        }
+        if (qd.active) {
+            float *__restrict__ g = G[c];
+            const float4 uv = make_float4(u[0], u[1], u[2], u[3]);
+            *reinterpret_cast<float4 *>(g + o) = uv;
+            if (qd.x0 == 0) *reinterpret_cast<float4 *>(g + o - 4) = make_float4(u[0], u[0], u[0], u[0]);
+            if (qd.x0 + 4 == X) *reinterpret_cast<float4 *>(g + o + 4) = make_float4(u[3], u[3], u[3], u[3]);
+            if (qd.y_lo) {
+#pragma unroll
+                for (int k = 1; k <= 3; ++k) *reinterpret_cast<float4 *>(g + o - (size_t)k * gl.PX) = uv;
+            }
+            if (qd.y_hi) {
+#pragma unroll
+                for (int k = 1; k <= 3; ++k) *reinterpret_cast<float4 *>(g + o + (size_t)k * gl.PX) = uv;
+            }
+            if (z_lo) {
+#pragma unroll
+                for (int k = 1; k <= 3; ++k) *reinterpret_cast<float4 *>(g + o - (size_t)k * gl.plane) = uv;
+            }
+            if (z_hi) {
+#pragma unroll
+                for (int k = 1; k <= 3; ++k) *reinterpret_cast<float4 *>(g + o + (size_t)k * gl.plane) = uv;
+            }
+        }
+    }
+}
+
 namespace pa {
 constexpr int LX = PA_LX, RW = 32 / LX, NW = PA_NW;
 constexpr int NTHREADS = NW * 32;
@@ -435,11 +549,6 @@ constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 3 * WBUF_BYTES + 128;
 constexpr unsigned TX_BYTES = 3u * SX * SY * 4u;
 constexpr int NHALO = 2 * TX + 2 * TY;            // cross halo cells of a plane: rows y0-1, y0+TY and columns x0-1, x0+TX
 static_assert(NHALO <= NTHREADS, "one halo cell per thread");
-
-SB_DEVI void sts4(unsigned saddr, float4 v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-SB_DEVI void sts1(unsigned saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
 
 // One CTA = NW warps marching a TX x TY column along z, all in lockstep (one block barrier per plane).  There is no producer
 // warp: after the barrier of step q the stage of plane q-3 is free by construction, and thread 0 refills it with plane q+1
@@ -527,18 +636,16 @@ __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
     else if (tid < 2 * TX + TY) { hx = 3; hy = 1 + tid - 2 * TX; }
     else if (tid < NHALO) { hx = 4 + TX; hy = 1 + tid - 2 * TX - TY; }
     const unsigned halo_off = (unsigned)((hy * SX + hx) * 4);
-    float *__restrict__ G[3] = {a.gx, a.gy, a.gz};
     const float *__restrict__ pn = a.pn;
-    const GLayout gl = a.gl;
     unsigned q = 0;
     St cs;
     for (cs.open(blockIdx.x, sc, d.Z); cs.valid(sc); cs.open(cs.item + (int)gridDim.x, sc, d.Z)) {
-        const int x0 = cs.x0t + 4 * lx, y = cs.y0t + ty;
-        const bool active = x0 < X && y < d.Y;
-        const int row = min(x0, X - 4) + X * min(y, d.Y - 1);
-        const bool y_lo = (y == 0), y_hi = (y == d.Y - 1), by = y_lo || y_hi;
-        // only the first / last voxel of a row can sit on an x face (X % 4 == 0)
-        const bool x_lo = (x0 == 0), x_hi = (x0 + 4 == X);
+        Quad qd;
+        qd.x0 = cs.x0t + 4 * lx; qd.y = cs.y0t + ty;
+        qd.active = qd.x0 < X && qd.y < d.Y;
+        const int row = min(qd.x0, X - 4) + X * min(qd.y, d.Y - 1);
+        qd.y_lo = (qd.y == 0); qd.y_hi = (qd.y == d.Y - 1);
+        qd.x_lo = (qd.x0 == 0); qd.x_hi = (qd.x0 + 4 == X);
         const int hgx = cs.x0t - 4 + hx, hgy = cs.y0t - 1 + hy;       // volume coordinates of the halo cell
         const bool halo_on = hx >= 0 && hgx >= 0 && hgx < X && hgy >= 0 && hgy < d.Y;
         float4 wm = make_float4(0.f, 0.f, 0.f, 0.f), wc = wm;        // this thread's quad of w at planes z-1 and z
@@ -559,42 +666,15 @@ __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
 #pragma unroll
             for (int k = 0; k < 3; ++k) zp[k] = lds4(stP + own_off + k * ARR_BYTES);
             const bool plane_on = (a.z0 + p >= 0 && a.z0 + p < dg.Z);        // planes outside the volume are never used
-            const bool z_lo = (a.z0 + zc == 0), z_hi = (a.z0 + zc == dg.Z - 1), bz = z_lo || z_hi;   // global faces only
-            const bool edge = by || bz;       // y / z faces are rare: their selects live in a branch interior threads skip
+            const bool z_lo = (a.z0 + zc == 0), z_hi = (a.z0 + zc == dg.Z - 1);   // global faces only
 
-            // ---- w_reg * laplacian(psi) at the centre plane (vector_fields.cu:291-337); on a boundary plane both neighbours
-            //      of that axis are the voxel itself ----
             float Lw[3][4];
-            if (centre_on) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const unsigned p0 = sC + c * ARR_BYTES;
-                    const float4 C = lds4(p0);
-                    float4 Ym = lds4(p0 - SX * 4), Yp = lds4(p0 + SX * 4), Zp = zp[c], Zm = lds4(sM + c * ARR_BYTES);
-                    const float xl = lds1(p0 - 4), xr = lds1(p0 + 16);
-                    const float xm[4] = {x_lo ? C.x : xl, C.x, C.y, x_hi ? C.w : C.z}, xp[4] = {x_lo ? C.x : C.y, C.z, C.w, x_hi ? C.w : xr};
-                    if (edge) {
-                        if (by) Yp = Ym = C;
-                        if (bz) Zp = Zm = C;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float v = mul(c4(C, j), -6.f);
-                        v = add(v, xp[j]);
-                        v = add(v, xm[j]);
-                        v = add(v, c4(Yp, j));
-                        v = add(v, c4(Ym, j));
-                        v = add(v, c4(Zp, j));
-                        v = add(v, c4(Zm, j));
-                        Lw[c][j] = mul(mul(v, -1.f), a.w_reg);
-                    }
-                }
-            }
+            if (centre_on) laplacian_quad<SX, ARR_BYTES>(Lw, qd, z_lo || z_hi, sC, sM, zp, a.w_reg);
 
             // ---- warp of plane p: own quad + this thread's cross-halo cell ----
             float4 wp = make_float4(0.f, 0.f, 0.f, 0.f);
             if (plane_on) {
-                if (active) {
+                if (qd.active) {
                     if (TEX) {
                         wp.x = warp_sample_tex(a.pn_tex, a.ashift, a.amask, zp[0].x, zp[1].x, zp[2].x, dg);
                         wp.y = warp_sample_tex(a.pn_tex, a.ashift, a.amask, zp[0].y, zp[1].y, zp[2].y, dg);
@@ -616,66 +696,7 @@ __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
             __syncthreads();                  // warped plane p (and p-1) visible to the CTA; ring stage of plane p-3 is free
             if (tid == 0) feed();
 
-            // ---- nabla_U of the centre plane ----
-            if (centre_on) {
-                // central differences of the warped TSDF (vector_fields.cu:157-208); both taps on the in-range neighbour at a
-                // boundary (-> +0)
-                float nx[4], ny[4], nz[4], df[4];
-                {
-                    const unsigned w0 = wctr + own_off;
-                    const float4 C = wc, Ym = lds4(w0 - SX * 4), Yp = lds4(w0 + SX * 4);
-                    const float xl = lds1(w0 - 4), xr = lds1(w0 + 16);
-                    const float xm[4] = {x_lo ? C.y : xl, C.x, C.y, C.z}, xp[4] = {C.y, C.z, C.w, x_hi ? C.z : xr};
-                    float4 Y1 = Yp, Y2 = Ym, Z1 = wp, Z2 = wm;
-                    if (edge) {
-                        if (y_hi) Y1 = Ym;
-                        if (y_lo) Y2 = Yp;
-                        if (z_hi) Z1 = wm;
-                        if (z_lo) Z2 = wp;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        nx[j] = mul(sub(xp[j], xm[j]), 0.5f);      // __fdividef(., 2.f)
-                        ny[j] = mul(sub(c4(Y1, j), c4(Y2, j)), 0.5f);
-                        nz[j] = mul(sub(c4(Z1, j), c4(Z2, j)), 0.5f);
-                        df[j] = sub(c4(C, j), c4(g4, j));
-                    }
-                }
-                const size_t o = gl.at(min(x0, X - 4), min(y, d.Y - 1), zc);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    float u[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float n = (c == 0) ? nx[j] : (c == 1 ? ny[j] : nz[j]);
-                        u[j] = add(mul(n, df[j]), Lw[c][j]);       // solver.cu:15-33
-                    }
-                    if (active) {
-                        float *__restrict__ g = G[c];
-                        const float4 uv = make_float4(u[0], u[1], u[2], u[3]);
-                        *reinterpret_cast<float4 *>(g + o) = uv;
-                        // replicated halo of 3 (clamp to edge of the filter, solver.cu:256,263,270)
-                        if (x0 == 0) *reinterpret_cast<float4 *>(g + o - 4) = make_float4(u[0], u[0], u[0], u[0]);
-                        if (x0 + 4 == X) *reinterpret_cast<float4 *>(g + o + 4) = make_float4(u[3], u[3], u[3], u[3]);
-                        if (y_lo) {
-#pragma unroll
-                            for (int k = 1; k <= 3; ++k) *reinterpret_cast<float4 *>(g + o - (size_t)k * gl.PX) = uv;
-                        }
-                        if (y_hi) {
-#pragma unroll
-                            for (int k = 1; k <= 3; ++k) *reinterpret_cast<float4 *>(g + o + (size_t)k * gl.PX) = uv;
-                        }
-                        if (z_lo) {
-#pragma unroll
-                            for (int k = 1; k <= 3; ++k) *reinterpret_cast<float4 *>(g + o - (size_t)k * gl.plane) = uv;
-                        }
-                        if (z_hi) {
-#pragma unroll
-                            for (int k = 1; k <= 3; ++k) *reinterpret_cast<float4 *>(g + o + (size_t)k * gl.plane) = uv;
-                        }
-                    }
-                }
-            }
+            if (centre_on) gradient_store_quad<SX>(a, qd, zc, z_lo, z_hi, wctr + own_off, wm, wc, wp, g4, Lw);
             wm = wc; wc = wp;
         }
         // peer mode: every plane of this item has been staged (thread 0 waited for the last one itself), so the item no longer
@@ -690,50 +711,47 @@ __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
 }  // namespace pa
 
 // =============================================================================================================
-// pass A, warp-specialised (EXPERIMENTAL: variant 3, not the default)
+// pass A, software-pipelined across planes (variant 4)
 // =============================================================================================================
-// Same arithmetic and the same outputs as pa::pass_a_tma_kernel, different division of labour inside the CTA.  The warp of the
-// live TSDF (two gather4 texture round trips per sample) is 30 % of pass A's instructions and all of its long-scoreboard stalls;
-// here it is done by dedicated SAMPLER warps that run a plane or two ahead and need few registers (setmaxnreg.dec), while one
-// STENCIL warpgroup (setmaxnreg.inc) turns finished planes of w into the Laplacian / gradient / nabla_U.  More warps per SM hide
-// the texture latency, and the FP32 work of the stencil overlaps it.
-//   psi ring   : NSTAGE stages filled by TMA (lane 0 of the first sampler warp feeds AHEAD planes ahead of its own position);
-//                full[stage] (tx count) / empty[stage] (NSAMP sampler warps + NWS stencil warps arrive)
-//   w ring     : NWB planes of warped TSDF (tile + cross halo); wfull[b] (NSAMP arrivals) / wempty[b] (NWS arrivals)
-//   stream pos : every role walks the same continuous plane stream (items of a CTA back to back); position q uses psi stage
-//                q % NSTAGE and w buffer q % NWB; the stencil at position q reads psi and w of positions q-2, q-1, q and then
-//                releases position q-2
-#ifndef PAW_NSAMP
-#define PAW_NSAMP 8          // sampler warps (multiple of 4: setmaxnreg works on warpgroups)
+// Same arithmetic and the same outputs as pa::pass_a_tma_kernel.  There the two gather4 fetches of a sample are consumed right
+// after they are issued: five dependent texture round trips per thread and plane, 16 warps per SM -- issue slots are used 51 % of
+// the time (profiles/r1_ncu_tma_v9_summary.md).  Here the fetches of plane p are issued in step p and consumed in step p+1: a whole
+// step of stencil arithmetic (and the other warps' steps) sits between a fetch and its first use.  Only the 8 result registers of
+// a fetch stay live across the step (5 samples per thread: 40 registers); the interpolation weights are recomputed from psi,
+// which is still in the ring.  Price: the centre plane trails the newest plane by two instead of one (one more pipeline-fill step
+// per work item, one more ring stage) and 168 registers (3 CTAs of 4 warps per SM instead of 4).
+#ifndef PA2_CTAS
+#define PA2_CTAS 3
 #endif
-#ifndef PAW_CTAS
-#define PAW_CTAS 2           // CTAs per SM
+#ifndef PA2_AHEAD
+#define PA2_AHEAD 1
 #endif
-#ifndef PAW_REG_STENCIL
-#define PAW_REG_STENCIL 144   // 128 x 144 + 256 x 48 = 30720 = 384 threads x 80 registers at launch
-#endif
-#ifndef PAW_REG_SAMPLER
-#define PAW_REG_SAMPLER 48
-#endif
-namespace paw {
-constexpr int LX = 8, RW = 32 / LX, NWS = 4, NSAMP = PAW_NSAMP;
-constexpr int NTHREADS = (NWS + NSAMP) * 32;
-constexpr int TX = 4 * LX, TY = NWS * RW;          // 32 x 16 outputs per plane, as pa
-constexpr int SX = TX + 8, SY = TY + 2;
-constexpr int NSTAGE = 6, AHEAD = 2, NWB = 5, PF_AHEAD = 4;
-constexpr int ARR_BYTES = ((SX * SY * 4 + 127) / 128) * 128;
-constexpr int STAGE_BYTES = 3 * ARR_BYTES;
-constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + NWB * ARR_BYTES + 128;
-constexpr unsigned TX_BYTES = 3u * SX * SY * 4u;
-constexpr int NHALO = 2 * TX + 2 * TY;
-constexpr int NSAMPLES = TX * TY + NHALO;
-static_assert(NSAMP % 4 == 0 && AHEAD <= NSTAGE - 3 && NWB >= 4, "ring depths");
-static_assert(TX == pa::TX && TY == pa::TY, "same tile as pass A: the schedule and the tensor maps are shared");
+namespace pa2 {
+constexpr int LX = pa::LX, RW = pa::RW, NW = pa::NW, NTHREADS = pa::NTHREADS;
+constexpr int TX = pa::TX, TY = pa::TY, SX = pa::SX, SY = pa::SY;     // same tile: the tensor maps are shared
+constexpr int AHEAD = PA2_AHEAD, NSTAGE = 4 + AHEAD;                  // planes p-3 .. p live + AHEAD in flight
+constexpr int PF_AHEAD = 4;
+constexpr int ARR_BYTES = pa::ARR_BYTES, STAGE_BYTES = 3 * ARR_BYTES;
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 3 * ARR_BYTES + 128;
+constexpr unsigned TX_BYTES = pa::TX_BYTES;
+constexpr int NHALO = pa::NHALO;
 
-template <bool TEX>
-__global__ void __launch_bounds__(NTHREADS, PAW_CTAS)
-    pass_a_ws_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__ CUtensorMap m1,
-                     const __grid_constant__ CUtensorMap m2, LoopArgs a, int it, Sched sc) {
+template <bool PEER>
+__global__ void __launch_bounds__(NTHREADS, PA2_CTAS)
+    pass_a_pipe_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__ CUtensorMap m1,
+                       const __grid_constant__ CUtensorMap m2, LoopArgs a, int it, Sched sc) {
+    pdl_launch_dependents();
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned smem = (smem_u32(smem_raw) + 127u) & ~127u;
+    const unsigned wbuf0 = smem + NSTAGE * STAGE_BYTES;
+    __shared__ unsigned long long bars[NSTAGE];
+    const unsigned full0 = smem_u32(&bars[0]);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(full0 + 8 * s, 1);
+        mbar_fence_init();
+    }
+    pdl_wait();
     if (a.a_uses_max ? loop_finished(a, it) : (a.check && a.state->converged)) {
         if (a.check && blockIdx.x == 0 && threadIdx.x == 0 && !a.state->converged) {
             a.state->iters = it;
@@ -741,227 +759,145 @@ __global__ void __launch_bounds__(NTHREADS, PAW_CTAS)
         }
         return;
     }
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const unsigned smem = (smem_u32(smem_raw) + 127u) & ~127u;
-    const unsigned wbuf0 = smem + NSTAGE * STAGE_BYTES;
-    __shared__ unsigned long long bars[2 * NSTAGE + 2 * NWB];
-    const unsigned full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[NSTAGE]);
-    const unsigned wfull0 = smem_u32(&bars[2 * NSTAGE]), wempty0 = smem_u32(&bars[2 * NSTAGE + NWB]);
+    if (PEER && threadIdx.x == 0) trace_begin(a.trace);
 
     const Dims d = a.d, dg = a.dg;
     const int X = d.X, XY = d.X * d.Y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NWS + NSAMP); }
-#pragma unroll
-        for (int b = 0; b < NWB; ++b) { mbar_init(wfull0 + 8 * b, NSAMP); mbar_init(wempty0 + 8 * b, NWS); }
-        mbar_fence_init();
-    }
     __syncthreads();
-    typedef Stream<TX, TY, 1, 1> St;
 
-    if (warp >= NWS) {
-        // ------------------------------------------------------------------------------------------------ samplers
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PAW_REG_SAMPLER));
-        const int sid = tid - NWS * 32;
-        const bool feeder = (sid == 0);
-        St pr{};                              // feeder only: position of the TMA loads in the plane stream
-        unsigned qi = 0;
-        auto feed = [&]() {
-            const unsigned slot = qi % NSTAGE, n = qi / NSTAGE;
-            if (n > 0) mbar_wait(empty0 + 8 * slot, (n - 1) & 1u);      // samplers and stencil are done with the plane that was here
-            const unsigned dst = smem + slot * STAGE_BYTES, bar = full0 + 8 * slot;
-            mbar_expect_tx(bar, TX_BYTES);
-            tma_load_3d(dst, &m0, bar, pr.x0t - 4, pr.y0t - 1, pr.p + PSI_HALO);
-            tma_load_3d(dst + ARR_BYTES, &m1, bar, pr.x0t - 4, pr.y0t - 1, pr.p + PSI_HALO);
-            tma_load_3d(dst + 2 * ARR_BYTES, &m2, bar, pr.x0t - 4, pr.y0t - 1, pr.p + PSI_HALO);
-            if (pr.p + PF_AHEAD <= pr.p_last) {
-                tma_prefetch_3d(&m0, pr.x0t - 4, pr.y0t - 1, pr.p + PF_AHEAD + PSI_HALO);
-                tma_prefetch_3d(&m1, pr.x0t - 4, pr.y0t - 1, pr.p + PF_AHEAD + PSI_HALO);
-                tma_prefetch_3d(&m2, pr.x0t - 4, pr.y0t - 1, pr.p + PF_AHEAD + PSI_HALO);
+    // planes zb-1 .. ze+1 of an item: the last step only drains the pipeline (its plane is staged but not used)
+    typedef Stream<TX, TY, 1, 2> St;
+    St pr;
+    unsigned qi = 0;
+    int halo_seen = 0;
+    auto feed = [&]() {
+        if (!pr.valid(sc)) return;
+        if (PEER && a.wait_halo && pr.face != 0 && !(halo_seen & pr.face)) {
+            const unsigned long long want = pr.face == 1 ? a.expect_lo : a.expect_hi;
+            if (want) {
+                const unsigned long long t0 = a.trace ? global_timer_ns() : 0ull;
+                peer_wait_ge(a.my_cnt + (pr.face - 1), want, a.peer_error);
+                trace_wait(a.trace, 4, t0);
             }
-            ++qi;
-            pr.next(sc, d.Z);
-        };
-        if (feeder) pr.open(blockIdx.x, sc, d.Z);
-        const float *__restrict__ pn = a.pn;
-        unsigned q = 0;
-        St ss;
-        for (ss.open(blockIdx.x, sc, d.Z); ss.valid(sc); ss.open(ss.item + (int)gridDim.x, sc, d.Z)) {
-            for (int p = ss.p; p <= ss.p_last; ++p) {
-                if (feeder) {
-                    while (qi <= q + AHEAD && pr.valid(sc)) feed();
-                }
-                const unsigned slot = q % NSTAGE, wb = q % NWB;
-                mbar_wait(full0 + 8 * slot, (q / NSTAGE) & 1u);
-                if (q >= (unsigned)NWB) mbar_wait(wempty0 + 8 * wb, ((q / NWB) - 1u) & 1u);   // the stencil has left the plane that was here
-                const unsigned stP = smem + slot * STAGE_BYTES, wcur = wbuf0 + wb * ARR_BYTES;
-                const bool plane_on = (a.z0 + p >= 0 && a.z0 + p < dg.Z);      // planes outside the volume are never used
-                if (plane_on) {
-                    // sample i -> cell of the staged box: the tile first (x fastest), then the cross halo (rows y0-1 and y0+TY,
-                    // columns x0-1 and x0+TX), as in pa::pass_a_tma_kernel.  off < 0: the cell lies outside the volume.
-                    auto cell = [&](int i) -> int {
-                        int bx, by;
-                        if (i < TX * TY) { bx = 4 + (i % TX); by = 1 + i / TX; }
-                        else {
-                            const int h = i - TX * TY;
-                            if (h < TX) { bx = 4 + h; by = 0; }
-                            else if (h < 2 * TX) { bx = 4 + h - TX; by = TY + 1; }
-                            else if (h < 2 * TX + TY) { bx = 3; by = 1 + h - 2 * TX; }
-                            else { bx = 4 + TX; by = 1 + h - 2 * TX - TY; }
-                        }
-                        const int gx = ss.x0t - 4 + bx, gy = ss.y0t - 1 + by;
-                        return (gx < 0 || gx >= X || gy < 0 || gy >= d.Y) ? -1 : (by * SX + bx) * 4;
-                    };
-                    // two samples per round: the gathers of both are in flight before the first result is touched
-                    for (int i = sid; i < NSAMPLES; i += 2 * NSAMP * 32) {
-                        const int o0 = cell(i), o1 = (i + NSAMP * 32 < NSAMPLES) ? cell(i + NSAMP * 32) : -1;
-                        if (TEX) {
-                            TexSample s0, s1;
-                            if (o0 >= 0) tex_issue(s0, a.pn_tex, a.ashift, a.amask, lds1(stP + o0), lds1(stP + o0 + ARR_BYTES), lds1(stP + o0 + 2 * ARR_BYTES), dg);
-                            if (o1 >= 0) tex_issue(s1, a.pn_tex, a.ashift, a.amask, lds1(stP + o1), lds1(stP + o1 + ARR_BYTES), lds1(stP + o1 + 2 * ARR_BYTES), dg);
-                            if (o0 >= 0) pa::sts1(wcur + o0, tex_finish(s0));
-                            if (o1 >= 0) pa::sts1(wcur + o1, tex_finish(s1));
-                        } else {
-                            if (o0 >= 0) pa::sts1(wcur + o0, warp_sample(pn, lds1(stP + o0), lds1(stP + o0 + ARR_BYTES), lds1(stP + o0 + 2 * ARR_BYTES), dg, X, XY));
-                            if (o1 >= 0) pa::sts1(wcur + o1, warp_sample(pn, lds1(stP + o1), lds1(stP + o1 + ARR_BYTES), lds1(stP + o1 + 2 * ARR_BYTES), dg, X, XY));
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(wfull0 + 8 * wb);        // this warp's share of w(p) is written (release)
-                    mbar_arrive(empty0 + 8 * slot);      // ... and it no longer reads psi(p)
-                }
-                ++q;
-            }
+            asm volatile("fence.proxy.async;" ::: "memory");
+            halo_seen |= pr.face;
         }
-        return;
+        const unsigned slot = qi % NSTAGE, dst = smem + slot * STAGE_BYTES, bar = full0 + 8 * slot;
+        mbar_expect_tx(bar, TX_BYTES);
+        tma_load_3d(dst, &m0, bar, pr.x0t - 4, pr.y0t - 1, pr.p + PSI_HALO);
+        tma_load_3d(dst + ARR_BYTES, &m1, bar, pr.x0t - 4, pr.y0t - 1, pr.p + PSI_HALO);
+        tma_load_3d(dst + 2 * ARR_BYTES, &m2, bar, pr.x0t - 4, pr.y0t - 1, pr.p + PSI_HALO);
+        if (pr.p + PF_AHEAD < pr.p_last) {
+            tma_prefetch_3d(&m0, pr.x0t - 4, pr.y0t - 1, pr.p + PF_AHEAD + PSI_HALO);
+            tma_prefetch_3d(&m1, pr.x0t - 4, pr.y0t - 1, pr.p + PF_AHEAD + PSI_HALO);
+            tma_prefetch_3d(&m2, pr.x0t - 4, pr.y0t - 1, pr.p + PF_AHEAD + PSI_HALO);
+        }
+        ++qi;
+        pr.next(sc, d.Z);
+    };
+    if (tid == 0) {
+        pr.open(blockIdx.x, sc, d.Z);
+        for (int k = 0; k < AHEAD; ++k) feed();
     }
 
-    // ---------------------------------------------------------------------------------------------------- stencil
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PAW_REG_STENCIL));
     const int lx = lane % LX, ty = warp * RW + lane / LX;
     const unsigned own_off = (unsigned)(((ty + 1) * SX + 4 * lx + 4) * 4);
-    float *__restrict__ G[3] = {a.gx, a.gy, a.gz};
-    const GLayout gl = a.gl;
+    int hx = -1, hy = -1;         // cross-halo cell served by this thread (threads 0 .. NHALO-1), as in pa
+    if (tid < TX) { hx = 4 + tid; hy = 0; }
+    else if (tid < 2 * TX) { hx = 4 + tid - TX; hy = TY + 1; }
+    else if (tid < 2 * TX + TY) { hx = 3; hy = 1 + tid - 2 * TX; }
+    else if (tid < NHALO) { hx = 4 + TX; hy = 1 + tid - 2 * TX - TY; }
+    const unsigned halo_off = (unsigned)((hy * SX + hx) * 4);
     unsigned q = 0;
     St cs;
     for (cs.open(blockIdx.x, sc, d.Z); cs.valid(sc); cs.open(cs.item + (int)gridDim.x, sc, d.Z)) {
-        const int x0 = cs.x0t + 4 * lx, y = cs.y0t + ty;
-        const bool active = x0 < X && y < d.Y;
-        const int row = min(x0, X - 4) + X * min(y, d.Y - 1);
-        const bool y_lo = (y == 0), y_hi = (y == d.Y - 1), by = y_lo || y_hi;
-        const bool x_lo = (x0 == 0), x_hi = (x0 + 4 == X);
+        Quad qd;
+        qd.x0 = cs.x0t + 4 * lx; qd.y = cs.y0t + ty;
+        qd.active = qd.x0 < X && qd.y < d.Y;
+        const int row = min(qd.x0, X - 4) + X * min(qd.y, d.Y - 1);
+        qd.y_lo = (qd.y == 0); qd.y_hi = (qd.y == d.Y - 1);
+        qd.x_lo = (qd.x0 == 0); qd.x_hi = (qd.x0 + 4 == X);
+        const int hgx = cs.x0t - 4 + hx, hgy = cs.y0t - 1 + hy;
+        const bool halo_on = hx >= 0 && hgx >= 0 && hgx < X && hgy >= 0 && hgy < d.Y;
+        float4 wm = make_float4(0.f, 0.f, 0.f, 0.f), wc = wm;        // the quad of w at planes p-3 and p-2
+        float4 lo[4], hi[4], hlo, hhi;                                // gathers in flight: the quad and the halo cell at plane p-1
+        bool pend = false;                                            // ... if that plane lies inside the volume
+#pragma unroll
+        for (int j = 0; j < 4; ++j) lo[j] = hi[j] = wm;
+        hlo = hhi = wm;
         for (int p = cs.p; p <= cs.p_last; ++p) {
-            const unsigned slot = q % NSTAGE, wb = q % NWB;
-            const int zc = p - 1;
+            const unsigned slot = q % NSTAGE;
+            const int zc = p - 2;             // centre: its z+1 neighbour w(p-1) is completed in this step
             const bool centre_on = zc >= cs.zb;
             float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (centre_on) g4 = *reinterpret_cast<const float4 *>(a.pg + row + XY * zc);
             mbar_wait(full0 + 8 * slot, (q / NSTAGE) & 1u);
-            mbar_wait(wfull0 + 8 * wb, (q / NWB) & 1u);
-            ++q;                                  // q-1: plane p, q-2: plane p-1 (centre), q-3: plane p-2
+            ++q;
+            const unsigned stP = smem + slot * STAGE_BYTES;                                       // plane p
+            const unsigned sP1 = smem + ((q + NSTAGE - 2u) % NSTAGE) * STAGE_BYTES;               // plane p-1
+            const unsigned sC = smem + ((q + NSTAGE - 3u) % NSTAGE) * STAGE_BYTES + own_off;      // plane p-2 (centre)
+            const unsigned sM = smem + ((q + 2u * NSTAGE - 4u) % NSTAGE) * STAGE_BYTES + own_off; // plane p-3
+            const unsigned wnew = wbuf0 + ((q + 1u) % 3u) * ARR_BYTES;                            // warped plane p-1 (completed now)
+            const unsigned wctr = wbuf0 + (q % 3u) * ARR_BYTES;                                   // warped plane p-2 (completed in the last step)
+
+            // ---- 1. the gathers of plane p-1 have had a whole step to arrive: interpolate (weights recomputed from psi(p-1)) ----
+            float4 z1[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) z1[k] = lds4(sP1 + own_off + k * ARR_BYTES);
+            float4 wp = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pend) {
+                if (qd.active) {
+                    float w4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        TexSample s;
+                        s.lo = lo[j]; s.hi = hi[j];
+                        tex_weights(s, c4(z1[0], j), c4(z1[1], j), c4(z1[2], j), dg);
+                        w4[j] = tex_finish(s);
+                    }
+                    wp = make_float4(w4[0], w4[1], w4[2], w4[3]);
+                }
+                if (halo_on) {
+                    TexSample s;
+                    s.lo = hlo; s.hi = hhi;
+                    tex_weights(s, lds1(sP1 + halo_off), lds1(sP1 + halo_off + ARR_BYTES), lds1(sP1 + halo_off + 2 * ARR_BYTES), dg);
+                    sts1(wnew + halo_off, tex_finish(s));
+                }
+                sts4(wnew + own_off, wp);
+            }
+            // ---- 2. issue the gathers of plane p (consumed in the next step) ----
+            pend = (a.z0 + p >= 0 && a.z0 + p < dg.Z) && p < cs.p_last;
+            if (pend) {
+                if (qd.active) {
+                    float4 zp[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) zp[k] = lds4(stP + own_off + k * ARR_BYTES);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) tex_fetch(lo[j], hi[j], a.pn_tex, a.ashift, a.amask, c4(zp[0], j), c4(zp[1], j), c4(zp[2], j), dg);
+                }
+                if (halo_on)
+                    tex_fetch(hlo, hhi, a.pn_tex, a.ashift, a.amask, lds1(stP + halo_off), lds1(stP + halo_off + ARR_BYTES), lds1(stP + halo_off + 2 * ARR_BYTES), dg);
+            }
+            // ---- 3. nabla_U of the centre plane p-2 ----
             if (centre_on) {
-                const unsigned stP = smem + slot * STAGE_BYTES + own_off;
-                const unsigned sC = smem + ((q + NSTAGE - 2u) % NSTAGE) * STAGE_BYTES + own_off;
-                const unsigned sM = smem + ((q + NSTAGE - 3u) % NSTAGE) * STAGE_BYTES + own_off;
-                const unsigned wP = wbuf0 + wb * ARR_BYTES + own_off;
-                const unsigned wC = wbuf0 + ((q + NWB - 2u) % NWB) * ARR_BYTES + own_off;
-                const unsigned wM = wbuf0 + ((q + NWB - 3u) % NWB) * ARR_BYTES + own_off;
-                const bool z_lo = (a.z0 + zc == 0), z_hi = (a.z0 + zc == dg.Z - 1), bz = z_lo || z_hi;   // global faces only
-                const bool edge = by || bz;
-                // ---- w_reg * laplacian(psi) at the centre plane (vector_fields.cu:291-337) ----
+                const bool z_lo = (a.z0 + zc == 0), z_hi = (a.z0 + zc == dg.Z - 1);   // global faces only
                 float Lw[3][4];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const unsigned p0 = sC + c * ARR_BYTES;
-                    const float4 C = lds4(p0);
-                    float4 Ym = lds4(p0 - SX * 4), Yp = lds4(p0 + SX * 4), Zp = lds4(stP + c * ARR_BYTES), Zm = lds4(sM + c * ARR_BYTES);
-                    const float xl = lds1(p0 - 4), xr = lds1(p0 + 16);
-                    const float xm[4] = {x_lo ? C.x : xl, C.x, C.y, x_hi ? C.w : C.z}, xp[4] = {x_lo ? C.x : C.y, C.z, C.w, x_hi ? C.w : xr};
-                    if (edge) {
-                        if (by) Yp = Ym = C;
-                        if (bz) Zp = Zm = C;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float v = mul(c4(C, j), -6.f);
-                        v = add(v, xp[j]);
-                        v = add(v, xm[j]);
-                        v = add(v, c4(Yp, j));
-                        v = add(v, c4(Ym, j));
-                        v = add(v, c4(Zp, j));
-                        v = add(v, c4(Zm, j));
-                        Lw[c][j] = mul(mul(v, -1.f), a.w_reg);
-                    }
-                }
-                // ---- central differences of the warped TSDF (vector_fields.cu:157-208) and nabla_U (solver.cu:15-33) ----
-                float nx[4], ny[4], nz[4], df[4];
-                {
-                    const float4 C = lds4(wC), Ym = lds4(wC - SX * 4), Yp = lds4(wC + SX * 4), wp = lds4(wP), wm = lds4(wM);
-                    const float xl = lds1(wC - 4), xr = lds1(wC + 16);
-                    const float xm[4] = {x_lo ? C.y : xl, C.x, C.y, C.z}, xp[4] = {C.y, C.z, C.w, x_hi ? C.z : xr};
-                    float4 Y1 = Yp, Y2 = Ym, Z1 = wp, Z2 = wm;
-                    if (edge) {
-                        if (y_hi) Y1 = Ym;
-                        if (y_lo) Y2 = Yp;
-                        if (z_hi) Z1 = wm;
-                        if (z_lo) Z2 = wp;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        nx[j] = mul(sub(xp[j], xm[j]), 0.5f);
-                        ny[j] = mul(sub(c4(Y1, j), c4(Y2, j)), 0.5f);
-                        nz[j] = mul(sub(c4(Z1, j), c4(Z2, j)), 0.5f);
-                        df[j] = sub(c4(C, j), c4(g4, j));
-                    }
-                }
-                const size_t o = gl.at(min(x0, X - 4), min(y, d.Y - 1), zc);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    float u[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float n = (c == 0) ? nx[j] : (c == 1 ? ny[j] : nz[j]);
-                        u[j] = add(mul(n, df[j]), Lw[c][j]);
-                    }
-                    if (active) {
-                        float *__restrict__ g = G[c];
-                        const float4 uv = make_float4(u[0], u[1], u[2], u[3]);
-                        *reinterpret_cast<float4 *>(g + o) = uv;
-                        if (x0 == 0) *reinterpret_cast<float4 *>(g + o - 4) = make_float4(u[0], u[0], u[0], u[0]);
-                        if (x0 + 4 == X) *reinterpret_cast<float4 *>(g + o + 4) = make_float4(u[3], u[3], u[3], u[3]);
-                        if (y_lo) {
-#pragma unroll
-                            for (int k = 1; k <= 3; ++k) *reinterpret_cast<float4 *>(g + o - (size_t)k * gl.PX) = uv;
-                        }
-                        if (y_hi) {
-#pragma unroll
-                            for (int k = 1; k <= 3; ++k) *reinterpret_cast<float4 *>(g + o + (size_t)k * gl.PX) = uv;
-                        }
-                        if (z_lo) {
-#pragma unroll
-                            for (int k = 1; k <= 3; ++k) *reinterpret_cast<float4 *>(g + o - (size_t)k * gl.plane) = uv;
-                        }
-                        if (z_hi) {
-#pragma unroll
-                            for (int k = 1; k <= 3; ++k) *reinterpret_cast<float4 *>(g + o + (size_t)k * gl.plane) = uv;
-                        }
-                    }
-                }
+                laplacian_quad<SX, ARR_BYTES>(Lw, qd, z_lo || z_hi, sC, sM, z1, a.w_reg);
+                gradient_store_quad<SX>(a, qd, zc, z_lo, z_hi, wctr + own_off, wm, wc, wp, g4, Lw);
             }
-            // plane p-2 (position q-3) is no longer needed by this warp
-            __syncwarp();
-            if (lane == 0 && q >= 3u) {
-                mbar_arrive(empty0 + 8 * ((q - 3u) % NSTAGE));
-                mbar_arrive(wempty0 + 8 * ((q - 3u) % NWB));
-            }
+            __syncthreads();                  // warped plane p-1 visible to the CTA; ring stage of plane p-3 is free
+            if (tid == 0) feed();
+            wm = wc; wc = wp;
+        }
+        if (PEER && a.wait_halo && cs.face != 0 && tid == 0) {
+            if (cs.face == 1 && a.ack_lo) atomicAdd_system(a.ack_lo, 1ull);
+            if (cs.face == 2 && a.ack_hi) atomicAdd_system(a.ack_hi, 1ull);
         }
     }
+    if (PEER && tid == 0) trace_end(a.trace);
 }
-}  // namespace paw
+}  // namespace pa2
 
 int sm_count() {
     static int sms = 0;
@@ -1104,6 +1040,8 @@ TmaMaps *tma_maps_create(const LoopArgs &a) {
     ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(pa::pass_a_tma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa::SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(pa2::pass_a_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa2::SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(pa2::pass_a_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pa2::SMEM_BYTES) == cudaSuccess;
     if (!ok) {
         fprintf(stderr, "sobfu_b200: TMA tensor maps unavailable; using the generic kernels\n");
         cudaGetLastError();
@@ -1125,7 +1063,7 @@ LaunchInfo launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, const 
     return launch_info(sc, grid);
 }
 
-// experimental kernels are selected per solver (sobfu_b200_solver_set_variant) through this per-thread switch, set by the host
+// alternative pass A kernels are selected per solver (sobfu_b200_solver_set_variant) through this per-thread switch, set by the host
 // loop before it launches; 0 = the default kernels
 static thread_local int g_pass_a_variant = 0;
 void set_pass_a_variant(int v) { g_pass_a_variant = v; }
@@ -1133,24 +1071,18 @@ void set_pass_a_variant(int v) { g_pass_a_variant = v; }
 LaunchInfo launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, const ZRanges &zr, cudaStream_t st) {
     if (log) {   // logging iterations (rare): materialise the warped plane, then the generic kernel that also sums the energies
         launch_initial_warp(a, st);
-        launch_pass_a_generic(a, it, 1, st);
+        launch_pass_a_generic(a, it, log, st);
         return LaunchInfo{0, {0, 0, 0}};
     }
     const bool peer = a.peer_n > 0 && a.wait_halo;
-    if (g_pass_a_variant == 3 && !peer) {      // warp-specialised sampling (experimental); the default path never touches this kernel
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(paw::pass_a_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, paw::SMEM_BYTES);
-            cudaFuncSetAttribute(paw::pass_a_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, paw::SMEM_BYTES);
-            attr_set = true;
-        }
-        const int wctas = PAW_CTAS * sm_count();
-        const Sched wsc = cached_sched(a.d, zr, paw::TX, paw::TY, 2, 0.5, wctas);
-        if (wsc.nitems == 0) return LaunchInfo{0, {0, 0, 0}};
-        const int wgrid = wsc.nitems < wctas ? wsc.nitems : wctas;
-        if (a.pn_tex) paw::pass_a_ws_kernel<true><<<wgrid, paw::NTHREADS, paw::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, wsc);
-        else paw::pass_a_ws_kernel<false><<<wgrid, paw::NTHREADS, paw::SMEM_BYTES, st>>>(m->in[0], m->in[1], m->in[2], a, it, wsc);
-        return launch_info(wsc, wgrid);
+    if (g_pass_a_variant == 4 && a.pn_tex) {      // software-pipelined gathers (one more pipeline-fill step per item: 3 halo steps)
+        const int pctas = PA2_CTAS * sm_count();
+        const Sched psc = cached_sched(a.d, zr, pa2::TX, pa2::TY, 3, 0.6, pctas);
+        if (psc.nitems == 0) return LaunchInfo{0, {0, 0, 0}};
+        const int pgrid = psc.nitems < pctas ? psc.nitems : pctas;
+        if (peer) launch_pdl(pa2::pass_a_pipe_kernel<true>, pgrid, pa2::NTHREADS, pa2::SMEM_BYTES, st, m->in[0], m->in[1], m->in[2], a, it, psc);
+        else launch_pdl(pa2::pass_a_pipe_kernel<false>, pgrid, pa2::NTHREADS, pa2::SMEM_BYTES, st, m->in[0], m->in[1], m->in[2], a, it, psc);
+        return launch_info(psc, pgrid);
     }
     const int ctas = PA_CTAS * sm_count();
     const Sched sc = cached_sched(a.d, zr, pa::TX, pa::TY, 2, 0.5, ctas);

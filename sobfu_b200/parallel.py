@@ -8,8 +8,8 @@ inside libsobfu_b200.so over its own NCCL communicator; torch.distributed only c
 import ctypes as C
 
 from . import _capi
-from ._capi import check, lib
-from .api import Solver
+from ._capi import check
+from .api import Solver, lib
 
 
 def slab_range(Z, rank, nranks):

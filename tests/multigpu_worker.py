@@ -20,7 +20,9 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl")
     rank, world = dist.get_rank(), dist.get_world_size()
-    cases = [((64, 64, 64), 12, 0.0, 0, -1.0), ((96, 40, 32), 7, 0.4, 2, -1.0), ((20, 18, 16), 5, 0.3, 1, -1.0), ((64, 32, 32), 60, 0.0, 0, None)]
+    # the fifth case displaces psi by up to 24 planes along z: psi^-1 leaves the 16-plane neighbour window and the all-gather fallback runs
+    cases = [((64, 64, 64), 12, 0.0, 0, -1.0), ((96, 40, 32), 7, 0.4, 2, -1.0), ((20, 18, 16), 5, 0.3, 1, -1.0), ((64, 32, 32), 60, 0.0, 0, None),
+             ((64, 32, 64), 4, 24.0, 0, -1.0)]
     for dims, iters, wavy, verbosity, thr in cases:
         X, Y, Z = dims
         pg, pn, vs, trunc, eta = sphere_pair(dims, r=0.07)
@@ -40,6 +42,7 @@ def main():
         assert slab["info"].max_norm == full["info"].max_norm and slab["info"].max_idx == full["info"].max_idx
         for k in ("psi", "psi_inv", "phi_n_psi", "phi_global_psi_inv"):
             assert_bits(slab[k], full[k][z0:z0 + nz], "%s rank %d %s" % (dims, rank, k))
+        assert (slab["tail_fallbacks"] > 0) == (wavy > 16.0), (dims, wavy, slab["tail_fallbacks"])
         for a, b in zip(slab["log"], full["log"]):
             assert a[0] == b[0] and a[1] == b[1]
             assert abs(a[2] - b[2]) <= 2e-5 * abs(b[2]) + 1e-6 and abs(a[3] - b[3]) <= 2e-5 * abs(b[3]) + 1e-6
@@ -97,7 +100,8 @@ def solve(p, dims, pg, pn, psi0, dist_or_none):
     _capi.check(_capi.lib().sobfu_b200_solver_estimate_psi(solver._h, ptr(d_pg), ptr(d_pgpi), ptr(d_pn), ptr(d_pnp), ptr(d_psi), ptr(d_inv), C.byref(info)))
     solver.info = info
     return dict(info=info, log=solver.get_log(), psi=d_psi.cpu().numpy(), psi_inv=d_inv.cpu().numpy(), phi_n_psi=d_pnp.cpu().numpy(),
-                phi_global_psi_inv=d_pgpi.cpu().numpy(), z0=z0, nz=nz, peer=bool(getattr(solver, "peer", False)))
+                phi_global_psi_inv=d_pgpi.cpu().numpy(), z0=z0, nz=nz, peer=bool(getattr(solver, "peer", False)),
+                tail_fallbacks=solver.tail_fallbacks())
 
 
 if __name__ == "__main__":

@@ -209,16 +209,18 @@ def run_ini(tool, text, tmp_path):
 
 
 def test_ini_reader_follows_program_options(tool, tmp_path):
-    rc, kv, _ = run_ini(tool, INI, tmp_path)
+    rc, _, out = run_ini(tool, INI, tmp_path)                      # ALPHA is given twice: boost throws multiple_occurrences
+    assert rc == 3 and "ALPHA" in out and "more than once" in out
+    rc, kv, _ = run_ini(tool, INI.replace("ALPHA=0.9\n", ""), tmp_path)
     assert rc == 0
     assert kv["VOL_DIMS"] == "96 80 64" and kv["VOL_SIZE"].split() == ["0.899999976", "0.75", "0.600000024"]
     assert kv["TSDF_TRUNC_DIST"] == "10" and kv["ETA"] == "5" and kv["VOL_POSE_T_Z"] == "0.0500000007"
     assert kv["INTR"].split() == ["517", "516.5", "320", "240"] and kv["BILATERAL"].split()[2] == "7"
     assert kv["MAX_ITER"] == "2048" and kv["MAX_UPDATE_NORM"] == "0.00100000005" and kv["S"] == "7"
-    assert kv["ALPHA"] == "0.100000001"                          # the first occurrence of an option wins
-    rc, _, out = run_ini(tool, INI + "RHO_0=1.0\n", tmp_path)      # an option the application does not declare is an error
+    assert kv["ALPHA"] == "0.100000001"
+    rc, _, out = run_ini(tool, INI.replace("ALPHA=0.9\n", "") + "RHO_0=1.0\n", tmp_path)      # an option the application does not declare is an error
     assert rc == 3 and "RHO_0" in out
-    rc, _, out = run_ini(tool, INI.replace("MAX_ITER=2048", "MAX_ITER=20.5"), tmp_path)
+    rc, _, out = run_ini(tool, INI.replace("ALPHA=0.9\n", "").replace("MAX_ITER=2048", "MAX_ITER=20.5"), tmp_path)
     assert rc == 3 and "MAX_ITER" in out                           # lexical_cast<int> rejects it
     rc, _, out = run_ini(tool, "VOL_DIMS_X 96\n", tmp_path)
     assert rc == 3

@@ -26,6 +26,6 @@ def test_slab_solve_matches_single_gpu(built, mode):
                         "--master-port", "29541" if mode == "peer" else "29543", os.path.join(ROOT, "tests", "multigpu_worker.py")],
                        capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
-    assert r.stdout.count("slab == single GPU, bit for bit") == 4
+    assert r.stdout.count("slab == single GPU, bit for bit") == 5
     assert r.stdout.count("slab meshes == single GPU, bit for bit") == 1
     assert ("peer mode: True" in r.stdout) == (mode == "peer"), r.stdout[-2000:]

@@ -107,3 +107,54 @@ def test_solver_with_a_computed_filter_matches_the_oracle(built):
     assert_bits(psi.get_data().cpu().numpy(), want["psi"], "computed filter: psi")
     assert_bits(psi_inv.get_data().cpu().numpy(), want["psi_inv"], "computed filter: psi_inv")
     assert_bits(vol[3].data().cpu().numpy(), want["phi_n_psi"], "computed filter: phi_n o psi")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("s,lam", [(3, 0.1), (9, 0.05), (9, 0.1), (11, 0.1)])
+def test_solver_with_the_other_tabulated_filter_lengths(built, s, lam):
+    """the reference tabulates 3-, 9- and 11-tap filters (solver.cpp:160-251) that its 7-tap kernels (KERNEL_RADIUS 3,
+    solver.cu:211) cannot run; here they run (radius (s - 1) / 2, same order of operations) and match the oracle's explicit-tap loop
+    bit for bit -- the whole estimate_psi and the stand-alone three-sweep filter."""
+    import torch
+    import sobfu_b200 as sf
+    from sobfu_b200 import _capi
+    from tests.common import assert_bits, random_field, sphere_pair, wavy_psi
+    dims = (40, 36, 28)
+    pg, pn, vs, trunc, eta = sphere_pair(dims, r=0.07)
+    psi0 = wavy_psi(dims, amp=0.4)
+    p = sf.Params(volume_dims=dims, volume_size=tuple(float(vs[i]) * dims[i] for i in range(3)), max_iter=6, max_update_norm=-1.0, s=s,
+                  lambda_=lam, alpha=0.05, w_reg=0.3, tsdf_max_weight=64.0, tsdf_trunc_dist=float(trunc), eta=float(eta))
+    solver = sf.Solver(p)
+    taps = solver.get_taps()
+    assert taps.shape == (s,) and np.array_equal(taps, orc.sobolev_taps(s, lam))
+    vol = [sf.TsdfVolume(p) for _ in range(4)]
+    vol[0].data().copy_(torch.from_numpy(pg))
+    vol[2].data().copy_(torch.from_numpy(pn))
+    psi, psi_inv = sf.DeformationField(dims), sf.DeformationField(dims)
+    psi.get_data().copy_(torch.from_numpy(psi0))
+    info = solver.estimate_psi(vol[0], vol[1], vol[2], vol[3], psi, psi_inv)
+    want = orc.estimate_psi(pg, pn, psi0, 6, -1.0, s, lam, 0.05, 0.3, taps=taps)
+    assert info.iters == want["iters"] and info.max_norm == want["max_norm"]
+    assert_bits(psi.get_data().cpu().numpy(), want["psi"], "s=%d: psi" % s)
+    assert_bits(psi_inv.get_data().cpu().numpy(), want["psi_inv"], "s=%d: psi_inv" % s)
+    assert_bits(vol[3].data().cpu().numpy(), want["phi_n_psi"], "s=%d: phi_n o psi" % s)
+    assert_bits(vol[1].data().cpu().numpy(), want["phi_global_psi_inv"], "s=%d: phi_global o psi_inv" % s)
+    # the stand-alone filter (sobfu_b200_sobolev_filter_s)
+    src = random_field(dims, seed=s)
+    d_src = torch.from_numpy(src).cuda()
+    d_dst = torch.empty_like(d_src)
+    t = (C.c_float * s)(*[float(v) for v in taps])
+    _capi.check(_capi.lib().sobfu_b200_sobolev_filter_s(C.c_void_p(d_dst.data_ptr()), C.c_void_p(d_src.data_ptr()), t, s, dims[0], dims[1], dims[2]))
+    assert_bits(d_dst.cpu().numpy(), orc.sobolev_filter(src, taps), "s=%d: three-sweep filter" % s)
+
+
+def test_filter_length_is_validated(built):
+    from sobfu_b200 import _capi
+    p = _capi.Params()
+    p.dims[:] = [16, 16, 16]
+    p.voxel_size[:] = [0.01, 0.01, 0.01]
+    p.max_iter, p.lambda_ = 1, 0.1
+    h = C.c_void_p()
+    for s in (5, 2, 13, 0):
+        p.s = s
+        assert _capi.lib().sobfu_b200_solver_create(C.byref(h), C.byref(p)) == -1       # SOBFU_B200_EINVAL, before any device call
