@@ -22,6 +22,9 @@ done
 for f in tsdf_volume.cu marching_cubes.cu; do
   nvcc $NVFLAGS -c "$TMP/$f" -o "$TMP/patched_$f.o" & pids+=($!)
 done
+# second oracle for marching cubes only: the same translation unit + the __syncwarp its compaction lacks (patch_textures.py)
+mkdir -p "$TMP/alt"
+nvcc $NVFLAGS -c "$TMP/marching_cubes_syncwarp.cu" -o "$TMP/alt/patched_marching_cubes.cu.o" & pids+=($!)
 for f in src/sobfu/solver.cpp src/sobfu/reductor.cpp src/sobfu/vector_fields.cpp src/sobfu/scalar_fields.cpp \
          src/sobfu/precomp.cpp src/kfusion/device_memory.cpp src/kfusion/tsdf_volume.cpp src/kfusion/precomp.cpp \
          src/kfusion/marching_cubes.cpp src/kfusion/imgproc.cpp src/kfusion/core.cpp; do
@@ -31,3 +34,7 @@ g++ $CXXFLAGS -c "$HERE/ref_harness.cpp" -o "$TMP/ref_harness.o" & pids+=($!)
 for p in "${pids[@]}"; do wait $p; done
 nvcc -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT/libsobfu_ref.so" "$TMP"/*.o -lcudart -L/usr/local/cuda/lib64/stubs -lcuda
 echo "build_ref: wrote $OUT/libsobfu_ref.so"
+objs=()
+for o in "$TMP"/*.o; do [ "$(basename "$o")" = "patched_marching_cubes.cu.o" ] || objs+=("$o"); done
+nvcc -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT/libsobfu_ref_mcsync.so" "${objs[@]}" "$TMP/alt/patched_marching_cubes.cu.o" -lcudart -L/usr/local/cuda/lib64/stubs -lcuda
+echo "build_ref: wrote $OUT/libsobfu_ref_mcsync.so (marching cubes with the missing __syncwarp; test oracle only)"

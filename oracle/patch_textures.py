@@ -41,6 +41,14 @@ def patch_mc(src):
     return s
 
 
+def patch_mc_syncwarp(patched):
+    """second oracle for marching cubes: the compaction of OccupiedVoxels (marching_cubes.cu:107-120) lets lanes 1..31 read
+    warps_buffer[warp_id] right after lane 0 wrote it, with no __syncwarp in between; under independent thread scheduling
+    (sm_70+) lanes can read a stale offset and voxels are dropped or overwritten.  This variant adds the missing barrier and
+    nothing else, so that the COMPLETE list of the reference's algorithm can be compared."""
+    return sub(patched, r'(warps_buffer\[warp_id\] = old;\n\s*\})\n', r'\1\n        __syncwarp();\n', 1)
+
+
 if __name__ == '__main__':
     ref, out = sys.argv[1], sys.argv[2]
     for name, fn in (('tsdf_volume.cu', patch_tsdf), ('marching_cubes.cu', patch_mc)):
@@ -48,3 +56,6 @@ if __name__ == '__main__':
             txt = f.read()
         with open(f'{out}/{name}', 'w') as f:
             f.write(fn(txt))
+        if name == 'marching_cubes.cu':
+            with open(f'{out}/marching_cubes_syncwarp.cu', 'w') as f:
+                f.write(patch_mc_syncwarp(fn(txt)))

@@ -10,6 +10,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_build", "liboracle.so")
 REF = os.path.join(HERE, "_ref", "libsobfu_ref.so")
+REF_MCSYNC = os.path.join(HERE, "_ref", "libsobfu_ref_mcsync.so")   # + the __syncwarp the reference's MC compaction lacks
 
 _P, _I, _F = C.c_void_p, C.c_int, C.c_float
 _FP = C.POINTER(C.c_float)
@@ -255,13 +256,15 @@ def compute_dists(depth, fx, fy, cx, cy):
 
 # ---- the reference's own CUDA (GPU box only) -------------------------------------------------------------------
 class Reference:
-    """Handle on oracle/_ref/libsobfu_ref.so: the unmodified reference driven through its public host API."""
+    """Handle on oracle/_ref/libsobfu_ref.so: the unmodified reference driven through its public host API.
+    lib=REF_MCSYNC: the build whose marching-cubes compaction has the __syncwarp the reference lacks (oracle/patch_textures.py)."""
 
     def __init__(self, dims, size, trunc, eta, max_weight, verbosity, max_iter, s, max_update_norm, lam, alpha, w_reg,
-                 pose_t=(0, 0, 0), intr=(1, 1, 0, 0)):
-        if not os.path.exists(REF):
-            raise FileNotFoundError(REF)
-        L = C.CDLL(REF)
+                 pose_t=(0, 0, 0), intr=(1, 1, 0, 0), lib=None):
+        lib = lib or REF
+        if not os.path.exists(lib):
+            raise FileNotFoundError(lib)
+        L = C.CDLL(lib)
         L.ref_create.restype = C.c_void_p
         L.ref_create.argtypes = [_I] * 3 + [_F] * 6 + [_I] * 3 + [_F] * 4 + [_F] * 3 + [_F] * 4
         L.ref_estimate_psi.restype = C.c_float

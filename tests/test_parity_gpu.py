@@ -303,6 +303,50 @@ def test_full_size_properties_at_256(env):
     assert_bits(d["phi_n_psi"][..., 0], pg[..., 0], "fixed point: phi_n o psi")
 
 
+def test_full_size_properties_at_512(env):
+    """BASELINE.json configs[3] size (512^3: voxel indices above 2^24 -- not exact as floats, reductor.cu:367 --, an 8192 x 16384
+    gather atlas, 2^27 voxels): the tiled kernels (default pass A and the pipelined one) against the one-thread-per-voxel
+    kernels, bit for bit on every output incl. the logged maxima and their voxel indices; inputs made on the device through
+    the library's own (reference-bit-exact) initialisers."""
+    sf, orc, torch = env
+    dims = (512, 512, 512)
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~60 GB of device memory")
+    vs = f32(0.5) / f32(512)
+    p = sf.Params(volume_dims=dims, volume_size=(0.5, 0.5, 0.5), max_iter=4, max_update_norm=-1.0, s=7, lambda_=0.1, alpha=0.05, w_reg=0.4,
+                  verbosity=0, tsdf_max_weight=64.0, tsdf_trunc_dist=float(f32(8) * vs), eta=float(f32(3) * vs))
+    vol = [sf.TsdfVolume(p) for _ in range(4)]
+    vol[0].initSphere((0.25, 0.25, 0.25), 0.16)
+    vol[2].initSphere((0.247, 0.251, 0.25), 0.16)
+    z, y, x = torch.meshgrid(torch.arange(512, device="cuda", dtype=torch.float32), torch.arange(512, device="cuda", dtype=torch.float32),
+                             torch.arange(512, device="cuda", dtype=torch.float32), indexing="ij")
+    psi0 = sf.DeformationField(dims)
+    psi0.get_data()[..., 0] += 0.45 * torch.sin(0.037 * y + 0.3) * torch.cos(0.023 * z + 1.1)
+    psi0.get_data()[..., 1] += 0.45 * torch.sin(0.029 * z + 2.0) * torch.cos(0.031 * x + 0.7)
+    psi0.get_data()[..., 2] += 0.45 * torch.sin(0.041 * x + 4.0) * torch.cos(0.019 * y + 5.2)
+    del x, y, z
+    out = {}
+    for variant in (2, 1, 4):
+        solver = sf.Solver(p)
+        solver.set_variant(variant)
+        psi, psi_inv = sf.DeformationField(dims), sf.DeformationField(dims)
+        psi.get_data().copy_(psi0.get_data())
+        info = solver.estimate_psi(vol[0], vol[1], vol[2], vol[3], psi, psi_inv)
+        got = dict(psi=psi.get_data(), psi_inv=psi_inv.get_data(), phi_n_psi=vol[3].data().clone(), phi_global_psi_inv=vol[1].data().clone(),
+                   log=[r[:2] for r in solver.get_log()], iters=info.iters, max_idx=info.max_idx)
+        del solver
+        if variant == 2:
+            out = got
+            assert info.iters == 4 and info.max_norm > 0 and all(r[0] > 0 for r in got["log"])
+            continue
+        for k in ("psi", "psi_inv", "phi_n_psi", "phi_global_psi_inv"):
+            assert torch.equal(out[k].view(torch.int32), got[k].view(torch.int32)), "512^3 variant %d vs tiled: %s" % (variant, k)
+        assert got["log"] == out["log"] and got["iters"] == out["iters"] and got["max_idx"] == out["max_idx"]
+        del got, psi, psi_inv
+        torch.cuda.empty_cache()
+
+
 @pytest.mark.timeout(90, method="thread")      # a pipeline bug would hang in cudaStreamSynchronize: kill the process, do not wait
 @pytest.mark.parametrize("dims,iters", [((64, 64, 64), 9), ((96, 40, 36), 6), ((128, 24, 16), 5), ((32, 8, 8), 4), ((256, 256, 40), 3)])
 def test_tiled_pass_a_with_pipelined_gathers(env, dims, iters):
