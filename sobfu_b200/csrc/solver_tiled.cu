@@ -72,7 +72,25 @@ struct Sched {
     int tiles_x, tiles_y, nitems;
     int nr;
     int zlo[3], zhi[3], nz[3], zchunk[3], face[3];
+    // balanced form (pass B, one range without face tag): the (tile, plane) space in tile-major order is cut into `grid` contiguous
+    // runs of seg_len planes; CTA b's k-th work item (item = b + k * grid) is the part of its run inside tile (first tile + k).
+    // Static round robin over (tile, chunk) items leaves the busiest CTA ~10 % above the mean at one CTA per SM; a run is one or
+    // two long segments instead of three chunks with a pipeline prologue each.
+    int balanced, grid, seg_len;
 };
+// Cuts are proportional in a space where every tile column is HALO_V planes longer than it is (the pipeline prologue a CTA pays when
+// it enters a column): CTAs whose run crosses a column boundary get that many planes less, so the modelled cost -- not the plane
+// count -- is even.  A cut closer than MIN_SEG planes to a column boundary snaps onto it (no sliver segments with 6 halo loads).
+constexpr int MIN_SEG = 3, HALO_V = 3;
+__host__ __device__ __forceinline__ int balanced_cut(const Sched &sc, int b, int Z, int L) {
+    if (b >= sc.grid) return L;
+    const int Zv = Z + HALO_V, ncol = L / Z;
+    const long v = (long)b * ((long)ncol * Zv) / sc.grid;
+    int t = (int)(v / Zv), o = (int)(v % Zv) - HALO_V;
+    if (o < MIN_SEG) o = 0;
+    else if (Z - o < MIN_SEG) { o = 0; ++t; }
+    return t * Z + o;
+}
 
 SB_DEVI float c4(const float4 &v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
 
@@ -139,6 +157,20 @@ SB_DEVI float warp_sample_tex(cudaTextureObject_t tex, int ashift, int amask, fl
 // schedule checks of the CPU tests (sobfu_b200_debug_schedule).
 __host__ __device__ __forceinline__ void locate_item(const Sched &sc, int item, int TX, int TY, int &x0t, int &y0t, int &zb, int &ze, int &face) {
     const int xy = sc.tiles_x * sc.tiles_y;
+    if (sc.balanced) {
+        const int Z = sc.zhi[0] - sc.zlo[0], L = xy * Z;
+        const int b = item % sc.grid, k = item / sc.grid;
+        const int lin0 = balanced_cut(sc, b, Z, L), lin1 = balanced_cut(sc, b + 1, Z, L);
+        const int t = lin0 / Z + k;
+        const int a = lin0 > t * Z ? lin0 : t * Z, e = lin1 < (t + 1) * Z ? lin1 : (t + 1) * Z;
+        const int tyi = t / sc.tiles_x;
+        x0t = (t - tyi * sc.tiles_x) * TX;
+        y0t = tyi * TY;
+        zb = sc.zlo[0] + (a - t * Z);
+        ze = e > a ? sc.zlo[0] + (e - t * Z) : zb;      // empty: past the end of this CTA's run
+        face = 0;
+        return;
+    }
     int tz = item / xy;
     const int rem = item - tz * xy;
     const int tyi = rem / sc.tiles_x;
@@ -163,6 +195,7 @@ struct Stream {
         if (item >= sc.nitems) return;
         locate_item(sc, item, TX, TY, x0t, y0t, zb, ze, face);
         (void)Z;
+        if (ze <= zb) { item = sc.nitems; return; }     // balanced form: the CTA's run has ended
         p = zb - LO;
         p_last = ze - 1 + HI;
     }
@@ -180,7 +213,13 @@ constexpr int LX = 16, RW = 32 / LX, NW = 12;     // 16 lanes x 4 voxels per row
 constexpr int TX = 4 * LX, TY = NW * RW;          // 64 x 24 outputs per plane
 constexpr int SX = TX + 8, SY = TY + 6;           // staged box 4|64|4 floats x 3|24|3 rows
 constexpr int NSTAGE = 6;                         // planes q-3..q live, two in flight
-constexpr int PF_AHEAD = 4;                       // L2 prefetch distance (planes) ahead of the shared-memory fill
+#ifndef PB_PF_AHEAD
+#define PB_PF_AHEAD 4
+#endif
+#ifndef PB_BACKOFF_NS
+#define PB_BACKOFF_NS 128
+#endif
+constexpr int PF_AHEAD = PB_PF_AHEAD;             // L2 prefetch distance (planes) ahead of the shared-memory fill
 constexpr int COMP_BYTES = ((SX * SY * 4 + 127) / 128) * 128;
 constexpr int STAGE_BYTES = 3 * COMP_BYTES;
 constexpr int NPSI = 3;                           // psi ring: centre plane of this step + the next two
@@ -266,7 +305,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
             const unsigned slot = qi % NSTAGE, n = qi / NSTAGE;
             // every warp released the previous plane of this slot; polling with a 128 ns back-off leaves the issue slots of this
             // scheduler to its three consumer warps (-2 % kernel time)
-            if (n > 0) mbar_wait_backoff(empty0 + 8 * slot, (n - 1) & 1u, 128u);
+            if (n > 0) mbar_wait_backoff(empty0 + 8 * slot, (n - 1) & 1u, (unsigned)PB_BACKOFF_NS);
             const unsigned dst = smem + slot * STAGE_BYTES, bar = full0 + 8 * slot;
             // psi of the plane that becomes the centre with this nabla_U plane rides on the same barrier; its slot (qi % 3) was
             // last read in the step whose end released this nabla_U slot, so the wait above covers it too
@@ -914,14 +953,40 @@ int sm_count() {
 // c planes costs c + halo_planes * halo_cost plane-steps.  Ranges of fewer than 16 planes stay one chunk; for the others the
 // chunk count that minimises the busiest CTA's load -- given the items already placed before it -- is taken (chunks of >= 16
 // planes -- 8 for ranges under 64 planes or when 16-plane chunks cannot fill the CTAs -- so that the pipeline prologue stays a small share).
-Sched make_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_planes, double halo_cost, int ctas, double *worst_load = nullptr) {
+Sched make_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_planes, double halo_cost, int ctas, double *worst_load = nullptr,
+                 bool balanced_ok = false) {
     Sched s;
     s.tiles_x = (d.X + TX - 1) / TX;
     s.tiles_y = (d.Y + TY - 1) / TY;
     const int xy = s.tiles_x * s.tiles_y;
     s.nr = zr.n;
     s.nitems = 0;
+    s.balanced = 0; s.grid = 0; s.seg_len = 0;
     for (int r = 0; r < 3; ++r) { s.zlo[r] = s.zhi[r] = 0; s.nz[r] = 0; s.zchunk[r] = 1; s.face[r] = 0; }
+    static const bool no_balanced = getenv("SOBFU_B200_NO_BALANCED") != nullptr;
+    if (balanced_ok && !no_balanced && zr.n == 1 && zr.face[0] == 0 && zr.hi[0] - zr.lo[0] >= 8) {
+        const int Z = zr.hi[0] - zr.lo[0], L = xy * Z;
+        if (L >= 8 * ctas) {                          // at least 8 planes per CTA: otherwise the chunked form below
+            s.balanced = 1;
+            s.grid = ctas;
+            s.seg_len = (L + ctas - 1) / ctas;
+            s.zlo[0] = zr.lo[0]; s.zhi[0] = zr.hi[0];
+            s.nz[0] = 1; s.zchunk[0] = Z;
+            s.nitems = s.grid * (s.seg_len / Z + 2);  // upper bound on the segments of a run; the surplus items are empty
+            if (worst_load) {
+                double w = 0.0;
+                for (int b = 0; b < s.grid; ++b) {
+                    const int lin0 = balanced_cut(s, b, Z, L), lin1 = balanced_cut(s, b + 1, Z, L);
+                    if (lin1 <= lin0) continue;
+                    const int segs = (lin1 - 1) / Z - lin0 / Z + 1;
+                    const double c = (lin1 - lin0) + segs * (halo_planes * halo_cost + 1.0);
+                    w = c > w ? c : w;
+                }
+                *worst_load = w;
+            }
+            return s;
+        }
+    }
     std::vector<double> load(ctas, 0.0), trial(ctas);
     for (int r = 0; r < zr.n && r < MAX_ZRANGES; ++r) {
         const int Z = zr.hi[r] - zr.lo[r];
@@ -966,17 +1031,17 @@ Sched make_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_plane
 }
 
 // the schedule depends on the shape and the ranges only: computed once per distinct launch geometry (the solver thread only)
-Sched cached_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_planes, double halo_cost, int ctas) {
+Sched cached_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_planes, double halo_cost, int ctas, bool balanced_ok = false) {
     struct Key { int v[16]; };
     static std::vector<std::pair<Key, Sched>> cache;
     static std::mutex mu;
     std::lock_guard<std::mutex> lock(mu);
     Key k{};
-    k.v[0] = d.X; k.v[1] = d.Y; k.v[2] = d.Z; k.v[3] = TX; k.v[4] = TY; k.v[5] = ctas; k.v[6] = zr.n;
+    k.v[0] = d.X; k.v[1] = d.Y; k.v[2] = d.Z; k.v[3] = TX; k.v[4] = TY; k.v[5] = ctas; k.v[6] = zr.n + (balanced_ok ? 16 : 0);
     for (int r = 0; r < MAX_ZRANGES; ++r) { k.v[7 + 3 * r] = r < zr.n ? zr.lo[r] : 0; k.v[8 + 3 * r] = r < zr.n ? zr.hi[r] : 0; k.v[9 + 3 * r] = r < zr.n ? zr.face[r] : 0; }
     for (auto &e : cache)
         if (!memcmp(&e.first, &k, sizeof k)) return e.second;
-    const Sched sc = make_sched(d, zr, TX, TY, halo_planes, halo_cost, ctas);
+    const Sched sc = make_sched(d, zr, TX, TY, halo_planes, halo_cost, ctas, nullptr, balanced_ok);
     if (cache.size() > 64) cache.clear();
     cache.emplace_back(k, sc);
     return sc;
@@ -984,6 +1049,7 @@ Sched cached_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_pla
 
 LaunchInfo launch_info(const Sched &sc, int grid) {
     LaunchInfo li{grid, {0, 0, 0}};
+    if (sc.balanced) { li.face_items[0] = sc.nitems; return li; }
     for (int r = 0; r < 3; ++r)
         if (sc.face[r] >= 0 && sc.face[r] < 3) li.face_items[sc.face[r]] += sc.tiles_x * sc.tiles_y * sc.nz[r];
     return li;
@@ -1055,9 +1121,9 @@ void tma_maps_destroy(TmaMaps *m) { delete m; }
 
 LaunchInfo launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, const ZRanges &zr, cudaStream_t st) {
     const int ctas = sm_count();
-    const Sched sc = cached_sched(a.d, zr, pb::TX, pb::TY, 6, 0.35, ctas);
+    const Sched sc = cached_sched(a.d, zr, pb::TX, pb::TY, 6, 0.35, ctas, true);
     if (sc.nitems == 0) return LaunchInfo{0, {0, 0, 0}};
-    const int grid = sc.nitems < ctas ? sc.nitems : ctas;
+    const int grid = sc.balanced ? sc.grid : (sc.nitems < ctas ? sc.nitems : ctas);
     if (a.peer_n > 0) launch_pdl(pb::pass_b_tma_kernel<true>, grid, (pb::NW + 1) * 32, pb::SMEM_BYTES, st, m->g[0], m->g[1], m->g[2], m->pb_psi[0], m->pb_psi[1], m->pb_psi[2], a, it, sc);
     else launch_pdl(pb::pass_b_tma_kernel<false>, grid, (pb::NW + 1) * 32, pb::SMEM_BYTES, st, m->g[0], m->g[1], m->g[2], m->pb_psi[0], m->pb_psi[1], m->pb_psi[2], a, it, sc);
     return launch_info(sc, grid);
@@ -1120,15 +1186,20 @@ extern "C" int sobfu_b200_debug_schedule(int pass, int X, int Y, int Zlocal, int
     for (int r = 0; r < MAX_ZRANGES; ++r) { zr.lo[r] = r < nranges ? lo[r] : 0; zr.hi[r] = r < nranges ? hi[r] : 0; zr.face[r] = r < nranges ? face[r] : 0; }
     const int TX = pass ? pb::TX : pa::TX, TY = pass ? pb::TY : pa::TY;
     const int ctas = pass ? sms : PA_CTAS * sms;
-    const Sched sc = pass ? make_sched(Dims{X, Y, Zlocal}, zr, TX, TY, 6, 0.35, ctas) : make_sched(Dims{X, Y, Zlocal}, zr, TX, TY, 2, 0.5, ctas);
-    *n_items = sc.nitems;
-    *grid = sc.nitems < ctas ? sc.nitems : ctas;
-    for (int i = 0; i < sc.nitems && i < cap; ++i) {
+    const Sched sc = pass ? make_sched(Dims{X, Y, Zlocal}, zr, TX, TY, 6, 0.35, ctas, nullptr, true) : make_sched(Dims{X, Y, Zlocal}, zr, TX, TY, 2, 0.5, ctas);
+    *grid = sc.balanced ? sc.grid : (sc.nitems < ctas ? sc.nitems : ctas);
+    int n = 0;
+    for (int i = 0; i < sc.nitems; ++i) {
         int x0, y0, zb, ze, f;
         locate_item(sc, i, TX, TY, x0, y0, zb, ze, f);
-        int *o = items + 6 * i;
-        o[0] = *grid ? i % *grid : 0; o[1] = x0; o[2] = y0; o[3] = zb; o[4] = ze; o[5] = f;
+        if (ze <= zb) continue;                    // balanced form: surplus items past the end of a CTA's run
+        if (n < cap) {
+            int *o = items + 6 * n;
+            o[0] = *grid ? i % *grid : 0; o[1] = x0; o[2] = y0; o[3] = zb; o[4] = ze; o[5] = f;
+        }
+        ++n;
     }
+    *n_items = n;
     return 0;
 }
 

@@ -172,17 +172,22 @@ class SlabFusion:
         p = self.params
         slab = upper_halo_plane(self.dist, vol.data(), self.rank, self.nranks)
         verts, normals = self.mc.run_slab(slab, p.volume_dims, p.volume_size, self.z0, self.nz, vertex_cap)
-        counts = [None] * self.nranks
-        self.dist.all_gather_object(counts, int(verts.shape[0]))
-        offs, total = slab_offsets(counts)
+        offs, total = slab_offsets(self._all_counts(int(verts.shape[0]), verts.device))
         return verts, normals, offs[self.rank], total
+
+    def _all_counts(self, n, device):
+        """every rank's vertex count (a tensor all-gather on the ranks' device: no pickling on the per-frame path)"""
+        import torch
+        mine = torch.tensor([n], dtype=torch.int64, device=device)
+        allc = torch.empty((self.nranks,), dtype=torch.int64, device=device)
+        self.dist.all_gather_into_tensor(allc, mine)
+        return [int(c) for c in allc.tolist()]
 
     def gather_mesh(self, vol, dst=0, vertex_cap=None):
         """the whole mesh on rank `dst` (vertices, normals), None elsewhere -- for export"""
         import torch
         verts, normals, off, total = self.slab_mesh(vol, vertex_cap)
-        counts = [None] * self.nranks
-        self.dist.all_gather_object(counts, int(verts.shape[0]))
+        counts = self._all_counts(int(verts.shape[0]), verts.device)
         if self.rank == dst:
             V = torch.empty((total, 4), dtype=torch.float32, device=verts.device)
             Nn = torch.empty((total, 4), dtype=torch.float32, device=verts.device)

@@ -75,7 +75,6 @@ def test_command_line(built):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("SOBFU_B200_TEST_EXPERIMENTAL"), reason="written after this round's GPU budget was spent: opt-in until it has run on hardware")
 def test_python_driver_matches_the_cpp_application(built, tmp_path):
     from tests.test_app_gpu import APP, make_sequence
     root = str(tmp_path / "seq")

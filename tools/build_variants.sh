@@ -2,9 +2,7 @@
 # Builds alternative libsobfu_b200.so files with different compile-time tuning macros into sobfu_b200/_lib/var/lib_<NAME>.so
 # (git-ignored; they travel to the GPU box).  tools/run_variants.sh then benchmarks and parity-tests each of them in ONE gpurun
 # call through SOBFU_B200_LIB.  Usage: tools/build_variants.sh NAME "<nvcc -D flags>" [NAME "<flags>" ...]
-#   tools/build_variants.sh A "" B "-DPAW_CTAS=3 -DPAW_REG_STENCIL=104 -DPAW_REG_SAMPLER=32 -DPAW_NSAMP=8" C "-DPAW_NSAMP=12 -DPAW_CTAS=2 -DPAW_REG_STENCIL=136 -DPAW_REG_SAMPLER=40"
-# (register split rule of variant 3: 128 * STENCIL + 32 * NSAMP * SAMPLER <= threads * regs-at-launch, regs-at-launch =
-#  floor(65536 / (threads * PAW_CTAS) / 8) * 8)
+#   tools/build_variants.sh A "" B "-DPA2_AHEAD=2" C "-DPA2_CTAS=2"
 set -euo pipefail
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 CSRC="$ROOT/sobfu_b200/csrc"
