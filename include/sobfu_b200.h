@@ -94,7 +94,8 @@ int sobfu_b200_solver_get_taps(sobfu_b200_solver *s, float *taps);
 /* bytes of device scratch owned by the handle */
 size_t sobfu_b200_solver_workspace_bytes(sobfu_b200_solver *s);
 /* kernel variant: 0 = auto (fastest applicable), 1 = generic per-voxel kernels, 2 = TMA pipelines for both passes,
- * 4 = TMA pipelines, pass A with software-pipelined gathers (fetches of a plane consumed one step later) */
+ * 4 = TMA pipelines with the round-1 pass A (gather4 fetches consumed in the step that issues them; the default consumes them one
+ *     step later) */
 int sobfu_b200_solver_set_variant(sobfu_b200_solver *s, int variant);
 /* benchmarking aid: run `iters` gradient-descent iterations on the state left by the last estimate_psi
  * without convergence checks; returns device ms of pass A, pass B and the whole loop */

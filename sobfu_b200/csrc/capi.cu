@@ -528,7 +528,7 @@ extern "C" int sobfu_b200_solver_get_taps(sobfu_b200_solver *s, float *t) {
     return 0;
 }
 extern "C" int sobfu_b200_solver_set_variant(sobfu_b200_solver *s, int v) {
-    if (!s || v < 0 || v > 4 || v == 3) return fail(SOBFU_B200_EINVAL, "variant must be 0 (default), 1 (generic), 2 (tiled) or 4 (tiled, pass A with software-pipelined gathers)");
+    if (!s || v < 0 || v > 4 || v == 3) return fail(SOBFU_B200_EINVAL, "variant must be 0 (default), 1 (generic), 2 (tiled) or 4 (tiled, pass A without software-pipelined gathers: the round-1 kernel)");
     if (v >= 2 && !(tiled_supported(s->d) && s->tma)) return fail(SOBFU_B200_EINVAL, "tiled/TMA kernels do not support dims %dx%dx%d", s->d.X, s->d.Y, s->d.Z);
     s->variant = v;
     return 0;

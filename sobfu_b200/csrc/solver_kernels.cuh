@@ -220,7 +220,7 @@ struct TmaMaps;   // opaque: CUtensorMaps of the nabla_U components (pass B) and
 TmaMaps *tma_maps_create(const LoopArgs &a);
 void tma_maps_destroy(TmaMaps *m);
 LaunchInfo launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, const ZRanges &zr, cudaStream_t st);
-void set_pass_a_variant(int v);   // 0: default kernel, 4: software-pipelined gathers; per host thread
+void set_pass_a_variant(int v);   // 0: default kernel (software-pipelined gathers), 4: the kernel without them; per host thread
 LaunchInfo launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int log, const ZRanges &zr, cudaStream_t st);   // grid 0: generic path
 // peer mode: the planes [lo, hi) of a launch (pass 0 = A, 1 = B) as | lower face chunk | upper face chunk | middle |
 ZRanges plan_peer_ranges(const Dims d, int pass, int lo, int hi, bool has_lo, bool has_hi, int sms = 0);

@@ -72,25 +72,7 @@ struct Sched {
     int tiles_x, tiles_y, nitems;
     int nr;
     int zlo[3], zhi[3], nz[3], zchunk[3], face[3];
-    // balanced form (pass B, one range without face tag): the (tile, plane) space in tile-major order is cut into `grid` contiguous
-    // runs of seg_len planes; CTA b's k-th work item (item = b + k * grid) is the part of its run inside tile (first tile + k).
-    // Static round robin over (tile, chunk) items leaves the busiest CTA ~10 % above the mean at one CTA per SM; a run is one or
-    // two long segments instead of three chunks with a pipeline prologue each.
-    int balanced, grid, seg_len;
 };
-// Cuts are proportional in a space where every tile column is HALO_V planes longer than it is (the pipeline prologue a CTA pays when
-// it enters a column): CTAs whose run crosses a column boundary get that many planes less, so the modelled cost -- not the plane
-// count -- is even.  A cut closer than MIN_SEG planes to a column boundary snaps onto it (no sliver segments with 6 halo loads).
-constexpr int MIN_SEG = 3, HALO_V = 3;
-__host__ __device__ __forceinline__ int balanced_cut(const Sched &sc, int b, int Z, int L) {
-    if (b >= sc.grid) return L;
-    const int Zv = Z + HALO_V, ncol = L / Z;
-    const long v = (long)b * ((long)ncol * Zv) / sc.grid;
-    int t = (int)(v / Zv), o = (int)(v % Zv) - HALO_V;
-    if (o < MIN_SEG) o = 0;
-    else if (Z - o < MIN_SEG) { o = 0; ++t; }
-    return t * Z + o;
-}
 
 SB_DEVI float c4(const float4 &v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
 
@@ -157,20 +139,6 @@ SB_DEVI float warp_sample_tex(cudaTextureObject_t tex, int ashift, int amask, fl
 // schedule checks of the CPU tests (sobfu_b200_debug_schedule).
 __host__ __device__ __forceinline__ void locate_item(const Sched &sc, int item, int TX, int TY, int &x0t, int &y0t, int &zb, int &ze, int &face) {
     const int xy = sc.tiles_x * sc.tiles_y;
-    if (sc.balanced) {
-        const int Z = sc.zhi[0] - sc.zlo[0], L = xy * Z;
-        const int b = item % sc.grid, k = item / sc.grid;
-        const int lin0 = balanced_cut(sc, b, Z, L), lin1 = balanced_cut(sc, b + 1, Z, L);
-        const int t = lin0 / Z + k;
-        const int a = lin0 > t * Z ? lin0 : t * Z, e = lin1 < (t + 1) * Z ? lin1 : (t + 1) * Z;
-        const int tyi = t / sc.tiles_x;
-        x0t = (t - tyi * sc.tiles_x) * TX;
-        y0t = tyi * TY;
-        zb = sc.zlo[0] + (a - t * Z);
-        ze = e > a ? sc.zlo[0] + (e - t * Z) : zb;      // empty: past the end of this CTA's run
-        face = 0;
-        return;
-    }
     int tz = item / xy;
     const int rem = item - tz * xy;
     const int tyi = rem / sc.tiles_x;
@@ -195,7 +163,6 @@ struct Stream {
         if (item >= sc.nitems) return;
         locate_item(sc, item, TX, TY, x0t, y0t, zb, ze, face);
         (void)Z;
-        if (ze <= zb) { item = sc.nitems; return; }     // balanced form: the CTA's run has ended
         p = zb - LO;
         p_last = ze - 1 + HI;
     }
@@ -214,10 +181,10 @@ constexpr int TX = 4 * LX, TY = NW * RW;          // 64 x 24 outputs per plane
 constexpr int SX = TX + 8, SY = TY + 6;           // staged box 4|64|4 floats x 3|24|3 rows
 constexpr int NSTAGE = 6;                         // planes q-3..q live, two in flight
 #ifndef PB_PF_AHEAD
-#define PB_PF_AHEAD 4
+#define PB_PF_AHEAD 4                             // 8 measured slower (0.1528 vs 0.1444 ms at 256^3)
 #endif
 #ifndef PB_BACKOFF_NS
-#define PB_BACKOFF_NS 128
+#define PB_BACKOFF_NS 128                         // 400 measured the same
 #endif
 constexpr int PF_AHEAD = PB_PF_AHEAD;             // L2 prefetch distance (planes) ahead of the shared-memory fill
 constexpr int COMP_BYTES = ((SX * SY * 4 + 127) / 128) * 128;
@@ -474,8 +441,34 @@ SB_DEVI void sts1(unsigned saddr, float v) { asm volatile("st.shared.f32 [%0], %
 // ---- the stencil half of pass A, shared by its kernels: one thread = 4 consecutive voxels (a "quad") of one tile row ----
 struct Quad {
     int x0, y;                        // volume coordinates of the first voxel
+    int lx;                           // position of the quad in its tile row (0 .. PA_LX-1): lanes lx-1 / lx+1 hold the x neighbours
     bool active, x_lo, x_hi, y_lo, y_hi;
 };
+// The voxel left of a quad's first / right of its last one.  Lanes own consecutive quads of a tile row, so the value sits in the
+// neighbouring lane's registers: one shuffle instead of a scalar shared load whose 32 addresses (every fourth float of four rows)
+// fall on 8 banks -- a 4-way bank conflict per load, in a kernel that is bound by the L1TEX data pipe (shared-memory + texture
+// wavefronts, profiles/r2_tuning_log.md).  Only the lanes at the ends of a tile row read the halo column from shared memory.
+// `quad` = shared address of the quad (row pitch SX floats); every lane of the warp must call these.
+template <int SX>
+SB_DEVI float x_left(unsigned quad, float own_w, int lx) {
+#ifdef PA_NO_SHFL
+    return lds1(quad - 4);
+#else
+    float v = __shfl_up_sync(0xffffffffu, own_w, 1);
+    if (lx == 0) v = lds1(quad - 4);
+    return v;
+#endif
+}
+template <int SX>
+SB_DEVI float x_right(unsigned quad, float own_x, int lx) {
+#ifdef PA_NO_SHFL
+    return lds1(quad + 16);
+#else
+    float v = __shfl_down_sync(0xffffffffu, own_x, 1);
+    if (lx == PA_LX - 1) v = lds1(quad + 16);
+    return v;
+#endif
+}
 // w_reg * laplacian(psi) at the centre plane (vector_fields.cu:291-337); on a boundary plane both neighbours of that axis are
 // the voxel itself.  sC / sM: shared addresses of the quad in the staged psi planes zc and zc-1 (component stride ARR bytes, row
 // pitch SX floats), Zpl: the quad of psi at zc+1; bz: zc is the first or last plane of the VOLUME
@@ -487,7 +480,7 @@ SB_DEVI void laplacian_quad(float (&Lw)[3][4], const Quad &qd, bool bz, unsigned
         const unsigned p0 = sC + c * ARR;
         const float4 C = lds4(p0);
         float4 Ym = lds4(p0 - SX * 4), Yp = lds4(p0 + SX * 4), Zp = Zpl[c], Zm = lds4(sM + c * ARR);
-        const float xl = lds1(p0 - 4), xr = lds1(p0 + 16);
+        const float xl = x_left<SX>(p0, C.w, qd.lx), xr = x_right<SX>(p0, C.x, qd.lx);
         // only the first / last voxel of a row can sit on an x face (X % 4 == 0)
         const float xm[4] = {qd.x_lo ? C.x : xl, C.x, C.y, qd.x_hi ? C.w : C.z}, xp[4] = {qd.x_lo ? C.x : C.y, C.z, C.w, qd.x_hi ? C.w : xr};
         if (edge) {
@@ -518,7 +511,7 @@ SB_DEVI void gradient_store_quad(const LoopArgs &a, const Quad &qd, int zc, bool
     float nx[4], ny[4], nz[4], df[4];
     {
         const float4 C = wc, Ym = lds4(w0 - SX * 4), Yp = lds4(w0 + SX * 4);
-        const float xl = lds1(w0 - 4), xr = lds1(w0 + 16);
+        const float xl = x_left<SX>(w0, C.w, qd.lx), xr = x_right<SX>(w0, C.x, qd.lx);
         const float xm[4] = {qd.x_lo ? C.y : xl, C.x, C.y, C.z}, xp[4] = {C.y, C.z, C.w, qd.x_hi ? C.z : xr};
         float4 Y1 = Yp, Y2 = Ym, Z1 = wp, Z2 = wm;
         if (edge) {
@@ -680,7 +673,7 @@ __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
     St cs;
     for (cs.open(blockIdx.x, sc, d.Z); cs.valid(sc); cs.open(cs.item + (int)gridDim.x, sc, d.Z)) {
         Quad qd;
-        qd.x0 = cs.x0t + 4 * lx; qd.y = cs.y0t + ty;
+        qd.x0 = cs.x0t + 4 * lx; qd.y = cs.y0t + ty; qd.lx = lx;
         qd.active = qd.x0 < X && qd.y < d.Y;
         const int row = min(qd.x0, X - 4) + X * min(qd.y, d.Y - 1);
         qd.y_lo = (qd.y == 0); qd.y_hi = (qd.y == d.Y - 1);
@@ -750,7 +743,7 @@ __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
 }  // namespace pa
 
 // =============================================================================================================
-// pass A, software-pipelined across planes (variant 4)
+// pass A, software-pipelined across planes (the default)
 // =============================================================================================================
 // Same arithmetic and the same outputs as pa::pass_a_tma_kernel.  There the two gather4 fetches of a sample are consumed right
 // after they are issued: five dependent texture round trips per thread and plane, 16 warps per SM -- issue slots are used 51 % of
@@ -758,9 +751,10 @@ __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
 // step of stencil arithmetic (and the other warps' steps) sits between a fetch and its first use.  Only the 8 result registers of
 // a fetch stay live across the step (5 samples per thread: 40 registers); the interpolation weights are recomputed from psi,
 // which is still in the ring.  Price: the centre plane trails the newest plane by two instead of one (one more pipeline-fill step
-// per work item, one more ring stage) and 168 registers (3 CTAs of 4 warps per SM instead of 4).
+// per work item, one more ring stage).  This is the default pass A; the kernel above stays for volumes without a gather atlas and
+// as variant 4.
 #ifndef PA2_CTAS
-#define PA2_CTAS 3
+#define PA2_CTAS 4      // measured at 256^3: 4 CTAs/SM (128 registers) 0.182 ms, 3 (168) 0.199, 2 (210) 0.249; the round-1 kernel 0.192
 #endif
 #ifndef PA2_AHEAD
 #define PA2_AHEAD 1
@@ -852,7 +846,7 @@ __global__ void __launch_bounds__(NTHREADS, PA2_CTAS)
     St cs;
     for (cs.open(blockIdx.x, sc, d.Z); cs.valid(sc); cs.open(cs.item + (int)gridDim.x, sc, d.Z)) {
         Quad qd;
-        qd.x0 = cs.x0t + 4 * lx; qd.y = cs.y0t + ty;
+        qd.x0 = cs.x0t + 4 * lx; qd.y = cs.y0t + ty; qd.lx = lx;
         qd.active = qd.x0 < X && qd.y < d.Y;
         const int row = min(qd.x0, X - 4) + X * min(qd.y, d.Y - 1);
         qd.y_lo = (qd.y == 0); qd.y_hi = (qd.y == d.Y - 1);
@@ -953,40 +947,14 @@ int sm_count() {
 // c planes costs c + halo_planes * halo_cost plane-steps.  Ranges of fewer than 16 planes stay one chunk; for the others the
 // chunk count that minimises the busiest CTA's load -- given the items already placed before it -- is taken (chunks of >= 16
 // planes -- 8 for ranges under 64 planes or when 16-plane chunks cannot fill the CTAs -- so that the pipeline prologue stays a small share).
-Sched make_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_planes, double halo_cost, int ctas, double *worst_load = nullptr,
-                 bool balanced_ok = false) {
+Sched make_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_planes, double halo_cost, int ctas, double *worst_load = nullptr) {
     Sched s;
     s.tiles_x = (d.X + TX - 1) / TX;
     s.tiles_y = (d.Y + TY - 1) / TY;
     const int xy = s.tiles_x * s.tiles_y;
     s.nr = zr.n;
     s.nitems = 0;
-    s.balanced = 0; s.grid = 0; s.seg_len = 0;
     for (int r = 0; r < 3; ++r) { s.zlo[r] = s.zhi[r] = 0; s.nz[r] = 0; s.zchunk[r] = 1; s.face[r] = 0; }
-    static const bool no_balanced = getenv("SOBFU_B200_NO_BALANCED") != nullptr;
-    if (balanced_ok && !no_balanced && zr.n == 1 && zr.face[0] == 0 && zr.hi[0] - zr.lo[0] >= 8) {
-        const int Z = zr.hi[0] - zr.lo[0], L = xy * Z;
-        if (L >= 8 * ctas) {                          // at least 8 planes per CTA: otherwise the chunked form below
-            s.balanced = 1;
-            s.grid = ctas;
-            s.seg_len = (L + ctas - 1) / ctas;
-            s.zlo[0] = zr.lo[0]; s.zhi[0] = zr.hi[0];
-            s.nz[0] = 1; s.zchunk[0] = Z;
-            s.nitems = s.grid * (s.seg_len / Z + 2);  // upper bound on the segments of a run; the surplus items are empty
-            if (worst_load) {
-                double w = 0.0;
-                for (int b = 0; b < s.grid; ++b) {
-                    const int lin0 = balanced_cut(s, b, Z, L), lin1 = balanced_cut(s, b + 1, Z, L);
-                    if (lin1 <= lin0) continue;
-                    const int segs = (lin1 - 1) / Z - lin0 / Z + 1;
-                    const double c = (lin1 - lin0) + segs * (halo_planes * halo_cost + 1.0);
-                    w = c > w ? c : w;
-                }
-                *worst_load = w;
-            }
-            return s;
-        }
-    }
     std::vector<double> load(ctas, 0.0), trial(ctas);
     for (int r = 0; r < zr.n && r < MAX_ZRANGES; ++r) {
         const int Z = zr.hi[r] - zr.lo[r];
@@ -1031,17 +999,17 @@ Sched make_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_plane
 }
 
 // the schedule depends on the shape and the ranges only: computed once per distinct launch geometry (the solver thread only)
-Sched cached_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_planes, double halo_cost, int ctas, bool balanced_ok = false) {
+Sched cached_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_planes, double halo_cost, int ctas) {
     struct Key { int v[16]; };
     static std::vector<std::pair<Key, Sched>> cache;
     static std::mutex mu;
     std::lock_guard<std::mutex> lock(mu);
     Key k{};
-    k.v[0] = d.X; k.v[1] = d.Y; k.v[2] = d.Z; k.v[3] = TX; k.v[4] = TY; k.v[5] = ctas; k.v[6] = zr.n + (balanced_ok ? 16 : 0);
+    k.v[0] = d.X; k.v[1] = d.Y; k.v[2] = d.Z; k.v[3] = TX; k.v[4] = TY; k.v[5] = ctas; k.v[6] = zr.n;
     for (int r = 0; r < MAX_ZRANGES; ++r) { k.v[7 + 3 * r] = r < zr.n ? zr.lo[r] : 0; k.v[8 + 3 * r] = r < zr.n ? zr.hi[r] : 0; k.v[9 + 3 * r] = r < zr.n ? zr.face[r] : 0; }
     for (auto &e : cache)
         if (!memcmp(&e.first, &k, sizeof k)) return e.second;
-    const Sched sc = make_sched(d, zr, TX, TY, halo_planes, halo_cost, ctas, nullptr, balanced_ok);
+    const Sched sc = make_sched(d, zr, TX, TY, halo_planes, halo_cost, ctas);
     if (cache.size() > 64) cache.clear();
     cache.emplace_back(k, sc);
     return sc;
@@ -1049,7 +1017,6 @@ Sched cached_sched(const Dims d, const ZRanges &zr, int TX, int TY, int halo_pla
 
 LaunchInfo launch_info(const Sched &sc, int grid) {
     LaunchInfo li{grid, {0, 0, 0}};
-    if (sc.balanced) { li.face_items[0] = sc.nitems; return li; }
     for (int r = 0; r < 3; ++r)
         if (sc.face[r] >= 0 && sc.face[r] < 3) li.face_items[sc.face[r]] += sc.tiles_x * sc.tiles_y * sc.nz[r];
     return li;
@@ -1121,9 +1088,9 @@ void tma_maps_destroy(TmaMaps *m) { delete m; }
 
 LaunchInfo launch_pass_b_tma(const LoopArgs &a, const TmaMaps *m, int it, const ZRanges &zr, cudaStream_t st) {
     const int ctas = sm_count();
-    const Sched sc = cached_sched(a.d, zr, pb::TX, pb::TY, 6, 0.35, ctas, true);
+    const Sched sc = cached_sched(a.d, zr, pb::TX, pb::TY, 6, 0.35, ctas);
     if (sc.nitems == 0) return LaunchInfo{0, {0, 0, 0}};
-    const int grid = sc.balanced ? sc.grid : (sc.nitems < ctas ? sc.nitems : ctas);
+    const int grid = sc.nitems < ctas ? sc.nitems : ctas;
     if (a.peer_n > 0) launch_pdl(pb::pass_b_tma_kernel<true>, grid, (pb::NW + 1) * 32, pb::SMEM_BYTES, st, m->g[0], m->g[1], m->g[2], m->pb_psi[0], m->pb_psi[1], m->pb_psi[2], a, it, sc);
     else launch_pdl(pb::pass_b_tma_kernel<false>, grid, (pb::NW + 1) * 32, pb::SMEM_BYTES, st, m->g[0], m->g[1], m->g[2], m->pb_psi[0], m->pb_psi[1], m->pb_psi[2], a, it, sc);
     return launch_info(sc, grid);
@@ -1141,7 +1108,7 @@ LaunchInfo launch_pass_a_tma(const LoopArgs &a, const TmaMaps *m, int it, int lo
         return LaunchInfo{0, {0, 0, 0}};
     }
     const bool peer = a.peer_n > 0 && a.wait_halo;
-    if (g_pass_a_variant == 4 && a.pn_tex) {      // software-pipelined gathers (one more pipeline-fill step per item: 3 halo steps)
+    if (g_pass_a_variant != 4 && a.pn_tex) {      // default: software-pipelined gathers (one more pipeline-fill step per item: 3 halo steps)
         const int pctas = PA2_CTAS * sm_count();
         const Sched psc = cached_sched(a.d, zr, pa2::TX, pa2::TY, 3, 0.6, pctas);
         if (psc.nitems == 0) return LaunchInfo{0, {0, 0, 0}};
@@ -1186,20 +1153,15 @@ extern "C" int sobfu_b200_debug_schedule(int pass, int X, int Y, int Zlocal, int
     for (int r = 0; r < MAX_ZRANGES; ++r) { zr.lo[r] = r < nranges ? lo[r] : 0; zr.hi[r] = r < nranges ? hi[r] : 0; zr.face[r] = r < nranges ? face[r] : 0; }
     const int TX = pass ? pb::TX : pa::TX, TY = pass ? pb::TY : pa::TY;
     const int ctas = pass ? sms : PA_CTAS * sms;
-    const Sched sc = pass ? make_sched(Dims{X, Y, Zlocal}, zr, TX, TY, 6, 0.35, ctas, nullptr, true) : make_sched(Dims{X, Y, Zlocal}, zr, TX, TY, 2, 0.5, ctas);
-    *grid = sc.balanced ? sc.grid : (sc.nitems < ctas ? sc.nitems : ctas);
-    int n = 0;
-    for (int i = 0; i < sc.nitems; ++i) {
+    const Sched sc = pass ? make_sched(Dims{X, Y, Zlocal}, zr, TX, TY, 6, 0.35, ctas) : make_sched(Dims{X, Y, Zlocal}, zr, TX, TY, 2, 0.5, ctas);
+    *n_items = sc.nitems;
+    *grid = sc.nitems < ctas ? sc.nitems : ctas;
+    for (int i = 0; i < sc.nitems && i < cap; ++i) {
         int x0, y0, zb, ze, f;
         locate_item(sc, i, TX, TY, x0, y0, zb, ze, f);
-        if (ze <= zb) continue;                    // balanced form: surplus items past the end of a CTA's run
-        if (n < cap) {
-            int *o = items + 6 * n;
-            o[0] = *grid ? i % *grid : 0; o[1] = x0; o[2] = y0; o[3] = zb; o[4] = ze; o[5] = f;
-        }
-        ++n;
+        int *o = items + 6 * i;
+        o[0] = *grid ? i % *grid : 0; o[1] = x0; o[2] = y0; o[3] = zb; o[4] = ze; o[5] = f;
     }
-    *n_items = n;
     return 0;
 }
 

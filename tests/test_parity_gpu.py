@@ -221,8 +221,10 @@ def test_solver_zero_iterations_and_rejects_bad_filter(env):
         assert_bits(got[k], want[k], "zero iterations: " + k)
     with pytest.raises(sf.Sobfu200Error):   # the reference would run with uninitialised taps (solver.cpp:160-251)
         sf.Solver(sf.Params(volume_dims=dims, max_iter=1, s=7, lambda_=0.3))
+    with pytest.raises(sf.Sobfu200Error):   # 9 taps are tabulated for lambda = 0.05 and 0.1 only; 5 taps not at all
+        sf.Solver(sf.Params(volume_dims=dims, max_iter=1, s=9, lambda_=0.2))
     with pytest.raises(sf.Sobfu200Error):
-        sf.Solver(sf.Params(volume_dims=dims, max_iter=1, s=9, lambda_=0.1))
+        sf.Solver(sf.Params(volume_dims=dims, max_iter=1, s=5, lambda_=0.1))
 
 
 def test_host_buffer_entry_point(env):
@@ -349,9 +351,9 @@ def test_full_size_properties_at_512(env):
 
 @pytest.mark.timeout(90, method="thread")      # a pipeline bug would hang in cudaStreamSynchronize: kill the process, do not wait
 @pytest.mark.parametrize("dims,iters", [((64, 64, 64), 9), ((96, 40, 36), 6), ((128, 24, 16), 5), ((32, 8, 8), 4), ((256, 256, 40), 3)])
-def test_tiled_pass_a_with_pipelined_gathers(env, dims, iters):
-    """variant 4 (pass A consumes the gather4 fetches of a plane one step after it issued them) must give the oracle's bits:
-    full and partial tiles, several z chunks and items per CTA, warm-started psi"""
+def test_tiled_pass_a_without_pipelined_gathers(env, dims, iters):
+    """variant 4 (the pass A that consumes its gather4 fetches in the step that issues them; the default consumes them one step
+    later) must give the oracle's bits too: full and partial tiles, several z chunks and items per CTA, warm-started psi"""
     sf, orc, torch = env
     pg, pn, vs, trunc, eta = sphere_pair(dims, r=0.07)
     psi0 = wavy_psi(dims, amp=0.5)
