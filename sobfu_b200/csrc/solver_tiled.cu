@@ -441,34 +441,8 @@ SB_DEVI void sts1(unsigned saddr, float v) { asm volatile("st.shared.f32 [%0], %
 // ---- the stencil half of pass A, shared by its kernels: one thread = 4 consecutive voxels (a "quad") of one tile row ----
 struct Quad {
     int x0, y;                        // volume coordinates of the first voxel
-    int lx;                           // position of the quad in its tile row (0 .. PA_LX-1): lanes lx-1 / lx+1 hold the x neighbours
     bool active, x_lo, x_hi, y_lo, y_hi;
 };
-// The voxel left of a quad's first / right of its last one.  Lanes own consecutive quads of a tile row, so the value sits in the
-// neighbouring lane's registers: one shuffle instead of a scalar shared load whose 32 addresses (every fourth float of four rows)
-// fall on 8 banks -- a 4-way bank conflict per load, in a kernel that is bound by the L1TEX data pipe (shared-memory + texture
-// wavefronts, profiles/r2_tuning_log.md).  Only the lanes at the ends of a tile row read the halo column from shared memory.
-// `quad` = shared address of the quad (row pitch SX floats); every lane of the warp must call these.
-template <int SX>
-SB_DEVI float x_left(unsigned quad, float own_w, int lx) {
-#ifdef PA_NO_SHFL
-    return lds1(quad - 4);
-#else
-    float v = __shfl_up_sync(0xffffffffu, own_w, 1);
-    if (lx == 0) v = lds1(quad - 4);
-    return v;
-#endif
-}
-template <int SX>
-SB_DEVI float x_right(unsigned quad, float own_x, int lx) {
-#ifdef PA_NO_SHFL
-    return lds1(quad + 16);
-#else
-    float v = __shfl_down_sync(0xffffffffu, own_x, 1);
-    if (lx == PA_LX - 1) v = lds1(quad + 16);
-    return v;
-#endif
-}
 // w_reg * laplacian(psi) at the centre plane (vector_fields.cu:291-337); on a boundary plane both neighbours of that axis are
 // the voxel itself.  sC / sM: shared addresses of the quad in the staged psi planes zc and zc-1 (component stride ARR bytes, row
 // pitch SX floats), Zpl: the quad of psi at zc+1; bz: zc is the first or last plane of the VOLUME
@@ -480,7 +454,7 @@ SB_DEVI void laplacian_quad(float (&Lw)[3][4], const Quad &qd, bool bz, unsigned
         const unsigned p0 = sC + c * ARR;
         const float4 C = lds4(p0);
         float4 Ym = lds4(p0 - SX * 4), Yp = lds4(p0 + SX * 4), Zp = Zpl[c], Zm = lds4(sM + c * ARR);
-        const float xl = x_left<SX>(p0, C.w, qd.lx), xr = x_right<SX>(p0, C.x, qd.lx);
+        const float xl = lds1(p0 - 4), xr = lds1(p0 + 16);
         // only the first / last voxel of a row can sit on an x face (X % 4 == 0)
         const float xm[4] = {qd.x_lo ? C.x : xl, C.x, C.y, qd.x_hi ? C.w : C.z}, xp[4] = {qd.x_lo ? C.x : C.y, C.z, C.w, qd.x_hi ? C.w : xr};
         if (edge) {
@@ -511,7 +485,7 @@ SB_DEVI void gradient_store_quad(const LoopArgs &a, const Quad &qd, int zc, bool
     float nx[4], ny[4], nz[4], df[4];
     {
         const float4 C = wc, Ym = lds4(w0 - SX * 4), Yp = lds4(w0 + SX * 4);
-        const float xl = x_left<SX>(w0, C.w, qd.lx), xr = x_right<SX>(w0, C.x, qd.lx);
+        const float xl = lds1(w0 - 4), xr = lds1(w0 + 16);
         const float xm[4] = {qd.x_lo ? C.y : xl, C.x, C.y, C.z}, xp[4] = {C.y, C.z, C.w, qd.x_hi ? C.z : xr};
         float4 Y1 = Yp, Y2 = Ym, Z1 = wp, Z2 = wm;
         if (edge) {
@@ -673,7 +647,7 @@ __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
     St cs;
     for (cs.open(blockIdx.x, sc, d.Z); cs.valid(sc); cs.open(cs.item + (int)gridDim.x, sc, d.Z)) {
         Quad qd;
-        qd.x0 = cs.x0t + 4 * lx; qd.y = cs.y0t + ty; qd.lx = lx;
+        qd.x0 = cs.x0t + 4 * lx; qd.y = cs.y0t + ty;
         qd.active = qd.x0 < X && qd.y < d.Y;
         const int row = min(qd.x0, X - 4) + X * min(qd.y, d.Y - 1);
         qd.y_lo = (qd.y == 0); qd.y_hi = (qd.y == d.Y - 1);
@@ -757,15 +731,19 @@ __global__ void __launch_bounds__(NTHREADS, PA_CTAS)
 #define PA2_CTAS 4      // measured at 256^3: 4 CTAs/SM (128 registers) 0.182 ms, 3 (168) 0.199, 2 (210) 0.249; the round-1 kernel 0.192
 #endif
 #ifndef PA2_AHEAD
-#define PA2_AHEAD 1
-#endif
+#define PA2_AHEAD 2     // planes requested ahead of the one being consumed: with 1 the TMA latency of every plane was exposed (21 % of the
+#endif                  // stall samples sat in the wait for the `full` barrier, profiles/r2_ncu_pa2_*.txt)
 namespace pa2 {
 constexpr int LX = pa::LX, RW = pa::RW, NW = pa::NW, NTHREADS = pa::NTHREADS;
 constexpr int TX = pa::TX, TY = pa::TY, SX = pa::SX, SY = pa::SY;     // same tile: the tensor maps are shared
-constexpr int AHEAD = PA2_AHEAD, NSTAGE = 4 + AHEAD;                  // planes p-3 .. p live + AHEAD in flight
+// ring: when thread 0 refills after the barrier of step p, planes p-2, p-1 and p are still needed (they are p-3 .. p-1 of the
+// next step) and AHEAD planes are in flight or about to be: the load goes into the stage of plane p-3, last read in this step
+constexpr int AHEAD = PA2_AHEAD, NSTAGE = 3 + AHEAD;
+constexpr int NWB = 2;       // warped planes p-1 (written in this step) and p-2 (its x / y neighbours read in this step); the block
+                             // barrier at the end of the step separates the reads of a buffer from its next writes
 constexpr int PF_AHEAD = 4;
 constexpr int ARR_BYTES = pa::ARR_BYTES, STAGE_BYTES = 3 * ARR_BYTES;
-constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 3 * ARR_BYTES + 128;
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + NWB * ARR_BYTES + 128;
 constexpr unsigned TX_BYTES = pa::TX_BYTES;
 constexpr int NHALO = pa::NHALO;
 
@@ -846,7 +824,7 @@ __global__ void __launch_bounds__(NTHREADS, PA2_CTAS)
     St cs;
     for (cs.open(blockIdx.x, sc, d.Z); cs.valid(sc); cs.open(cs.item + (int)gridDim.x, sc, d.Z)) {
         Quad qd;
-        qd.x0 = cs.x0t + 4 * lx; qd.y = cs.y0t + ty; qd.lx = lx;
+        qd.x0 = cs.x0t + 4 * lx; qd.y = cs.y0t + ty;
         qd.active = qd.x0 < X && qd.y < d.Y;
         const int row = min(qd.x0, X - 4) + X * min(qd.y, d.Y - 1);
         qd.y_lo = (qd.y == 0); qd.y_hi = (qd.y == d.Y - 1);
@@ -871,8 +849,8 @@ __global__ void __launch_bounds__(NTHREADS, PA2_CTAS)
             const unsigned sP1 = smem + ((q + NSTAGE - 2u) % NSTAGE) * STAGE_BYTES;               // plane p-1
             const unsigned sC = smem + ((q + NSTAGE - 3u) % NSTAGE) * STAGE_BYTES + own_off;      // plane p-2 (centre)
             const unsigned sM = smem + ((q + 2u * NSTAGE - 4u) % NSTAGE) * STAGE_BYTES + own_off; // plane p-3
-            const unsigned wnew = wbuf0 + ((q + 1u) % 3u) * ARR_BYTES;                            // warped plane p-1 (completed now)
-            const unsigned wctr = wbuf0 + (q % 3u) * ARR_BYTES;                                   // warped plane p-2 (completed in the last step)
+            const unsigned wnew = wbuf0 + ((q + 1u) % NWB) * ARR_BYTES;                           // warped plane p-1 (completed now)
+            const unsigned wctr = wbuf0 + (q % NWB) * ARR_BYTES;                                  // warped plane p-2 (completed in the last step)
 
             // ---- 1. the gathers of plane p-1 have had a whole step to arrive: interpolate (weights recomputed from psi(p-1)) ----
             float4 z1[3];
@@ -919,7 +897,7 @@ __global__ void __launch_bounds__(NTHREADS, PA2_CTAS)
                 laplacian_quad<SX, ARR_BYTES>(Lw, qd, z_lo || z_hi, sC, sM, z1, a.w_reg);
                 gradient_store_quad<SX>(a, qd, zc, z_lo, z_hi, wctr + own_off, wm, wc, wp, g4, Lw);
             }
-            __syncthreads();                  // warped plane p-1 visible to the CTA; ring stage of plane p-3 is free
+            __syncthreads();                  // warped plane p-1 visible to the CTA (and p-2 no longer read); ring stage of plane p-3 is free
             if (tid == 0) feed();
             wm = wc; wc = wp;
         }
