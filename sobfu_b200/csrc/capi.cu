@@ -247,7 +247,8 @@ struct sobfu_b200_solver {
     double *energies = nullptr;    // e_data[max_iter], e_reg[max_iter]
     float *energy_partial = nullptr;   // block results of the reference-order energy reduction (2 x 65536 floats)
     // host side
-    LoopState *h_state = nullptr;  // pinned
+    LoopState *h_state = nullptr;  // pinned; [0]: end of the solve, [1], [2]: the two chunk peeks in flight
+    cudaEvent_t ev_chunk[2] = {nullptr, nullptr};
     std::vector<unsigned long long> h_maxkey;
     std::vector<double> h_energies;
     std::vector<sobfu_b200_iter_log> log;
@@ -453,6 +454,7 @@ extern "C" int sobfu_b200_solver_destroy(sobfu_b200_solver *s) {
     if (s->pn_array) cudaFreeArray(s->pn_array);
     cudaFree(s->state); cudaFree(s->maxkey); cudaFree(s->tickets); cudaFree(s->energies); cudaFree(s->energy_partial); cudaFree(s->trace);
     if (s->h_state) cudaFreeHost(s->h_state);
+    for (auto &e : s->ev_chunk) if (e) cudaEventDestroy(e);
     cudaFree(s->overflow);
     if (s->h_overflow) cudaFreeHost(s->h_overflow);
     for (auto &e : s->ev) if (e) cudaEventDestroy(e);
@@ -498,7 +500,8 @@ extern "C" int sobfu_b200_solver_create(sobfu_b200_solver **out, const sobfu_b20
     CKD(cudaMalloc(&s->tickets, mi * sizeof(unsigned int)));
     CKD(cudaMalloc(&s->energies, 2 * mi * sizeof(double)));
     CKD(cudaMalloc(&s->energy_partial, 2 * 65536 * sizeof(float)));
-    CKD(cudaMallocHost(&s->h_state, sizeof(LoopState)));
+    CKD(cudaMallocHost(&s->h_state, 3 * sizeof(LoopState)));
+    for (auto &e : s->ev_chunk) CKD(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CKD(cudaMalloc(&s->overflow, sizeof(int)));
     CKD(cudaMallocHost(&s->h_overflow, sizeof(int)));
     CKD(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -966,32 +969,39 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
     }
     launch_unpack(psi, phi_global, phi_n, s->args, st);
     if ((rc = exchange_psi(s, st)) || (rc = exchange_pg(s, st))) return rc;
-    launch_initial_warp(s->args, st);
-    launches += 2;
+    ++launches;
+    // solver.cu:106: the generic kernels read the warped plane from memory; the tiled pass A computes it itself (and a logging
+    // iteration of the tiled path materialises it on demand)
+    if (!use_tiled(s)) { launch_initial_warp(s->args, st); ++launches; }
     CK_LAST();
     CK(cudaEventRecord(s->ev[1], st));
 
     // gradient descent (solver.cu:114-193).  Iterations are enqueued in chunks; the device decides convergence.
+    // The sticky flag (raised by the first kernel after the converged iteration) is copied out after every chunk; the host looks
+    // at the copy of chunk k-1 only after chunk k is enqueued, so the device never runs dry while the host decides.
     const int CHUNK = 64;
-    int converged = 0, iters = mi;
-    for (int it0 = 0; it0 < mi && !converged; it0 += CHUNK) {
+    int converged = 0, iters = mi, k = 0;
+    for (int it0 = 0; it0 < mi && !converged; it0 += CHUNK, ++k) {
         const int it1 = it0 + CHUNK < mi ? it0 + CHUNK : mi;
         for (int it = it0; it < it1; ++it)
             if ((rc = launch_iteration(s, it, log_iter(p, it + 1) ? 1 : 0, &launches))) return rc;
-        if ((rc = join_psi_exchange(s)) || (rc = join_max(s))) return rc;
         CK_LAST();
-        if (it1 < mi) {   // peek at the sticky flag (it is raised by pass A of the iteration after the converged one)
-            CK(cudaMemcpyAsync(s->h_state, s->state, sizeof(LoopState), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            if (s->h_state->converged) { converged = 1; iters = s->h_state->iters; }
+        if (it1 < mi) {
+            CK(cudaMemcpyAsync(s->h_state + 1 + (k & 1), s->state, sizeof(LoopState), cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(s->ev_chunk[k & 1], st));
+        }
+        if (k >= 1) {
+            CK(cudaEventSynchronize(s->ev_chunk[(k - 1) & 1]));
+            const LoopState &peek = s->h_state[1 + ((k - 1) & 1)];
+            if (peek.converged) { converged = 1; iters = peek.iters; }
         }
     }
+    if ((rc = join_psi_exchange(s)) || (rc = join_max(s))) return rc;
     if ((rc = peer_end(s, st))) return rc;
     CK(cudaEventRecord(s->ev[2], st));
 
     // tail (solver.cu:195-199): write back psi / phi_n o psi, psi^-1 from identity (48 fixed-point steps), phi_global o psi^-1
-    if (use_tiled(s) && mi > 0) { launch_initial_warp(s->args, st); ++launches; }   // the TMA loop keeps phi_n o psi on chip
-    launch_pack(psi, phi_n_psi, phi_n, s->args, st);
+    launch_pack(psi, phi_n_psi, phi_n, s->args, use_tiled(s), st);   // the tiled loop keeps phi_n o psi on chip: pack samples it
     if (s->nranks == 1) {
         launch_estimate_inverse(psi, psi_inv, s->dg, 48, true, st);
         launch_apply(phi_global, phi_global_psi_inv, psi_inv, s->dg, st);
@@ -1002,7 +1012,7 @@ static int solve_device(sobfu_b200_solver *s, const float2 *phi_global, float2 *
         } else {
             if ((rc = tail_gathered(s, phi_global, phi_global_psi_inv, psi, psi_inv, st))) return rc;
         }
-        if (mi > 0) CKN(n.AllReduce(s->energies, s->energies, 2 * mi, ncclDouble, ncclSum, s->comm, st));
+        if (mi > 0 && p.verbosity > 0) CKN(n.AllReduce(s->energies, s->energies, 2 * mi, ncclDouble, ncclSum, s->comm, st));   // only logged iterations fill them
         // peer mode keeps the per-rank maxima in maxkey[] (the global ones live in the allmax tables): reduce them for the log
         if (mi > 0 && peer_mode(s)) CKN(n.AllReduce(s->maxkey, s->maxkey, mi, ncclUint64, ncclMax, s->comm, st));
     }

@@ -306,6 +306,9 @@ __global__ void __launch_bounds__(BX *BY *BZ) pass_b_generic_kernel(LoopArgs a, 
 // ---- epilogue: planes -> AoS ---------------------------------------------------------------------------------
 // psi.w is preserved (update_psi_kernel never writes it); phi_n_psi = {warped tsdf, weight of the floor voxel}
 // (utils.hpp:83).
+// WARP: the warped plane a.w is not current (the tiled loop keeps phi_n o psi on chip): sample it here (apply_kernel,
+// vector_fields.cu:81-100) instead of a separate pass that writes a.w and a read of it
+template <bool WARP>
 __global__ void pack_kernel(float4 *__restrict__ psi, float2 *__restrict__ phi_n_psi, const float2 *__restrict__ phi_n,
                             LoopArgs a) {
     const size_t n = (size_t)a.d.X * a.d.Y * a.d.Z;
@@ -316,7 +319,7 @@ __global__ void pack_kernel(float4 *__restrict__ psi, float2 *__restrict__ phi_n
         psi[i] = p;
         const TriCoord t = tri_coord(x, y, z, a.dg);
         const float wgt = phi_n[(size_t)t.gx + (size_t)a.dg.X * ((size_t)t.gy + (size_t)a.dg.Y * t.gz)].y;
-        phi_n_psi[i] = make_float2(a.w[i], wgt);
+        phi_n_psi[i] = make_float2(WARP ? sample_scalar<1>(a.pn, t, a.dg) : a.w[i], wgt);
     }
 }
 }  // namespace
@@ -355,9 +358,10 @@ void launch_energy_trees(const LoopArgs &a, int it, float *partial, cudaStream_t
 void launch_pass_b_generic(const LoopArgs &a, int it, cudaStream_t st) {
     pass_b_generic_kernel<<<grid_for(a.d), dim3(BX, BY, BZ), 0, st>>>(a, it);
 }
-void launch_pack(float4 *psi, float2 *phi_n_psi, const float2 *phi_n, const LoopArgs &a, cudaStream_t st) {
+void launch_pack(float4 *psi, float2 *phi_n_psi, const float2 *phi_n, const LoopArgs &a, bool warp, cudaStream_t st) {
     const size_t n = (size_t)a.d.X * a.d.Y * a.d.Z;
-    pack_kernel<<<stream_grid(n), 256, 0, st>>>(psi, phi_n_psi, phi_n, a);
+    if (warp) pack_kernel<true><<<stream_grid(n), 256, 0, st>>>(psi, phi_n_psi, phi_n, a);
+    else pack_kernel<false><<<stream_grid(n), 256, 0, st>>>(psi, phi_n_psi, phi_n, a);
 }
 
 }  // namespace sb

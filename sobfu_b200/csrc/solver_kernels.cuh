@@ -212,7 +212,7 @@ void launch_pass_a_generic(const LoopArgs &a, int it, int log, cudaStream_t st);
 unsigned energy_tree_blocks(size_t n);
 void launch_energy_trees(const LoopArgs &a, int it, float *partial, cudaStream_t st);
 void launch_pass_b_generic(const LoopArgs &a, int it, cudaStream_t st);
-void launch_pack(float4 *psi, float2 *phi_n_psi, const float2 *phi_n, const LoopArgs &a, cudaStream_t st);
+void launch_pack(float4 *psi, float2 *phi_n_psi, const float2 *phi_n, const LoopArgs &a, bool warp, cudaStream_t st);   // warp: a.w is stale, sample here
 
 // tiled kernels (pass_a_tiled.cu / pass_b_tma.cu); return false when the shape is not supported
 bool tiled_supported(const Dims d);

@@ -2,8 +2,9 @@
 
 The volume is partitioned along z; rank r owns planes [r*Z/n, (r+1)*Z/n) of psi, psi^-1, phi_global, phi_global o psi^-1
 and phi_n o psi, and keeps the whole phi_n (every rank integrates the 640x480 depth frame itself).  The halo exchanges
-(nabla_U: 3 planes, psi: 1 plane, per iteration and direction) and the scalar MAX all-reduce of the convergence test run
-inside libsobfu_b200.so over its own NCCL communicator; torch.distributed only carries the NCCL unique id at start-up.
+(psi: 4 planes per iteration and direction; nabla_U on the halo planes is recomputed) and the maximum of the convergence test run
+inside libsobfu_b200.so -- by default inside its kernels over NVLink peer memory (CUDA IPC), else over its own NCCL communicator;
+torch.distributed only carries the NCCL unique id and the IPC handles at start-up.
 """
 import ctypes as C
 
@@ -78,9 +79,9 @@ class SlabSolver(Solver):
         the blocks are all-gathered, every rank maps its neighbours.  Returns False (NCCL exchange stays) when the ranks are
         not all on one node / cannot map each other; the decision is collective so that all ranks run the same protocol."""
         import os
-        # Opt-in: measured on B200 (profiles/r1_tuning_log.md) the NCCL exchange overlapped on a second stream is faster at
-        # 2 and 4 GPUs (256^3: 4528 vs 4351 and 7496 vs 6755 it/s), so it stays the default.
-        if not os.environ.get("SOBFU_B200_PEER") or os.environ.get("SOBFU_B200_NO_PEER"):
+        # Default since round 2 (profiles/r2_tuning_log.md): 256^3 on 8 GPUs 12709 vs 8416 it/s over NCCL, on 2 GPUs 4878 vs 4778;
+        # SOBFU_B200_NO_PEER=1 keeps the NCCL exchange (also the automatic fallback when the IPC mappings cannot be made).
+        if os.environ.get("SOBFU_B200_NO_PEER"):
             return False
         blk = (C.c_ubyte * 128)()
         ok = lib().sobfu_b200_solver_peer_export(self._h, blk) == 0

@@ -8,7 +8,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("SOBFU_B200_QUIET", "1")
-os.environ["SOBFU_B200_PEER"] = "1"      # peer mode is opt-in
+os.environ.pop("SOBFU_B200_NO_PEER", None)   # peer mode is the default
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402

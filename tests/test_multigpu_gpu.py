@@ -20,8 +20,8 @@ def test_slab_solve_matches_single_gpu(built, mode):
     env = dict(os.environ)
     env.pop("SOBFU_B200_NO_PEER", None)
     env.pop("SOBFU_B200_PEER", None)
-    if mode == "peer":
-        env["SOBFU_B200_PEER"] = "1"         # opt-in; the NCCL exchange is the default (faster at 2 and 4 GPUs, measured)
+    if mode == "nccl":
+        env["SOBFU_B200_NO_PEER"] = "1"      # peer mode is the default; this keeps the exchange over NCCL
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % n, "--master-addr", "127.0.0.1",
                         "--master-port", "29541" if mode == "peer" else "29543", os.path.join(ROOT, "tests", "multigpu_worker.py")],
                        capture_output=True, text=True, timeout=900, env=env)
