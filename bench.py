@@ -40,6 +40,9 @@ COLS, ROWS = 640, 480
 ALGO_BYTES_PASS_A = 64      # R psi 16 + R phi_n_psi 8 + R phi_global 8 + W nabla_U 16  +  warp: R phi_n 8 + W phi_n_psi 8
 ALGO_BYTES_PASS_B = 48      # R nabla_U 16 + R psi 16 + W psi 16   (Sobolev filter + psi update + max-norm partials)
 ALGO_BYTES_ITER = 112
+# compulsory bytes of the layouts this library actually uses inside the loop (float planes; phi_n o psi never leaves the SM):
+OWN_BYTES_PASS_A = 32       # R psi 12 + R phi_global 4 + R phi_n (gathers) ~4 + W nabla_U 12
+OWN_BYTES_PASS_B = 36       # R nabla_U 12 + R psi 12 + W psi 12
 
 
 def synth_depth(frame, radius=0.15, z0=0.5, intr=None):
@@ -215,6 +218,9 @@ def measure_solver(args, rank, world, torch, dist, dim, iters, steps, warmup):
         "iteration_roofline_frac": ALGO_BYTES_ITER * Nl / (loop_ms / (steps * iters) * 1e-3) / 1e9 / peak,
         "pass_b_roofline_frac": ALGO_BYTES_PASS_B * Nl / (ms_b * 1e-3) / 1e9 / peak,
         "pass_a_roofline_frac": ALGO_BYTES_PASS_A * Nl / (ms_a * 1e-3) / 1e9 / peak,
+        # the same two kernels against the bytes of OUR layouts (what a perfectly HBM-bound version of these kernels would move)
+        "own_layout_frac": {"pass_a": OWN_BYTES_PASS_A * Nl / (ms_a * 1e-3) / 1e9 / peak, "pass_b": OWN_BYTES_PASS_B * Nl / (ms_b * 1e-3) / 1e9 / peak,
+                            "bytes_per_voxel": {"pass_a": OWN_BYTES_PASS_A, "pass_b": OWN_BYTES_PASS_B}},
         "clocks": clk,
         "e2e": {"value": N * iters * steps / (ms_e2e * 1e-3) / 1e9, "unit": "Gvoxel-iter/s", "frames_per_s": steps / (ms_e2e * 1e-3),
                 "h2d_bytes_per_step": COLS * ROWS * 2, "d2h_bytes_per_step": 4 + iters * 24 + 16},
@@ -351,7 +357,7 @@ def measure_traffic(dim):
     ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
     if not os.path.exists(ncu):
         return None, "ncu not found"
-    cmd = [ncu, "--csv", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:pass_[ab]_tma",
+    cmd = [ncu, "--csv", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:pass_[ab]_",
            "-s", "4", "-c", "6", sys.executable, os.path.abspath(__file__), "--traffic-child", "--dim", str(dim)]
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=dict(os.environ, SOBFU_B200_QUIET="1"))

@@ -921,6 +921,10 @@ int sm_count() {
     return sms;
 }
 
+// (Measured in round 2 and NOT adopted: scoring a candidate by the busiest SM -- sum over its resident CTAs -- instead of the busiest CTA
+// picks longer chunks (256^3: 8 x 32 planes instead of 9 x 29) and pass A ran 9 % slower: with 1024 items on 592 CTAs a quarter of the
+// CTAs has one item instead of two and the SMs run half empty for the second half of the kernel.  Even work per CTA matters more than
+// fewer pipeline prologues.)
 // Number of z chunks per range.  The CTAs take items round robin (item b, b + G, ...), ranges in the given order; a chunk of
 // c planes costs c + halo_planes * halo_cost plane-steps.  Ranges of fewer than 16 planes stay one chunk; for the others the
 // chunk count that minimises the busiest CTA's load -- given the items already placed before it -- is taken (chunks of >= 16
@@ -1125,13 +1129,15 @@ extern "C" int sobfu_b200_debug_peer_ranges(int pass, int X, int Y, int Zlocal, 
 extern "C" int sobfu_b200_debug_schedule(int pass, int X, int Y, int Zlocal, int nranges, const int *lo, const int *hi, const int *face, int sms,
                                          int *items, int cap, int *n_items, int *grid) {
     using namespace sb;
-    if (!lo || !hi || !face || !n_items || !grid || nranges < 1 || nranges > MAX_ZRANGES || sms < 1 || (pass != 0 && pass != 1)) return -1;
+    if (!lo || !hi || !face || !n_items || !grid || nranges < 1 || nranges > MAX_ZRANGES || sms < 1 || pass < 0 || pass > 2) return -1;
     ZRanges zr;
     zr.n = nranges;
     for (int r = 0; r < MAX_ZRANGES; ++r) { zr.lo[r] = r < nranges ? lo[r] : 0; zr.hi[r] = r < nranges ? hi[r] : 0; zr.face[r] = r < nranges ? face[r] : 0; }
-    const int TX = pass ? pb::TX : pa::TX, TY = pass ? pb::TY : pa::TY;
-    const int ctas = pass ? sms : PA_CTAS * sms;
-    const Sched sc = pass ? make_sched(Dims{X, Y, Zlocal}, zr, TX, TY, 6, 0.35, ctas) : make_sched(Dims{X, Y, Zlocal}, zr, TX, TY, 2, 0.5, ctas);
+    // pass 0: pass A without pipelined gathers (variant 4), 1: pass B, 2: pass A (default kernel: one more pipeline-fill step per item)
+    const int TX = pass == 1 ? pb::TX : pa::TX, TY = pass == 1 ? pb::TY : pa::TY;
+    const int ctas = pass == 1 ? sms : (pass == 2 ? PA2_CTAS : PA_CTAS) * sms;
+    const Sched sc = pass == 1 ? make_sched(Dims{X, Y, Zlocal}, zr, TX, TY, 6, 0.35, ctas)
+                               : (pass == 2 ? make_sched(Dims{X, Y, Zlocal}, zr, TX, TY, 3, 0.6, ctas) : make_sched(Dims{X, Y, Zlocal}, zr, TX, TY, 2, 0.5, ctas));
     *n_items = sc.nitems;
     *grid = sc.nitems < ctas ? sc.nitems : ctas;
     for (int i = 0; i < sc.nitems && i < cap; ++i) {

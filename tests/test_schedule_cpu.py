@@ -37,7 +37,7 @@ def check(built, pas, dims, ranges, max_imbalance):
     X, Y, Z = dims
     TX, TY = TILE[pas]
     it, grid = schedule(built, pas, dims, ranges)
-    ctas = 148 * (4 if pas == 0 else 1)
+    ctas = 148 * (1 if pas == 1 else 4)
     assert grid == min(len(it), ctas) and np.array_equal(it[:, 0], np.arange(len(it)) % grid)
     tiles = sorted({(int(a), int(b)) for a, b in it[:, 1:3]})
     assert tiles == sorted((x, y) for x in range(0, X, TX) for y in range(0, Y, TY))
@@ -67,7 +67,8 @@ def check(built, pas, dims, ranges, max_imbalance):
 
 @pytest.mark.parametrize("dim", [32, 64, 96, 128, 192, 256, 512])
 def test_whole_volume_schedules(built, dim):
-    for pas in (0, 1):
+    TILE[2], COST[2] = TILE[0], (3, 0.6)         # the default pass A: same tile, one more pipeline-fill step per item
+    for pas in (0, 1, 2):
         it = check(built, pas, (dim, dim, dim), [(0, dim, 0)], max_imbalance=1.35 if dim >= 256 else 1e9)
         if dim >= 256:
             assert (it[:, 4] - it[:, 3]).min() >= 16          # big volumes keep chunks of >= 16 planes
@@ -110,5 +111,5 @@ def test_bad_arguments(built):
     from sobfu_b200 import _capi
     z = (C.c_int * 3)()
     n, g = C.c_int(), C.c_int()
-    assert _capi.lib().sobfu_b200_debug_schedule(2, 64, 64, 64, 1, z, z, z, 148, None, 0, C.byref(n), C.byref(g)) != 0
+    assert _capi.lib().sobfu_b200_debug_schedule(3, 64, 64, 64, 1, z, z, z, 148, None, 0, C.byref(n), C.byref(g)) != 0
     assert _capi.lib().sobfu_b200_debug_schedule(0, 64, 64, 64, 4, z, z, z, 148, None, 0, C.byref(n), C.byref(g)) != 0
