@@ -34,7 +34,16 @@ os.environ.setdefault("SOBFU_B200_QUIET", "1")
 BOXING = dict(vol_size=0.75, trunc_vox=48.0, eta_vox=3.0, max_weight=128.0, fx=570.342, fy=570.342, cx=320.0, cy=240.0,
               trunc_depth=1.0, pose_tz=0.1, sigma_depth=0.005, sigma_spatial=4.5, ksz=7, start_frame=1,
               max_update_norm=1e-10, s=7, lam=0.1, alpha=0.001, w_reg=0.6)
+# params/params_umbrella.ini (reference): BASELINE.json configs[3] names it for the 512^3 volume (MAX_ITER -> 200 as everywhere here)
+UMBRELLA = dict(vol_size=1.0, trunc_vox=8.0, eta_vox=3.0, max_weight=128.0, fx=570.342, fy=570.342, cx=320.0, cy=240.0,
+                trunc_depth=1.5, pose_tz=0.3, sigma_depth=0.04, sigma_spatial=4.5, ksz=7, start_frame=1,
+                max_update_norm=1e-10, s=7, lam=0.1, alpha=0.001, w_reg=0.2)
 COLS, ROWS = 640, 480
+
+
+def params_for(dim):
+    """(ini values, ini name) of the solver workload at `dim`^3: params_umbrella.ini at 512^3, params_boxing.ini otherwise"""
+    return (UMBRELLA, "params_umbrella.ini") if dim >= 512 else (BOXING, "params_boxing.ini")
 # algorithmic bytes per voxel-iteration in the reference's layouts (SURVEY.md 8d); the warp of the live TSDF is fused
 # into pass A here (SURVEY fuses it into pass B), so its 16 B move with it: 48 + 16 | 48 = 112
 ALGO_BYTES_PASS_A = 64      # R psi 16 + R phi_n_psi 8 + R phi_global 8 + W nabla_U 16  +  warp: R phi_n 8 + W phi_n_psi 8
@@ -99,7 +108,7 @@ class ClockSampler:
 
 
 def make_params(sf, dim, iters):
-    b = BOXING
+    b, _ = params_for(dim)
     p = sf.Params(cols=COLS, rows=ROWS, volume_dims=(dim, dim, dim), volume_size=(b["vol_size"],) * 3,
                   intr=sf.Intr(b["fx"], b["fy"], b["cx"], b["cy"]), icp_truncate_depth_dist=b["trunc_depth"],
                   bilateral_sigma_depth=b["sigma_depth"], bilateral_sigma_spatial=b["sigma_spatial"], bilateral_kernel_size=b["ksz"],
@@ -208,8 +217,8 @@ def measure_solver(args, rank, world, torch, dist, dim, iters, steps, warmup):
         "metric": "solver_gvoxel_iters_per_s", "value": N * iters * steps / (ms * 1e-3) / 1e9, "unit": "Gvoxel-iter/s",
         "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%d^3 volume, params_boxing.ini (dims->%d, MAX_ITER->%d), 640x480 synthetic sphere depth, 1 step = 1 frame = "
-                               "estimate_psi with %d iterations" % (dim, dim, iters, iters), "l2": ("inputs exceed L2 (%.0f MB of solver state)" if 36 * N > 126e6 else
+        "config": {"workload": "%d^3 volume, %s (dims->%d, MAX_ITER->%d), 640x480 synthetic sphere depth, 1 step = 1 frame = "
+                               "estimate_psi with %d iterations" % (dim, params_for(dim)[1], dim, iters, iters), "l2": ("inputs exceed L2 (%.0f MB of solver state)" if 36 * N > 126e6 else
                           "NOT flushed: the solver state (%.0f MB) fits in the 126 MB L2 at this size; only volumes of >= 192^3 are HBM-bound") % (36 * N / 1e6),
                    "parallelism": "1 GPU" if world == 1 else "z-slab x%d" % world},
         "solver_iters_per_s": iters * steps / (ms * 1e-3), "loop_ms_per_iter": loop_ms / (steps * iters),
@@ -274,11 +283,11 @@ def parity_block(args, rank, world, torch, dist, fusion, dim, iters):
         from oracle import pyoracle as orc
         if not os.path.exists(orc.REF):
             return {"checked": False, "why": "oracle/_ref/libsobfu_ref.so is not built on this box"}
+        b, _ = params_for(dim)
         psi, psi_inv = sf.DeformationField((X, Y, Z)), sf.DeformationField((X, Y, Z))
         info = solver.estimate_psi(fusion.phi_global, fusion.phi_global_psi_inv, fusion.phi_n, fusion.phi_n_psi, psi, psi_inv)
         ours = {"psi": psi.get_data().cpu().numpy(), "psi_inv": psi_inv.get_data().cpu().numpy(),
                 "phi_n_psi": fusion.phi_n_psi.data().cpu().numpy(), "phi_global_psi_inv": fusion.phi_global_psi_inv.data().cpu().numpy()}
-        b = BOXING
         vs = np.float32(b["vol_size"]) / np.float32(dim)
         ref = orc.Reference((dim,) * 3, (b["vol_size"],) * 3, float(np.float32(b["trunc_vox"]) * vs), float(np.float32(b["eta_vox"]) * vs),
                             b["max_weight"], 0, iters, b["s"], b["max_update_norm"], b["lam"], b["alpha"], b["w_reg"])
@@ -390,8 +399,8 @@ def run_ours(args, rank, world, torch, dist):
             out["parity"] = par
     extra_dim = args.extra_dim if args.extra_dim is not None else (512 if world == 8 else 0)
     if extra_dim and extra_dim != args.dim:
-        # BASELINE.json configs[3]: the 512^3 volume z-slabbed over the GPUs of the box (params_umbrella.ini has the same solver
-        # parameters as params_boxing.ini but for the truncation band); fewer steps, the same timing rules
+        # BASELINE.json configs[3]: the 512^3 volume, params_umbrella.ini, z-slabbed over the GPUs of the box; fewer steps, the same
+        # timing rules
         del fusion
         torch.cuda.empty_cache()
         ex, fusion = measure_solver(args, rank, world, torch, dist, extra_dim, args.iters, min(args.steps, 3), 3)
@@ -510,7 +519,7 @@ def measure_reference(dim, iters, steps, warmup):
     """solver workload through the unmodified reference CUDA and its own host classes: (line as a dict)"""
     from oracle import pyoracle as orc
     import torch
-    b = BOXING
+    b, ini = params_for(dim)
     vs = np.float32(b["vol_size"]) / np.float32(dim)
     ref = orc.Reference((dim,) * 3, (b["vol_size"],) * 3, float(np.float32(b["trunc_vox"]) * vs), float(np.float32(b["eta_vox"]) * vs),
                         b["max_weight"], 0, iters, b["s"], b["max_update_norm"], b["lam"], b["alpha"], b["w_reg"],
@@ -551,8 +560,8 @@ def measure_reference(dim, iters, steps, warmup):
         "impl": "reference", "metric": "solver_gvoxel_iters_per_s", "value": v, "unit": "Gvoxel-iter/s", "n_gpus": 1, "steps": steps,
         "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%d^3 volume, params_boxing.ini (dims->%d, MAX_ITER->%d), 640x480 synthetic sphere depth, 1 step = 1 frame = "
-                               "estimate_psi with %d iterations" % (dim, dim, iters, iters), "parallelism": "1 GPU (the reference is single-GPU)"},
+        "config": {"workload": "%d^3 volume, %s (dims->%d, MAX_ITER->%d), 640x480 synthetic sphere depth, 1 step = 1 frame = "
+                               "estimate_psi with %d iterations" % (dim, ini, dim, iters, iters), "parallelism": "1 GPU (the reference is single-GPU)"},
         "solver_iters_per_s": iters * steps / (ms * 1e-3), "clocks": clk,
         "cpu_baseline": {"value": v, "unit": "Gvoxel-iter/s", "cores": os.cpu_count(), "kind": "reference",
                          "sample": "the reference has no CPU solver path: this is its own CUDA (sm_100a build of the unmodified sources) on one B200"},
