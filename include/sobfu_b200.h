@@ -196,13 +196,12 @@ int sobfu_b200_solver_tail_fallbacks(sobfu_b200_solver *s);
 /* Peer mode (ranks on one NVLink / NVSwitch domain, e.g. the 8 GPUs of a B200 node): the per-iteration psi halo exchange
  * and the convergence test leave NCCL.  Pass B on the slab faces stores its new psi planes straight into the neighbours'
  * halo planes over NVLink (CUDA IPC mappings) and signals through counters in the neighbours' memory; every rank publishes
- * its per-iteration maximum into every rank's table (last CTA of pass B).  An iteration is then TWO kernels on one stream:
- * pass A does the middle of the slab first and the halo-reading work items last, pass B the face items first, so the halo
- * planes travel while the middle of the slab is computed.
+ * its per-iteration maximum into every rank's table (last CTA of pass B).  An iteration is then TWO kernels on one stream; the
+ * work items next to a slab face are full-length z chunks issued first in both passes, so the halo planes and the
+ * acknowledgements travel while the middle of the slab is computed.
  *   every rank: peer_export(block);  launcher: all-gather the blocks (rank-major);  every rank: peer_attach(all blocks).
- * Optional: without it (or with SOBFU_B200_NO_PEER set, or when attach fails) the solver keeps exchanging over NCCL -- which
- * is what the Python launcher does unless SOBFU_B200_PEER is set: on B200 the NCCL exchange overlapped on a second stream
- * measured faster at 2 and 4 GPUs (256^3: 4528 vs 4351, 7496 vs 6755 iterations/s).
+ * Optional: without it (or with SOBFU_B200_NO_PEER set, or when attach fails) the solver keeps exchanging over NCCL.  The Python
+ * launcher attaches it by default: measured on B200 at 256^3, 12709 vs 8416 iterations/s on 8 GPUs, 4878 vs 4778 on 2.
  * Results are bit-identical in both modes.  Replaces nothing in the reference (single GPU, solver.cu:85-205). */
 #define SOBFU_B200_PEER_HANDLE_BYTES 128
 int sobfu_b200_solver_peer_export(sobfu_b200_solver *s, void *handle_block_host);
