@@ -171,7 +171,9 @@ extern "C" int sobfu_b200_sobolev_taps_computed(int s, float lambda, float *h) {
     }
     const double sign = u[s / 2] < 0.0 ? -1.0 : 1.0;
     float sum = 0.f;
-    for (int i = 0; i < s; ++i) { h[i] = (float)(sign * u[i]); sum += h[i]; }     // solver.cpp:253-261: fp32, left to right
+    for (int i = 0; i < s; ++i) h[i] = (float)(sign * u[i]);
+    for (int i = 0; i < s / 2; ++i) h[s - 1 - i] = h[i];                           // the filter is symmetric; make it so to the bit (the tiled pass B relies on it)
+    for (int i = 0; i < s; ++i) sum += h[i];                                       // solver.cpp:253-261: fp32, left to right
     for (int i = 0; i < s; ++i) h[i] /= sum;
     return 0;
 }
@@ -483,6 +485,8 @@ extern "C" int sobfu_b200_solver_create(sobfu_b200_solver **out, const sobfu_b20
     // filter its tables were derived by, instead of being refused
     if (rc && (g_compute_filter || getenv("SOBFU_B200_COMPUTE_FILTER"))) rc = sobfu_b200_sobolev_taps_computed(p->s, p->lambda, s->taps);
     if (rc) { delete s; return rc; }
+    for (int i = 0; i < p->s / 2; ++i)      // every filter the tables or the computed form produce is symmetric to the bit
+        if (s->taps[i] != s->taps[p->s - 1 - i]) { delete s; return fail(SOBFU_B200_EINVAL, "the Sobolev filter is not symmetric"); }
     s->dg = Dims{p->dims[0], p->dims[1], p->dims[2]};
     s->Ng = (size_t)s->dg.X * s->dg.Y * s->dg.Z;
     const int mi = p->max_iter > 0 ? p->max_iter : 1;
@@ -849,10 +853,6 @@ static int launch_iteration(sobfu_b200_solver *s, int it, int log, int *launches
         a.a_uses_max = 0;
         // measurement aid (sobfu_b200_solver_time_phases): timing events between the launches of the compute stream
         auto mark = [&]() { if (s->phase_pos < s->phase_ev.size()) cudaEventRecord(s->phase_ev[s->phase_pos++], s->stream); };
-        // SOBFU_B200_SLAB_SCHED=3 (experiment, off by default): pass B as ONE launch -- the psi exchange then starts after the
-        // whole pass and hides behind A_mid of the next iteration only; saves the small B_edge launch (10 plane-steps of pipeline
-        // for 4 planes of output on 88 of 148 CTAs at 256^2) and one kernel boundary
-        static const bool whole_b = getenv("SOBFU_B200_SLAB_SCHED") && atoi(getenv("SOBFU_B200_SLAB_SCHED")) == 3;
         mark();
         launch_pass_a_tma(a, s->tma, it, 0, a_mid, s->stream);
         mark();
@@ -860,15 +860,14 @@ static int launch_iteration(sobfu_b200_solver *s, int it, int log, int *launches
         launch_pass_a_tma(a, s->tma, it, 0, a_edge, s->stream);
         mark();
         if ((rc = join_max(s))) return rc;
-        if (whole_b) launch_pass_b_tma(a, s->tma, it, whole_slab(s), s->stream);
-        else launch_pass_b_tma(a, s->tma, it, b_edge, s->stream);
+        launch_pass_b_tma(a, s->tma, it, b_edge, s->stream);
         mark();
         CK(cudaEventRecord(s->ev_b, s->stream));
         CK(cudaStreamWaitEvent(s->comm_stream, s->ev_b, 0));
         if ((rc = exchange_psi(s, s->comm_stream))) return rc;
         CK(cudaEventRecord(s->ev_p, s->comm_stream));
         s->psi_exchange_pending = true;
-        if (!whole_b) launch_pass_b_tma(a, s->tma, it, b_mid, s->stream);
+        launch_pass_b_tma(a, s->tma, it, b_mid, s->stream);
         mark();
         if (s->args.check) {
             ncclComm_t cm = s->comm_max ? s->comm_max : s->comm;
@@ -879,7 +878,7 @@ static int launch_iteration(sobfu_b200_solver *s, int it, int log, int *launches
             CK(cudaEventRecord(s->ev_m, ms));
             s->max_pending = true;
         }
-        *launches += whole_b ? 3 : 4;
+        *launches += 4;
         return 0;
     }
     // serial form: pass A on the owned planes, nabla_U halo exchange, pass B, psi halo exchange, global max
@@ -1174,8 +1173,7 @@ extern "C" int sobfu_b200_solver_time_loop(sobfu_b200_solver *s, int iters, floa
 }
 
 // Measurement aid for the z-slab (NCCL) schedule: `iters` iterations with timing events between the launches of the compute
-// stream.  out[0..3] = mean milliseconds of A_mid | wait psi halos + A_edge | wait global max + B_edge (or the whole pass B with
-// SOBFU_B200_SLAB_SCHED=3) | B_mid; out[4] = mean milliseconds of a whole iteration.  Collective: every rank calls it.
+// stream.  out[0..3] = mean milliseconds of A_mid | wait psi halos + A_edge | wait global max + B_edge | B_mid; out[4] = mean milliseconds of a whole iteration.  Collective: every rank calls it.
 extern "C" int sobfu_b200_solver_time_phases(sobfu_b200_solver *s, int iters, float *out5) {
     if (!s || !out5 || iters <= 0 || iters > 1000) return fail(SOBFU_B200_EINVAL, "time_phases: bad argument");
     if (!s->have_state) return fail(SOBFU_B200_EINVAL, "time_phases needs the state left by a previous estimate_psi");

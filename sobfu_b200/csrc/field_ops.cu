@@ -59,7 +59,8 @@ SB_DEV float3 disp(const float4 *__restrict__ psi, int x, int y, int z, int zk, 
     return make_float3(sub(p.x, (float)x), sub(p.y, (float)y), sub(p.z, (float)z));   // get_displacement
 }
 // psi covers the window `w` of the volume `d`; psi_inv covers the z-slab [z0, z0 + nzl).  The fixed-point loop stops as soon as
-// a step reproduces its input bit for bit: every later step of the reference would return the same value.
+// a step reproduces its input bit for bit (every later step of the reference would return the same value) or the value of two
+// steps ago (a 2-cycle: the outcome of the remaining steps is known).
 __global__ void __launch_bounds__(BX *BY *BZ) estimate_inverse_kernel(const float4 *__restrict__ psi,
                                                                     float4 *__restrict__ psi_inv, Dims d, int z0, int nzl,
                                                                     int iters, int from_identity, ZWindow w) {
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(BX *BY *BZ) estimate_inverse_kernel(const floa
     if (from_identity) { vx = (float)x; vy = (float)y; vz = (float)z; vw = 0.f; }
     else { const float4 v = psi_inv[i]; vx = v.x; vy = v.y; vz = v.z; vw = v.w; }
     bool bad = false;
+    float qx = __int_as_float(0x7fc00000), qy = qx, qz = qx;      // the value before (vx, vy, vz); NaN: none yet
     for (int it = 0; it < iters; ++it) {
         const TriCoord t = tri_coord(vx, vy, vz, d);
         const int kg = win_plane(t.gz, w, bad), k1 = win_plane(t.z1, w, bad);
@@ -86,6 +88,17 @@ __global__ void __launch_bounds__(BX *BY *BZ) estimate_inverse_kernel(const floa
         const float nz = sub((float)z, mul(iz, 1.f));
         const bool same = __float_as_uint(nx) == __float_as_uint(vx) && __float_as_uint(ny) == __float_as_uint(vy) &&
                           __float_as_uint(nz) == __float_as_uint(vz);
+        // ... and a step that reproduces the value of two steps ago has entered a 2-cycle (the last-ulp oscillation of a
+        // contraction in fp32): the reference's remaining steps alternate between the two values, so the result after `iters`
+        // steps is known -- the new value if an even number of steps remains, the previous one otherwise
+        const bool cycle = __float_as_uint(nx) == __float_as_uint(qx) && __float_as_uint(ny) == __float_as_uint(qy) &&
+                           __float_as_uint(nz) == __float_as_uint(qz);
+        if (cycle && !same) {
+            if (!((iters - 1 - it) & 1)) { vx = nx; vy = ny; vz = nz; }
+            vw = 0.f;
+            break;
+        }
+        qx = vx; qy = vy; qz = vz;
         vx = nx; vy = ny; vz = nz; vw = 0.f;
         if (same) break;
     }

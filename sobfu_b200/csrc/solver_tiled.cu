@@ -180,6 +180,9 @@ constexpr int LX = 16, RW = 32 / LX, NW = 12;     // 16 lanes x 4 voxels per row
 constexpr int TX = 4 * LX, TY = NW * RW;          // 64 x 24 outputs per plane
 constexpr int SX = TX + 8, SY = TY + 6;           // staged box 4|64|4 floats x 3|24|3 rows
 constexpr int NSTAGE = 6;                         // planes q-3..q live, two in flight
+#ifndef PB_SCATTER_Z
+#define PB_SCATTER_Z 1
+#endif
 #ifndef PB_PF_AHEAD
 #define PB_PF_AHEAD 4                             // 8 measured slower (0.1528 vs 0.1444 ms at 256^3)
 #endif
@@ -298,7 +301,15 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
     unsigned q = 0;                       // planes consumed so far
     MaxCand best{0u, 0u, 0u};
     const unsigned zoff = (unsigned)a.z0 * (unsigned)XY;
+#if PB_SCATTER_Z
+    // z taps in scatter form: acc[i] accumulates the z sum of the OUTPUT plane (newest plane - 6 + i); a plane that arrives adds its
+    // seven tap products to the seven sums in flight, in the reference's order (input planes ascending = k = -3 .. 3, each sum started
+    // from 0).  The taps are symmetric (S[i] == S[6 - i] bit for bit: tables and computed filters alike), so a value needs 4 products
+    // instead of 7 -- 36 FMUL less per thread and plane of ~870 instructions; the centre quad is re-read from the ring instead.
+    float4 acc[7][3];
+#else
     float4 win[7][3];                     // nabla_U of this thread's 4 voxels at planes c-3 .. c+3
+#endif
     int ack_seen = 0;                     // faces whose acknowledgement this CTA has already waited for
     St cs;
     for (cs.open(blockIdx.x, sc, d.Z); cs.valid(sc); cs.open(cs.item + (int)gridDim.x, sc, d.Z)) {
@@ -322,14 +333,35 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
             const unsigned pslot = psi0 + (q % NPSI) * PSI_STAGE_BYTES + psi_own;
             mbar_wait(full0 + 8 * slot, (q / NSTAGE) & 1u);
             ++q;
+            const unsigned sp = smem + slot * STAGE_BYTES + own_off;
+#if PB_SCATTER_Z
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float4 g = lds4(sp + c * COMP_BYTES);
+                float pr[4][4];           // pr[t][j] = S[t] * g_j, t = 0 .. 3 (S[6 - t] == S[t])
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) pr[t][j] = mul(a.S[t], c4(g, j));
+                }
+                // output plane p-3+i takes tap S[3 - k] with k = p - (p-3+i) = 3 - i, i.e. S[i]: acc[i] += S[i] * g (i = 6 starts a sum)
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    const int t = i < 3 ? i : 6 - i;          // acc[i] is the shifted acc[i + 1] of the previous step
+                    acc[i][c] = make_float4(add(acc[i + 1][c].x, pr[t][0]), add(acc[i + 1][c].y, pr[t][1]), add(acc[i + 1][c].z, pr[t][2]),
+                                            add(acc[i + 1][c].w, pr[t][3]));
+                }
+                acc[6][c] = make_float4(add(0.f, pr[0][0]), add(0.f, pr[0][1]), add(0.f, pr[0][2]), add(0.f, pr[0][3]));
+            }
+#else
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) win[k][c] = win[k + 1][c];
             }
-            const unsigned sp = smem + slot * STAGE_BYTES + own_off;
 #pragma unroll
             for (int c = 0; c < 3; ++c) win[6][c] = lds4(sp + c * COMP_BYTES);
+#endif
             if (zc >= cs.zb) {
                 const unsigned sc0 = smem + ((q - 4u) % NSTAGE) * STAGE_BYTES + own_off;   // stage of the centre plane
                 // psi of the centre plane arrived with this step's nabla_U plane (a plain LDG here exposed its latency: the
@@ -341,19 +373,29 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const unsigned s0 = sc0 + c * COMP_BYTES;
+#if PB_SCATTER_Z
+                    const float4 L = lds4(s0 - 16), R = lds4(s0 + 16), C = lds4(s0);
+                    float fz[4] = {acc[0][c].x, acc[0][c].y, acc[0][c].z, acc[0][c].w};     // complete with this plane
+#else
                     const float4 L = lds4(s0 - 16), R = lds4(s0 + 16), C = win[3][c];
+                    float fz[4] = {0.f, 0.f, 0.f, 0.f};
+#endif
                     const float v[12] = {L.x, L.y, L.z, L.w, C.x, C.y, C.z, C.w, R.x, R.y, R.z, R.w};
-                    float fx[4] = {0.f, 0.f, 0.f, 0.f}, fy[4] = {0.f, 0.f, 0.f, 0.f}, fz[4] = {0.f, 0.f, 0.f, 0.f};
+                    float fx[4] = {0.f, 0.f, 0.f, 0.f}, fy[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int k = -3; k <= 3; ++k) {
                         const float s = a.S[3 - k];
                         const float4 yk = (k == 0) ? C : lds4(s0 + k * (SX * 4));
+#if !PB_SCATTER_Z
                         const float4 zk = win[3 + k][c];
+#endif
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             fx[j] = add(fx[j], mul(s, v[4 + j + k]));
                             fy[j] = add(fy[j], mul(s, c4(yk, j)));
+#if !PB_SCATTER_Z
                             fz[j] = add(fz[j], mul(s, c4(zk, j)));
+#endif
                         }
                     }
 #pragma unroll
