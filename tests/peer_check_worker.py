@@ -1,6 +1,6 @@
 """torchrun worker (N >= 2 GPUs): (1) slab solve in peer mode == single-GPU solve, bit for bit, on a small volume (exercises
 ranks with TWO neighbours when N >= 3); (2) it/s of a 256^3 estimate_psi (200 iterations) in peer mode and over NCCL in the
-same process.  Usage: python -m torch.distributed.run --nproc-per-node N ... tests/peer_check_worker.py [dim] [iters]"""
+same process.  Usage: python -m torch.distributed.run --nproc-per-node N ... tests/peer_check_worker.py [dim] [iters] [Z]"""
 import json
 import os
 import sys
@@ -41,7 +41,7 @@ def main():
     if rank == 0:
         print("peer slab == single GPU, bit for bit:", dims, "ranks", world, flush=True)
     # (2) timing: peer, then NCCL
-    dims = (dim, dim, dim)
+    dims = (dim, dim, int(sys.argv[3]) if len(sys.argv) > 3 else dim)     # optional third argument: Z (thin slabs on few GPUs)
     pg, pn, vs, trunc, eta = sphere_pair(dims, r=0.07)
     p = sf.Params(volume_dims=dims, volume_size=tuple(float(vs[i]) * dims[i] for i in range(3)), max_iter=iters, max_update_norm=1e-10, s=7,
                   lambda_=0.1, alpha=0.001, w_reg=0.6, verbosity=0, tsdf_max_weight=64.0, tsdf_trunc_dist=float(trunc), eta=float(eta))
