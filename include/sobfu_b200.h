@@ -192,6 +192,8 @@ int sobfu_b200_solver_attach_comm(sobfu_b200_solver *s, const void *id128_host, 
  * device and the step is repeated on the all-gathered volumes, so results do not depend on the bound.  Returns how many solves of
  * this handle took that fallback. */
 int sobfu_b200_solver_tail_fallbacks(sobfu_b200_solver *s);
+/* host-only: the planes [win_z0, win_z0 + win_nz) that window covers for `rank` of `nranks` (halo < 0: the default of 16 planes) */
+int sobfu_b200_tail_window(int Z, int rank, int nranks, int halo, int *win_z0, int *win_nz, int *halo_used);
 
 /* Peer mode (ranks on one NVLink / NVSwitch domain, e.g. the 8 GPUs of a B200 node): the per-iteration psi halo exchange
  * and the convergence test leave NCCL.  Pass B on the slab faces stores its new psi planes straight into the neighbours'

@@ -84,6 +84,7 @@ SIGNATURES = {
     "sobfu_b200_solver_peer_export": [_P, _P],
     "sobfu_b200_solver_peer_attach": [_P, _P],
     "sobfu_b200_slab_range": [_I, _I, _I, _IP, _IP],
+    "sobfu_b200_tail_window": [_I, _I, _I, _I, _IP, _IP, _IP],
 }
 OTHER_SYMBOLS = ["sobfu_b200_last_error", "sobfu_b200_version", "sobfu_b200_solver_workspace_bytes", "sobfu_b200_io_last_error",
                  "sobfu_b200_solver_tail_fallbacks"]

@@ -395,14 +395,10 @@ static int alloc_workspace(sobfu_b200_solver *s, int z0, int nzl) {
     if (s->nranks > 1) {
         // window of the tail: up to 16 planes of either neighbour (SOBFU_B200_TAIL_HALO overrides; 0 = always all-gather), never
         // more than a neighbour owns
-        int H = 16;
-        if (const char *e = getenv("SOBFU_B200_TAIL_HALO")) H = atoi(e);
-        if (H > nzl) H = nzl;
-        if (H < 0) H = 0;
-        s->tail_halo = H;
-        s->win_z0 = z0 - H > 0 ? z0 - H : 0;
-        const int zend = z0 + nzl + H < s->dg.Z ? z0 + nzl + H : s->dg.Z;
-        s->win_nz = zend - s->win_z0;
+        int H = -1;
+        if (const char *e = getenv("SOBFU_B200_TAIL_HALO")) H = atoi(e) < 0 ? 0 : atoi(e);
+        if (int wrc = sobfu_b200_tail_window(s->dg.Z, s->rank, s->nranks, H, &s->win_z0, &s->win_nz, &s->tail_halo)) return wrc;
+        H = s->tail_halo;
         if (H > 0) {
             CKA(cudaMalloc(&s->psi_win, (size_t)s->win_nz * s->XY * sizeof(float4)));
             CKA(cudaMalloc(&s->phig_win, (size_t)s->win_nz * s->XY * sizeof(float2)));
@@ -558,6 +554,21 @@ extern "C" int sobfu_b200_slab_range(int Z, int rank, int nranks, int *z0, int *
         return fail(SOBFU_B200_EINVAL, "slab partition needs Z %% nranks == 0 and at least 4 planes per rank (Z=%d, nranks=%d)", Z, nranks);
     if (z0) *z0 = rank * (Z / nranks);
     if (nz) *nz = Z / nranks;
+    return 0;
+}
+// window of psi / phi_global the per-frame tail of rank `rank` reads: its planes + `halo` planes of either neighbour (never more
+// than a neighbour owns, clipped at the volume faces); halo < 0: the default of 16
+extern "C" int sobfu_b200_tail_window(int Z, int rank, int nranks, int halo, int *win_z0, int *win_nz, int *halo_used) {
+    int z0 = 0, nz = 0;
+    const int rc = sobfu_b200_slab_range(Z, rank, nranks, &z0, &nz);
+    if (rc) return rc;
+    int H = halo < 0 ? 16 : halo;
+    if (H > nz) H = nz;
+    if (nranks == 1) H = 0;
+    const int lo = z0 - H > 0 ? z0 - H : 0, hi = z0 + nz + H < Z ? z0 + nz + H : Z;
+    if (win_z0) *win_z0 = lo;
+    if (win_nz) *win_nz = hi - lo;
+    if (halo_used) *halo_used = H;
     return 0;
 }
 extern "C" int sobfu_b200_solver_attach_comm(sobfu_b200_solver *s, const void *id128, int rank, int nranks) {

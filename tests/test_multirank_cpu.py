@@ -99,3 +99,26 @@ def test_slab_range_rejects_bad_partitions(built):
     for Z, n in ((250, 8), (16, 8), (64, 0)):
         with pytest.raises(sf.Sobfu200Error):
             sf.slab_range(Z, 0, n)
+
+
+def test_tail_window_partitions(built):
+    """the per-frame tail reads the rank's planes + min(16, planes per rank) planes of either neighbour, clipped at the volume faces:
+    the windows cover the volume, contain the rank's slab, and neighbouring windows overlap by twice the halo"""
+    import ctypes as C
+    import sobfu_b200 as sf
+    from sobfu_b200 import _capi
+    L = _capi.lib()
+    for Z, n, halo in ((256, 8, -1), (256, 2, -1), (512, 8, -1), (64, 4, -1), (64, 8, -1), (256, 4, 5), (256, 1, -1), (64, 4, 0)):
+        wins = []
+        for r in range(n):
+            z0, nz, h = C.c_int(), C.c_int(), C.c_int()
+            assert L.sobfu_b200_tail_window(Z, r, n, halo, C.byref(z0), C.byref(nz), C.byref(h)) == 0
+            s0, sn = sf.slab_range(Z, r, n)
+            want_h = 0 if n == 1 else min(16 if halo < 0 else halo, sn)
+            assert h.value == want_h
+            assert z0.value == max(0, s0 - want_h) and z0.value + nz.value == min(Z, s0 + sn + want_h)
+            wins.append((z0.value, z0.value + nz.value))
+        assert wins[0][0] == 0 and wins[-1][1] == Z
+        for a, b in zip(wins, wins[1:]):
+            assert a[1] - b[0] == 2 * (0 if n == 1 else min(16 if halo < 0 else halo, Z // n))
+    assert L.sobfu_b200_tail_window(250, 0, 8, -1, None, None, None) != 0          # not a valid partition
