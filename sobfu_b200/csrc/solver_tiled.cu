@@ -781,9 +781,12 @@ constexpr int TX = pa::TX, TY = pa::TY, SX = pa::SX, SY = pa::SY;     // same ti
 // ring: when thread 0 refills after the barrier of step p, planes p-2, p-1 and p are still needed (they are p-3 .. p-1 of the
 // next step) and AHEAD planes are in flight or about to be: the load goes into the stage of plane p-3, last read in this step
 constexpr int AHEAD = PA2_AHEAD, NSTAGE = 3 + AHEAD;
+#ifndef PA2_PF_AHEAD
+#define PA2_PF_AHEAD 4       // 2, 6 and 8 measured the same (0.1695 - 0.1712 ms)
+#endif
 constexpr int NWB = 2;       // warped planes p-1 (written in this step) and p-2 (its x / y neighbours read in this step); the block
                              // barrier at the end of the step separates the reads of a buffer from its next writes
-constexpr int PF_AHEAD = 4;
+constexpr int PF_AHEAD = PA2_PF_AHEAD;       // L2 prefetch distance ahead of the shared-memory fill
 constexpr int ARR_BYTES = pa::ARR_BYTES, STAGE_BYTES = 3 * ARR_BYTES;
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + NWB * ARR_BYTES + 128;
 constexpr unsigned TX_BYTES = pa::TX_BYTES;
@@ -856,7 +859,9 @@ __global__ void __launch_bounds__(NTHREADS, PA2_CTAS)
 
     const int lx = lane % LX, ty = warp * RW + lane / LX;
     const unsigned own_off = (unsigned)(((ty + 1) * SX + 4 * lx + 4) * 4);
-    int hx = -1, hy = -1;         // cross-halo cell served by this thread (threads 0 .. NHALO-1), as in pa
+    int hx = -1, hy = -1;         // cross-halo cell served by this thread (threads 0 .. NHALO-1), as in pa.  (Spreading the cells evenly
+                                  // over the four warps -- 24 lanes each -- measured slower: 0.1729 vs 0.1697 ms; all four warps then run
+                                  // the halo path.)
     if (tid < TX) { hx = 4 + tid; hy = 0; }
     else if (tid < 2 * TX) { hx = 4 + tid - TX; hy = TY + 1; }
     else if (tid < 2 * TX + TY) { hx = 3; hy = 1 + tid - 2 * TX; }
