@@ -1307,9 +1307,10 @@ extern "C" int sobfu_b200_update_psi(void *psi, const void *g, void *upd, float 
     SYNC_RET();
 }
 
-// 16 bytes of device scratch for the scalar reductions, one per (host thread, device): the buffer handed out always lives on
-// the device that is current at the call
-static int reduce_partials(float **pbuf) {      // 65536 floats: block results of the reference-order energy reductions
+// device scratch of the scalar reductions, one set per (host thread, device): the buffers handed out always live on the device
+// that is current at the call.  reduce_partials: 65536 floats, the block results of the reference-order energy reductions;
+// reduce_scalar: 16 bytes for the result
+static int reduce_partials(float **pbuf) {
     static thread_local float *buf[64] = {};
     int dev = 0;
     CK(cudaGetDevice(&dev));
