@@ -240,6 +240,7 @@ def measure_solver(args, rank, world, torch, dist, dim, iters, steps, warmup):
                      "traffic": None, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"},
     }
     if world > 1:
+        out["roofline"]["traffic_source"] = "not measured at N > 1 (ncu profiles one process); the N = 1 line of the same build carries it"
         peer = bool(getattr(fusion.solver, "peer", False))
         out["config"]["multi_gpu"] = ("z-slab of %d planes per GPU; nabla_U on the 3 halo planes is recomputed locally, so an iteration needs "
                                       "one psi halo exchange (4 planes) + one scalar MAX; " % (dim // world)) + (
