@@ -660,7 +660,7 @@ def main():
     ap.add_argument("--workload", default="solver", choices=["solver", "pipeline"],
                     help="solver: BASELINE.json configs[2] (default, the headline metric); pipeline: configs[4], the per-frame pipeline incl. marching cubes")
     ap.add_argument("--frames", type=int, default=50, help="pipeline workload: length of the synthetic sequence")
-    ap.add_argument("--variant", type=int, default=0, help="kernel variant of the solver (0 default; 1 generic; 2 tiled; 3 experimental)")
+    ap.add_argument("--variant", type=int, default=0, help="kernel variant of the solver (0 default; 1 generic; 2 tiled; 4 tiled with the round-1 pass A)")
     ap.add_argument("--no-parity", action="store_true", help="skip the post-timing parity check (reference CUDA at N=1, single-GPU solve at N>1)")
     ap.add_argument("--no-traffic", action="store_true", help="skip the ncu child process that measures DRAM bytes per launch (N=1)")
     ap.add_argument("--extra-dim", type=int, default=None, help="also measure this volume size and report it under extra_<dim> (default: 512 when --gpus 8)")
