@@ -169,3 +169,29 @@ def test_primitive_signed_distance_fields():
         vol = orc.tsdf_init_shape(dims, vs, f32(trunc), shape, prm)
         assert (vol[..., 1] == 1).all(), shape
         assert np.abs(vol[..., 0] - clamp(sdf)).max() < 2e-5, shape
+
+
+@pytest.mark.parametrize("s", [3, 7, 9, 11])
+def test_filter_of_any_odd_length_against_a_numpy_restatement(s):
+    """orc_sobolev_filter_r (2 * R + 1 taps; the reference compiles R = 3 only, solver.cu:211) against an independent numpy float32
+    restatement of the same three sweeps: taps S[R - j] for j = -R..R accumulated from 0 with un-fused multiply and add, clamp to edge,
+    (x + y) + z.  For s = 7 this is the filter the golden vectors pin against the reference CUDA."""
+    dims = (13, 11, 9)
+    src = random_field(dims, seed=40 + s)
+    src[np.abs(src) < 1e-30] = 0                      # nothing denormal: numpy does not flush to zero
+    taps = orc.sobolev_taps(s, 0.1)
+    R = s // 2
+    X, Y, Z = dims
+    want = np.zeros_like(src)
+    sums = []
+    for axis, n in ((2, X), (1, Y), (0, Z)):          # array axes of [Z, Y, X, C]: x is axis 2
+        acc = np.zeros(src.shape[:3] + (3,), dtype=f32)
+        idx = np.arange(n)
+        for j in range(-R, R + 1):
+            sel = np.clip(idx + j, 0, n - 1)
+            moved = np.take(src[..., :3], sel, axis=axis)
+            acc = (acc + (moved * f32(taps[R - j])).astype(f32)).astype(f32)
+        sums.append(acc)
+    want[..., :3] = ((sums[0] + sums[1]).astype(f32) + sums[2]).astype(f32)
+    got = orc.sobolev_filter(src, taps)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
